@@ -1,0 +1,197 @@
+/*
+ * ttneval.h — C ABI of libttneval.so: batched evaluation of a quantics tree
+ * tensor-network function on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE path of ITensorNumericalAnalysis.jl
+ * (reference at /root/reference, v0.2.1): the caller loop around
+ *     evaluate(fitn::ITensorNetworkFunction, xs::Vector, dims)   src/itensornetworkfunction.jl:96-106
+ * i.e.  calculate_ind_values  (src/IndexMaps/realindexmap.jl:67-76,
+ *                              src/IndexMaps/complexindexmap.jl:116-132,
+ *                              greedy loop src/IndexMaps/abstractindexmap.jl:121-138)
+ *    -> project               (src/itensornetworkfunction.jl:84-94)
+ *    -> scalar(tn; alg="bp")  (src/itensornetworkfunction.jl:105; ITensorNetworks.jl, un-vendored)
+ * executed for MANY points per call.  The reference has no FFI for this path
+ * (it is 100% Julia); the Julia method that binds these symbols with `ccall`
+ * is shown in INTEGRATION.md and shipped in
+ * itensornumericalanalysis.jl_b200/julia/TTNEvalB200.jl.
+ *
+ * Conventions
+ *  - plain C, no C++ types, no torch types; all pointers are caller-owned for
+ *    the duration of the (synchronous) call; the plan copies everything it
+ *    needs at ttn_plan_create time.
+ *  - every function returning int returns 0 (TTN_OK) on success, else a
+ *    TTN_ERR_* code; the message is available from ttn_last_error() (thread
+ *    local).  No C++ exception crosses this boundary.
+ *  - there is NO CPU fallback behind this ABI: if no CUDA device is usable,
+ *    calls fail with TTN_ERR_CUDA.
+ */
+#ifndef TTNEVAL_H
+#define TTNEVAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTN_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------ */
+enum {
+  TTN_OK = 0,
+  TTN_ERR_INVALID = 1, /* malformed description / arguments */
+  TTN_ERR_DOMAIN = 2,  /* a coordinate is negative or NaN: the reference's greedy loop
+                          (abstractindexmap.jl:121-138) never terminates on such input; we
+                          return an error instead (documented deviation) */
+  TTN_ERR_CUDA = 3,    /* CUDA runtime failure, or no device */
+  TTN_ERR_UNSUPPORTED = 4,
+  TTN_ERR_NOMEM = 5
+};
+
+/* ---- coordinate layouts ------------------------------------------------ */
+enum {
+  TTN_LAYOUT_AOS = 0, /* coords[p * n_coords + c]  (Julia D x Npts Matrix, column major;
+                         Vector{<:Vector} after reduce(hcat, ...)) */
+  TTN_LAYOUT_SOA = 1  /* coords[c * npts + p] */
+};
+
+/* ---- memory spaces for coords / out ------------------------------------ */
+enum {
+  TTN_MEM_HOST = 0,  /* host pointers; H2D / D2H copies happen inside the call */
+  TTN_MEM_DEVICE = 1 /* device pointers on the plan's device; no copies */
+};
+
+/* ---- kernel selection --------------------------------------------------- */
+enum {
+  TTN_KERNEL_AUTO = 0,
+  TTN_KERNEL_GENERIC = 1, /* any tree, any dims: thread-per-point, messages in HBM scratch */
+  TTN_KERNEL_CHAIN = 2,   /* MPS-shaped networks: per-point state in registers, site matrices
+                             streamed through a shared-memory ring by bulk async copies (TMA) */
+  TTN_KERNEL_DMMA = 3     /* large bond dimension: points grouped by digit, FP64 DMMA tiles */
+};
+
+/*
+ * Flat description of one ITensorNetworkFunction on a TREE, rooted at `root`.
+ *
+ * Vertices are numbered 0..n_vertices-1.  `parent[v]` is the vertex towards the
+ * root (-1 for the root).  The children of v are the vertices u with
+ * parent[u]==v, taken in ascending u.  `link_dim[v]` is the dimension of the
+ * link index between v and parent[v] (must be 1 for the root).
+ *
+ * Site indices (the "Digit" indices of src/digit_inds.jl:72-115) are listed in
+ * CSR form per vertex: vertex v owns entries site_ptr[v] .. site_ptr[v+1]-1.
+ * A vertex may own zero, one or several site indices
+ * (src/digit_inds.jl:78-83, test/test_complexitensorfunction.jl:183-191).
+ * For site index s:
+ *   site_dim[s]    its dimension b (the base; 2 for binary digits)
+ *   site_coord[s]  which REAL coordinate slot drives it, 0..n_coords-1.  For a
+ *                  RealIndexMap slot i is xs[i]; for a ComplexIndexMap slot 2i is
+ *                  real(xs[i]) and slot 2i+1 is imag(xs[i])
+ *                  (complexindexmap.jl:116-132).
+ *   site_digit[s]  its digit number (1 = most significant; realindexmap.jl:48-58).
+ *                  Within one coordinate slot the greedy loop visits site
+ *                  indices in ascending digit number (realindexmap.jl:72).
+ *   thr[thr_ptr[s] + v], v = 0..b-1 :  abs(index_value_to_scalar(imap, ind, v))
+ *                  (realindexmap.jl:13-15, complexindexmap.jl:25-32), computed
+ *                  by the caller with the reference's own function so that the
+ *                  thresholds are bit-identical for every base.
+ *
+ * Tensor of vertex v: element type double (is_complex==0) or interleaved
+ * (re,im) double pairs (is_complex==1), starting at element offset
+ * tensor_ptr[v] of `tensors`, C order (last axis fastest), axes
+ *   [site_0] ... [site_{m-1}] [child_0] ... [child_{k-1}] [parent]
+ * so that one setting of the site indices selects one contiguous slice
+ * (what `project` does with onehot, src/itensornetworkfunction.jl:84-94).
+ */
+typedef struct ttn_desc {
+  int32_t abi_version; /* TTN_ABI_VERSION */
+  int32_t n_vertices;
+  int32_t n_coords;
+  int32_t is_complex;
+  int32_t root;
+  int32_t n_sites; /* == site_ptr[n_vertices] */
+  const int32_t* parent;     /* [n_vertices] */
+  const int32_t* link_dim;   /* [n_vertices] */
+  const int32_t* site_ptr;   /* [n_vertices + 1] */
+  const int32_t* site_dim;   /* [n_sites] */
+  const int32_t* site_coord; /* [n_sites] */
+  const int32_t* site_digit; /* [n_sites] */
+  const int32_t* thr_ptr;    /* [n_sites + 1] */
+  const double* thr;         /* [thr_ptr[n_sites]] */
+  const int64_t* tensor_ptr; /* [n_vertices + 1], in elements (complex counts as one) */
+  const void* tensors;
+} ttn_desc;
+
+typedef struct ttn_opts {
+  int32_t coords_mem;   /* TTN_MEM_* */
+  int32_t out_mem;      /* TTN_MEM_* */
+  int32_t kernel;       /* TTN_KERNEL_* (AUTO = planner's choice) */
+  int32_t reduce_sum;   /* 0: write one value per point to out; 1: also/only accumulate the sum
+                           of all values into sum_out (out may then be NULL) */
+  int64_t chunk_points; /* 0 = auto; host-memory calls are pipelined in chunks of this many points */
+  /* outputs */
+  double sum_out[2];    /* (re, im) of the sum when reduce_sum != 0 */
+  float kernel_ms;      /* device time of the contraction kernel launches of this call, measured
+                           with CUDA events on the launching stream */
+  float total_ms;       /* device time of the whole call incl. copies (events) */
+  int32_t kernel_used;  /* TTN_KERNEL_* actually run */
+  int32_t n_launches;   /* kernels launched by this call */
+} ttn_opts;
+
+/* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:
+ * coordinate slot c takes the values i * step[c], i = 0..count[c]-1, and the evaluation set is
+ * the Cartesian product of all slots (slot 0 slowest).  Points are generated on the device; no
+ * coordinate bytes are read. */
+typedef struct ttn_grid {
+  int32_t n_coords;
+  const double* step;   /* [n_coords] a / b^L */
+  const int64_t* count; /* [n_coords] number of kept points (those < 1) */
+  int64_t first;        /* linear index of the first grid point of this call (sharding) */
+  int64_t npts;         /* how many consecutive grid points to evaluate */
+} ttn_grid;
+
+typedef struct ttn_info {
+  int32_t n_vertices, n_coords, is_complex, n_sites;
+  int32_t max_link_dim;
+  int32_t is_chain;          /* every vertex has <= 1 child once rooted */
+  int32_t auto_kernel;       /* TTN_KERNEL_* chosen by the planner */
+  int32_t device;
+  double flops_per_point;    /* SURVEY §8(d) flop rule: 2 (real) / 8 (complex) * sum of MACs */
+  double bytes_per_point;    /* 8 * n_coords read + 8/16 written */
+  int64_t tensor_bytes;
+} ttn_info;
+
+typedef struct ttn_plan ttn_plan; /* opaque; owns all device memory and streams */
+
+/* Build a plan on CUDA device `device` (>= 0).  Replaces the per-point `copy(fitn)` +
+ * dictionary construction of the reference (itensornetworkfunction.jl:85, realindexmap.jl:69). */
+int ttn_plan_create(const ttn_desc* desc, int32_t device, ttn_plan** out);
+void ttn_plan_destroy(ttn_plan* plan);
+int ttn_plan_info(const ttn_plan* plan, ttn_info* info);
+
+/* out[p] = f(point p).  `out` holds npts doubles (real network) or npts (re,im) pairs.
+ * Replaces the caller loop over evaluate(), e.g. examples/2d_laplace_solver.jl:49-53. */
+int ttn_evaluate(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coords,
+                 int32_t layout, void* out, ttn_opts* opts);
+
+/* Same on a generated grid (grid_points), optionally with the summed-grid quadrature
+ * (identity: sum over all b^L points == integrate(fitn; take_sum=true), src/integration.jl:6-17). */
+int ttn_evaluate_grid(ttn_plan* plan, const ttn_grid* grid, void* out_or_null, ttn_opts* opts);
+
+/* Digit decomposition only — batched calculate_ind_values (realindexmap.jl:67-76).
+ * digits_out[p * n_sites + s] (uint8) = value chosen for site index s of the description. */
+int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coords,
+               int32_t layout, uint8_t* digits_out, ttn_opts* opts);
+
+/* FP64 roofline denominators measured on the plan's device: a dependent-free DFMA loop
+ * (vector pipe) and an mma.sync m8n8k4 f64 loop (DMMA pipe); TFLOP/s. */
+int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);
+
+const char* ttn_last_error(void);
+int ttn_device_count(void);
+int ttn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTNEVAL_H */
