@@ -1,0 +1,138 @@
+// Internal structures of libttneval.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ttneval.h"
+
+namespace ttn {
+
+void set_error(const std::string& msg);
+#define TTN_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ttn::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+      return TTN_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+// ---- digit extraction tables (device) ------------------------------------------------
+// One entry per site index, grouped by coordinate slot and sorted by digit number ascending
+// (sort(indices; by=digit), src/IndexMaps/realindexmap.jl:72).
+struct DigitEntry {
+  int32_t site;    // site id in the description (for ttn_digits output)
+  int32_t base;    // dim(ind)
+  int32_t thr_off; // offset into thr[]: thr[thr_off + v] = abs(index_value_to_scalar(ind, v))
+  int32_t vertex;  // owner vertex
+  int32_t stride;  // stride of this digit inside the vertex's mixed-radix slice index
+  int32_t word;    // chain kernel: which 64-bit word of the packed slice stream
+  int32_t shift;   // chain kernel: bit offset inside that word
+  int32_t pad_;
+};
+
+struct DigitTable {
+  int32_t n_coords;
+  int32_t n_sites;
+  const int32_t* coord_ptr;  // [n_coords + 1] into entries
+  const DigitEntry* entries; // [n_sites]
+  const double* thr;
+};
+
+// Where coordinates come from: a caller array or the grid generator (grid_points,
+// src/IndexMaps/realindexmap.jl:78-86).
+#define TTN_MAX_COORDS 16
+struct CoordSource {
+  const double* coords; // device pointer, or nullptr in grid mode
+  int64_t npts;         // points in this launch
+  int32_t n_coords;
+  int32_t layout;       // TTN_LAYOUT_*
+  int32_t grid;         // 1: generate
+  int64_t first;        // grid: linear index of point 0 of this launch
+  double step[TTN_MAX_COORDS];
+  int64_t count[TTN_MAX_COORDS];
+};
+
+// ---- generic tree program (device) ---------------------------------------------------
+struct TreeDev {
+  int32_t n_vertices, root, is_complex;
+  const int32_t* post;      // post order
+  const int32_t* child_ptr; // CSR children
+  const int32_t* child;
+  const int32_t* link_dim;
+  const int64_t* slice_size; // elements per slice
+  const int64_t* tensor_off; // element offset of the vertex tensor
+  const int64_t* msg_off;    // per-point message offsets (elements)
+  const double* tensors;
+  int64_t msg_total;  // elements per point in the message area
+  int64_t max_inter;  // elements of the largest intermediate
+};
+
+// ---- chain (MPS) program --------------------------------------------------------------
+struct ChainDev {
+  int32_t n_steps;     // middle vertices streamed through the shared-memory ring
+  int32_t n_vertices;  // chain length (leaf .. root)
+  int32_t chi;         // padded bond dimension (template instance)
+  int32_t nsl;         // padded slices per vertex (template instance)
+  int32_t bits;        // bits per vertex in the packed slice stream
+  int32_t per_word;    // vertices per 64-bit word
+  int32_t n_words;
+  const double* leaf;  // [nsl][chi] (x2 if complex)
+  const double* root;  // [nsl][chi]
+  const double* steps; // [n_steps] stage images, see k_chain.cu for the layout
+  int64_t stage_bytes;
+};
+
+struct Stream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr;
+  double* d_coords = nullptr;
+  double* d_out = nullptr;
+  int64_t cap_points = 0;
+  double* d_work = nullptr; // generic-kernel workspace
+  size_t work_bytes = 0;
+  double* d_partial = nullptr; // per-CTA partial sums (reduce_sum)
+  size_t partial_cap = 0;
+};
+
+} // namespace ttn
+
+struct ttn_plan {
+  int device = 0;
+  int sm_count = 0;
+  ttn_info info{};
+  // host copies
+  std::vector<int32_t> parent, link_dim, post, child_ptr, child, chain_order;
+  std::vector<int64_t> slice_size, tensor_off, msg_off;
+  std::vector<int32_t> nslices;
+  bool is_chain = false;
+  // device memory
+  std::vector<void*> allocs;
+  ttn::DigitTable digits{};
+  ttn::TreeDev tree{};
+  ttn::ChainDev chain{};
+  bool chain_ok = false;
+  int* d_err = nullptr;    // domain-error flag
+  double* d_sum = nullptr; // (re, im)
+  ttn::Stream streams[3];
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  std::mutex mu;
+};
+
+namespace ttn {
+// kernel launchers (defined in the .cu files).  All return a TTN_* code.
+int launch_digits(ttn_plan* p, const CoordSource& src, uint8_t* d_digits, cudaStream_t s);
+int launch_generic(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
+                   double* d_partial, int* n_partial, cudaStream_t s);
+int launch_chain(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
+                 double* d_partial, int* n_partial, cudaStream_t s);
+int launch_sum_partials(ttn_plan* p, const double* d_partial, int n_partial, int nc,
+                        double* d_sum, cudaStream_t s);
+int build_chain(ttn_plan* p, const ttn_desc* d);
+bool chain_supported(int chi, int nsl, bool cplx);
+int measure_fp64_peak(int device, double* dfma, double* dmma);
+} // namespace ttn

@@ -61,16 +61,19 @@ class Plan:
         return o
 
     def evaluate_host(self, coords, layout=_capi.TTN_LAYOUT_AOS, kernel="auto", reduce_sum=False,
-                      want_values=True, chunk_points=0):
+                      want_values=True, chunk_points=0, out=None):
         """coords: float64 array, (npts, n_coords) for AOS or (n_coords, npts) for SOA."""
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         nc = self.packed.n_coords
         npts = coords.shape[0] if layout == _capi.TTN_LAYOUT_AOS else coords.shape[1]
         if coords.ndim != 2 or coords.size != npts * nc:
             raise ValueError(f"coords must hold {nc} coordinate slots per point")
-        out = None
-        if want_values:
-            out = np.empty(npts, dtype=np.complex128 if self.packed.is_complex else np.float64)
+        dt = np.complex128 if self.packed.is_complex else np.float64
+        if out is not None:  # caller-owned (e.g. pinned) result buffer
+            if out.dtype != dt or out.size != npts or not out.flags.c_contiguous:
+                raise ValueError("out must be a contiguous array of npts values of the network's eltype")
+        elif want_values:
+            out = np.empty(npts, dtype=dt)
         o = self._opts(kernel, reduce_sum, chunk_points=chunk_points)
         rc = _capi.lib().ttn_evaluate(
             self._h, coords.ctypes.data_as(C.c_void_p), npts, nc, layout,

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _have_gpu():
+    from itna_b200 import _capi
+    return _capi.lib().ttn_device_count() > 0  # raises if libttneval.so is missing
+
+
+def pytest_collection_modifyitems(config, items):
+    gpu_items = [i for i in items if "gpu" in i.keywords]
+    if not gpu_items:
+        return
+    if not _have_gpu():
+        skip = pytest.mark.skip(reason="no CUDA device on this host")
+        for i in gpu_items:
+            i.add_marker(skip)

@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): digits bit-exact; values within 1e-12 of the 80-bit oracle in
+the floored relative metric of SURVEY §8(d):  |v - ref| / max(|ref|, 1e-3 * rms(ref)).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import itna_b200 as t
+import oracle as orc
+from itna_b200 import _capi
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = cases.load_golden()
+
+
+def coords_of(packed, pts):
+    pts = np.asarray(pts)
+    if packed.complex_coords:
+        z = pts.astype(np.complex128)
+        c = np.empty((z.shape[0], 2 * z.shape[1]))
+        c[:, 0::2], c[:, 1::2] = z.real, z.imag
+        return c
+    return pts.astype(np.float64)
+
+
+def kernels_for(plan):
+    ks = ["generic"]
+    if plan.info()["auto_kernel"] == _capi.TTN_KERNEL_CHAIN:
+        ks.append("chain")
+    return ks
+
+
+ALL_CASES = [(c, False) for c in cases.real_cases()] + [(c, True) for c in cases.complex_cases()]
+
+
+@pytest.mark.parametrize("case,cplx", ALL_CASES, ids=lambda x: x[0] if isinstance(x, tuple) else "")
+def test_digits_bit_exact_and_values(case, cplx):
+    name, f, dims, L = case
+    rng = np.random.default_rng(11)
+    pts = cases.complex_points(L, len(dims), rng) if cplx else cases.edge_points(L, len(dims), rng)
+    plan = f.plan(dims)
+    coords = coords_of(plan.packed, pts)
+    # digits: identical integers
+    assert (plan.digits_host(coords) == orc.digits(plan.packed, coords)).all()
+    ref = orc.evaluate(plan.packed, coords, orc.ORACLE_LD)
+    for k in kernels_for(plan):
+        got, o = plan.evaluate_host(coords, kernel=k)
+        assert o.kernel_used == _capi.KERNEL_IDS[k] and o.n_launches >= 1
+        err = orc.error_metric(got, ref).max()
+        assert err < TOL, (name, k, err)
+        # SOA layout gives bitwise the same values
+        got2, _ = plan.evaluate_host(np.ascontiguousarray(coords.T), layout=_capi.TTN_LAYOUT_SOA, kernel=k)
+        assert (got2 == got).all()
+    # public API, batched and single-point forms
+    vals = t.evaluate(f, pts, dims)
+    assert orc.error_metric(vals, ref).max() < TOL
+    one = t.evaluate(f, list(pts[3]), dims)
+    assert abs(one - ref[3]) <= TOL * max(abs(ref[3]), 1e-3)
+
+
+def test_chain_cases_really_use_the_chain_kernel():
+    names = {c[0]: c for c in cases.real_cases() + cases.complex_cases()}
+    for n in ("mps2d_chi8", "comb2x6_chi16", "base3_mps", "sin_qtt20", "mps2d_chi32", "cplx_alt",
+              "cplx_2site", "cplx_default2d", "sum_chi3p2", "single_vertex", "two_vertices"):
+        _, f, dims, _ = names[n]
+        assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_CHAIN, n
+    for n in ("comb3x4_chi4", "bintree4_chi5", "cplx_comb3x3"):
+        _, f, dims, _ = names[n]
+        assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GENERIC, n
+
+
+@pytest.mark.parametrize("spec", GOLD["value_cases"], ids=lambda s: s["name"])
+def test_reference_known_answers_on_gpu(spec):
+    f, point, dims, want = cases.build_golden_case(spec)
+    got = complex(t.evaluate(f, point, dims))
+    assert abs(got - want) <= spec.get("tol", 1e-12) * max(1.0, abs(want)), (got, want)
+
+
+def test_delta_p_on_gpu():
+    """test/test_realitensorfunction.jl:210-258 through the batched path."""
+    L = 10
+    s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=2)
+    x0, y0, d = 0.625, 0.25, 2.0 ** -L
+    xs = [0.0, d, 0.25, 0.5, 0.625, 0.875, 1 - d]
+    psi = t.delta_p(s, [[x0, y0], [0.5]], [[1, 2], [2]])
+    pts = [[x0, y0]] + [[x, 0.5] for x in xs] + [[0, 0], [0, y0]]
+    assert t.evaluate(psi, pts, [1, 2]).tolist() == [1.0] * 8 + [0.0, 0.0]
+    # integer coordinates are legal (test/test_realitensorfunction.jl:242)
+    assert t.evaluate(psi, [0, 0], [1, 2]) == 0.0
+
+
+def test_domain_errors_and_saturation():
+    s = t.continuous_siteinds(t.named_grid((8, 1)))
+    f = t.rand_itn(s, link_space=3, rng=1)
+    ones = t.evaluate(f, [[1.0], [3.0], [1 - 2.0 ** -8]])
+    assert ones[0] == ones[1] == ones[2]          # x >= 1 saturates to all-ones digits
+    for bad in (-1e-9, np.nan, -np.inf):
+        with pytest.raises(_capi.TTNError) as e:
+            t.evaluate(f, [[0.5], [bad]])
+        assert e.value.code == _capi.TTN_ERR_DOMAIN
+    assert t.evaluate(f, [[-0.0]])[0] == t.evaluate(f, [[0.0]])[0]
+    with pytest.raises(ValueError):               # wrong number of coordinate slots (host check)
+        f.plan().evaluate_host(np.zeros((4, 2)))
+    o = f.plan()._opts("auto", False)             # ... and the same mistake straight at the C ABI
+    z = np.zeros((4, 2))
+    rc = _capi.lib().ttn_evaluate(f.plan()._h, z.ctypes.data_as(C.c_void_p), 4, 2, 0,
+                                  z.ctypes.data_as(C.c_void_p), C.byref(o))
+    assert rc == _capi.TTN_ERR_INVALID and b"n_coords" in _capi.lib().ttn_last_error()
+    assert t.evaluate(f, np.zeros((0, 1))).shape == (0,)   # empty batch
+
+
+def test_sum_reduction_and_chunking_are_deterministic():
+    g = t.named_comb_tree((2, 8))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 9)] for i in (1, 2)])
+    f = t.rand_itn(s, link_space=16, rng=4, normalise=True)
+    rng = np.random.default_rng(2)
+    pts = rng.random((200_003, 2))
+    plan = f.plan()
+    full, _ = plan.evaluate_host(pts)
+    for chunk in (1 << 14, 77_777):
+        v, o = plan.evaluate_host(pts, chunk_points=chunk, reduce_sum=True)
+        assert (v == full).all()                   # chunking never changes a value
+        s1 = o.sum_out[0]
+        _, o2 = plan.evaluate_host(pts, chunk_points=chunk, reduce_sum=True, want_values=False)
+        assert o2.sum_out[0] == s1                 # bitwise reproducible
+        assert abs(s1 - np.sum(full)) <= 1e-12 * np.sum(np.abs(full))
+    # permutation equivariance: a point's value does not depend on its neighbours in the batch
+    perm = rng.permutation(len(pts))
+    v2, _ = plan.evaluate_host(pts[perm])
+    assert (v2 == full[perm]).all()
+
+
+def test_grid_mode_matches_points_and_integrate_identity():
+    """grid_points(s, N, d) evaluated on the device (no coordinate bytes read) == explicit points;
+    the sum over all 2^L grid points == integrate(fitn; take_sum=true) (src/integration.jl:6-17),
+    i.e. the network contracted with all-ones vectors on every site index."""
+    L = 16
+    s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=2)
+    f = t.rand_itn(s, link_space=8, rng=5, normalise=True)
+    n = 2 ** (L // 2)
+    xs, ys = s.grid_points(n, 1), s.grid_points(n, 2)
+    assert len(xs) == n and len(ys) == n
+    plan = f.plan()
+    vals, o = plan.evaluate_grid([xs[1], ys[1]], [n, n], want_values=True, reduce_sum=True)
+    pts = np.array([[x, y] for x in xs for y in ys])
+    explicit, _ = plan.evaluate_host(pts)
+    assert (vals == explicit).all()
+    # integrate identity via the dense oracle: sum of all entries of the dense tensor
+    dense, _ = orc.dense_tensor(f)
+    assert abs(o.sum_out[0] - dense.sum()) <= 1e-11 * np.abs(dense).sum()
+    # sharded grid (what each rank of a multi-GPU run does) gives the same values
+    half = n * n // 2
+    a, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=0, npts=half, want_values=True)
+    b, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=half, npts=n * n - half, want_values=True)
+    assert (np.concatenate([a, b]) == vals).all()
+
+
+def test_device_pointer_path_with_torch():
+    import torch
+    g = t.named_grid((20, 1))
+    s = t.continuous_siteinds(g, map_dimension=2)
+    f = t.rand_itn(s, link_space=16, rng=6, normalise=True)
+    plan = f.plan()
+    x = torch.rand((100_000, 2), dtype=torch.float64, device="cuda:0")
+    out = torch.empty(100_000, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    o = plan.evaluate_device(x.data_ptr(), x.shape[0], out.data_ptr(), reduce_sum=True)
+    host, _ = plan.evaluate_host(x.cpu().numpy())
+    assert (out.cpu().numpy() == host).all()
+    assert o.kernel_ms > 0 and o.n_launches == 2
+    assert abs(o.sum_out[0] - host.sum()) <= 1e-12 * np.abs(host).sum()
+
+
+def test_linearity_at_scale():
+    """Size-independent property at 10^6 points on the BASELINE config-2 shape (2x30 bits,
+    chi=16): (f + g)(x) == f(x) + g(x) within 1e-12, with the sum network built by direct sum
+    (chi = 32, a different kernel instance)."""
+    g = t.named_comb_tree((2, 30))
+    dv = [[(i, j) for j in range(1, 31)] for i in (1, 2)]
+    s = t.continuous_siteinds(g, dv)
+    f1 = t.rand_itn(s, link_space=16, rng=7, normalise=True)
+    f2 = t.rand_itn(s, link_space=16, rng=8, normalise=True)
+    rng = np.random.default_rng(3)
+    pts = rng.random((1_000_000, 2))
+    a, b, c = t.evaluate(f1, pts), t.evaluate(f2, pts), t.evaluate(f1 + f2, pts)
+    assert orc.error_metric(c, a + b).max() < TOL
+    # audited sample against the 80-bit oracle
+    idx = rng.integers(0, len(pts), 20000)
+    ref = orc.evaluate(f1.plan().packed, pts[idx], orc.ORACLE_LD, nthreads=orc.max_threads())
+    assert orc.error_metric(a[idx], ref).max() < TOL
+
+
+def test_fp64_peak_measurement():
+    dfma, dmma = C.c_double(), C.c_double()
+    _capi.check(_capi.lib().ttn_measure_fp64_peak(0, C.byref(dfma), C.byref(dmma)))
+    print(f"measured FP64 peaks: DFMA {dfma.value:.1f} TFLOP/s, DMMA {dmma.value:.1f} TFLOP/s")
+    assert 5.0 < dfma.value < 100.0 and 1.0 < dmma.value < 200.0
