@@ -156,6 +156,8 @@ typedef struct ttn_info {
   int32_t is_chain;          /* every vertex has <= 1 child once rooted */
   int32_t auto_kernel;       /* TTN_KERNEL_* chosen by the planner */
   int32_t device;
+  int32_t kernels_available; /* bit k set: TTN_KERNEL_k can run this network */
+  int32_t reserved_;
   double flops_per_point;    /* SURVEY §8(d) flop rule: 2 (real) / 8 (complex) * sum of MACs */
   double bytes_per_point;    /* 8 * n_coords read + 8/16 written */
   int64_t tensor_bytes;

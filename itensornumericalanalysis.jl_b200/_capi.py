@@ -73,6 +73,8 @@ class ttn_info(C.Structure):
         ("is_chain", C.c_int32),
         ("auto_kernel", C.c_int32),
         ("device", C.c_int32),
+        ("kernels_available", C.c_int32),
+        ("reserved_", C.c_int32),
         ("flops_per_point", C.c_double),
         ("bytes_per_point", C.c_double),
         ("tensor_bytes", C.c_int64),

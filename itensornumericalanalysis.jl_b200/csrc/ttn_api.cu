@@ -175,6 +175,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   if ((rc = upload(p, tensors, &t.tensors))) return rc;
 
   if ((rc = build_chain(p, d))) return rc;
+  if ((rc = build_chain_mma(p, d))) return rc;
 
   ttn_info& I = p->info;
   I.n_vertices = n;
@@ -183,8 +184,16 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   I.n_sites = d->n_sites;
   I.max_link_dim = max_link;
   I.is_chain = p->is_chain;
-  I.auto_kernel = p->chain_ok ? TTN_KERNEL_CHAIN : TTN_KERNEL_GENERIC;
+  // planner: DMMA tiles once the (real-embedded) row is wide enough to fill them, the register
+  // kernel for narrow chains, the generic kernel for everything that is not a chain
+  const int width = (d->is_complex ? 2 : 1) * max_link;
+  if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
+  else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
+  else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
+  else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
+  I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
+                        (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
@@ -217,6 +226,7 @@ static int run_kernel(ttn_plan* p, int kernel, Stream& st, const CoordSource& sr
   switch (kernel) {
     case TTN_KERNEL_GENERIC: return launch_generic(p, st, src, d_out, d_partial, n_partial, st.s);
     case TTN_KERNEL_CHAIN: return launch_chain(p, st, src, d_out, d_partial, n_partial, st.s);
+    case TTN_KERNEL_DMMA: return launch_chain_mma(p, st, src, d_out, d_partial, n_partial, st.s);
     default: break;
   }
   return fail(TTN_ERR_UNSUPPORTED, "requested kernel is not available in this build");
@@ -254,6 +264,8 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
+  if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_DMMA: network is not a chain with chi <= 32 (real) / 16 (complex), <= 4 slices per vertex and <= 128 slice bits");
   const bool coords_host = !base.grid && opts->coords_mem == TTN_MEM_HOST;
   const bool out_host = out != nullptr && opts->out_mem == TTN_MEM_HOST;
   const bool do_sum = opts->reduce_sum != 0;

@@ -87,6 +87,19 @@ struct ChainDev {
   int64_t stage_bytes;
 };
 
+// chain networks on FP64 tensor cores (k_chain_mma.cu)
+struct ChainMmaDev {
+  int32_t n_vertices, n_steps, n_rounds;
+  int32_t spr;      // sites per round (one shared-memory round trip of the state per round)
+  int32_t nsl;      // padded slices per vertex
+  int32_t chi;      // real row width (2*chi for complex networks, embedded), padded: 8, 16 or 32
+  int32_t nout;     // 1 (real) or 2 (re, im)
+  int32_t bits, per_word, n_words;
+  const double* leaf;  // [nsl][chi]
+  const double* root;  // [nout][nsl][chi]
+  const double* frags; // [n_steps][nsl][chi*chi], B-fragment order
+};
+
 struct Stream {
   cudaStream_t s = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
@@ -116,6 +129,8 @@ struct ttn_plan {
   ttn::TreeDev tree{};
   ttn::ChainDev chain{};
   bool chain_ok = false;
+  ttn::ChainMmaDev cmma{};
+  bool cmma_ok = false;
   int* d_err = nullptr;    // domain-error flag
   double* d_sum = nullptr; // (re, im)
   ttn::Stream streams[3];
@@ -133,6 +148,9 @@ int launch_chain(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
 int launch_sum_partials(ttn_plan* p, const double* d_partial, int n_partial, int nc,
                         double* d_sum, cudaStream_t s);
 int build_chain(ttn_plan* p, const ttn_desc* d);
+int build_chain_mma(ttn_plan* p, const ttn_desc* d);
+int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
+                     double* d_partial, int* n_partial, cudaStream_t s);
 bool chain_supported(int chi, int nsl, bool cplx);
 int measure_fp64_peak(int device, double* dfma, double* dmma);
 } // namespace ttn

@@ -40,9 +40,13 @@ class Plan:
         _capi.check(L.ttn_plan_create(C.byref(packed.desc()), self.device, C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            _capi.lib().ttn_plan_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _capi is not None and _capi._lib is not None:
+            try:
+                _capi._lib.ttn_plan_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+            self._h = None
 
     __del__ = close
 

@@ -27,13 +27,28 @@ def run(name, f, ncol, kernel="auto", npts=npts):
 
 g = t.named_comb_tree((2, 30))
 s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
-run("cfg2 comb2x30 chi16", t.rand_itn(s, link_space=16, rng=0, normalise=True), 2)
+f2 = t.rand_itn(s, link_space=16, rng=0, normalise=True)
+run("cfg2 comb2x30 chi16", f2, 2, kernel="chain")
+for spr in (1, 2, 3, 4):
+    os.environ["TTN_MMA_SPR"] = str(spr)
+    f2._plans.clear()
+    run(f"cfg2 dmma spr={spr}", f2, 2, kernel="dmma")
+del os.environ["TTN_MMA_SPR"]
+s4 = t.continuous_siteinds(t.named_grid((28, 1)), map_dimension=2)
+f4 = t.rand_itn(s4, link_space=32, rng=0, normalise=True)
+for spr in (1, 2):
+    os.environ["TTN_MMA_SPR"] = str(spr)
+    f4._plans.clear()
+    run(f"cfg4 dmma spr={spr}", f4, 2, kernel="dmma", npts=npts // 2)
+del os.environ["TTN_MMA_SPR"]
 s = t.continuous_siteinds(t.named_grid((28, 1)), map_dimension=2)
-run("cfg4 mps28 chi32", t.rand_itn(s, link_space=32, rng=0, normalise=True), 2, npts=npts // 2)
+run("cfg4 mps28 chi32 chain", t.rand_itn(s, link_space=32, rng=0, normalise=True), 2, kernel="chain", npts=npts // 2)
 s = t.continuous_siteinds(t.named_grid((20, 1)))
 run("cfg1 sin qtt20 chi2 cplx", t.sin_itn(s, k=2.0), 1)
 s = t.continuous_siteinds(t.named_grid((40, 1)), map_dimension=2)
-run("mps40 chi8", t.rand_itn(s, link_space=8, rng=0, normalise=True), 2)
+f8 = t.rand_itn(s, link_space=8, rng=0, normalise=True)
+run("mps40 chi8 chain", f8, 2, kernel="chain")
+run("mps40 chi8 dmma", f8, 2, kernel="dmma")
 run("exp product state chi1", t.exp_itn(s, k=1.0, dim=1), 2)
 g = t.named_comb_tree((2, 30))
 s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])

@@ -27,7 +27,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_capi.ttn_desc) == 6 * 4 + 10 * 8
     assert C.sizeof(_capi.ttn_opts) == 4 * 4 + 8 + 16 + 4 + 4 + 4 + 4
     assert C.sizeof(_capi.ttn_grid) == 8 + 8 + 8 + 8 + 8
-    assert C.sizeof(_capi.ttn_info) == 8 * 4 + 8 + 8 + 8
+    assert C.sizeof(_capi.ttn_info) == 10 * 4 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback():
