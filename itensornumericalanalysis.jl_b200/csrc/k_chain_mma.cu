@@ -382,6 +382,418 @@ __global__ void __launch_bounds__(NTH * NH + 32 * NH, 1)
   }
 }
 
+// =====================================================================================
+// v3: warp-specialised version of the scheme above.  The MMA warps do nothing but
+// gather -> DMMA -> scatter; everything else runs concurrently on front-end warps:
+//   * digit warps   compute the packed slice streams of the NEXT tile (K1),
+//   * the list warp counting-sorts the points of the CURRENT tile by class, one round ahead
+//                   (double-buffered lists),
+//   * B fragments are prefetched by MMA thread 0 into the ring slot the end-of-round barrier has
+//     just freed (no producer warp, no "empty" barriers).
+// Handshakes are mbarriers: tile_ready/tile_free (slice streams), list_full/list_empty, ring full.
+constexpr int kFeMaxSites = 160;
+constexpr int kFeMaxThr = 640;
+
+__device__ __forceinline__ int greedy_digit_smem(double& x, const double* thr, int base) {
+  int v = base - 1;
+  double t = thr[v];
+  while (v > 0 && !(x >= t)) {
+    --v;
+    t = thr[v];
+  }
+  x = __dsub_rn(x, t);
+  return v;
+}
+
+template <int CHI, int P, int NMW, int GB>
+__global__ void __launch_bounds__(NMW * 32 + 128, 1)
+    chain_mma3_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
+                      double* __restrict__ partial, int do_sum, int n_stage, int resident,
+                      uint32_t stage_stride) {
+  constexpr int NTM = NMW * 32;    // MMA threads
+  constexpr int NDT = 96;          // digit threads (3 warps); the 4th front-end warp builds lists
+  constexpr int PPT = P / NTM;
+  constexpr int CPR = CHI / 2;
+  constexpr int LIST_CAP = P + 8 * kMaxClasses;
+  static_assert(P % NTM == 0 && P % 32 == 0 && P / 32 <= 32, "tile shape");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t ring_full[kMmaMaxStages];
+  __shared__ __align__(8) uint64_t list_full[2], list_empty[2], tile_ready[2], tile_free[2];
+  __shared__ double red[2][NMW];
+  __shared__ int meta[2][kMaxClasses + 2];
+  __shared__ DigitEntry s_ent[kFeMaxSites];
+  __shared__ double s_thr[kFeMaxThr];
+  __shared__ int s_cptr[TTN_MAX_COORDS + 1];
+
+  unsigned char* state_p = smem;                                                    // (P + 8) rows
+  ulonglong2* words = reinterpret_cast<ulonglong2*>(smem + (size_t)(P + 8) * CHI * 8); // [2][P]
+  uint16_t* lists = reinterpret_cast<uint16_t*>(words + 2 * P);                     // [2][LIST_CAP]
+  unsigned char* ring = reinterpret_cast<unsigned char*>(lists + 2 * LIST_CAP);
+  ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~(uintptr_t)127);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < n_stage; ++s) mbar_init(smem_u32(&ring_full[s]), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&list_full[b]), 1);
+      mbar_init(smem_u32(&list_empty[b]), NMW);
+      mbar_init(smem_u32(&tile_ready[b]), NDT / 32);
+      mbar_init(smem_u32(&tile_free[b]), NMW + 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < 8 * CHI; i += NTM + 128) reinterpret_cast<double*>(state_p + (size_t)P * CHI * 8)[i] = 0.0;
+  for (int i = tid; i < dg.n_sites; i += NTM + 128) s_ent[i] = dg.entries[i];
+  for (int i = tid; i <= dg.n_coords; i += NTM + 128) s_cptr[i] = dg.coord_ptr[i];
+  {
+    int nthr = 0; // thr[] length = max over entries of thr_off + base
+    for (int i = 0; i < dg.n_sites; ++i) nthr = max(nthr, dg.entries[i].thr_off + dg.entries[i].base);
+    for (int i = tid; i < nthr; i += NTM + 128) s_thr[i] = dg.thr[i];
+  }
+  __syncthreads();
+
+  const int64_t n_tiles = (src.npts + P - 1) / P;
+  const int n_rounds = ch.n_rounds, spr = ch.spr, nsl = ch.nsl, n_steps = ch.n_steps;
+  const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
+  const uint32_t ring_base = smem_u32(ring);
+  const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
+  const int bits = ch.bits, per_word = ch.per_word;
+  const int lane = tid & 31;
+  int64_t my_tiles = 0;
+  if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  // slice of chain position `pos` of a packed stream
+  auto slice_at = [&](const ulonglong2& w, int pos) -> int {
+    if (bits == 0) return 0;
+    const int wi = pos / per_word, sh = (pos - wi * per_word) * bits;
+    return (int)(((wi ? w.y : w.x) >> sh) & MASK);
+  };
+
+  if (tid >= NTM + 32) {
+    // ===== digit warps: K1 for the tiles of this CTA, one tile ahead of the MMA warps =====
+    const int dtid = tid - (NTM + 32);
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int b = (int)(i & 1);
+      mbar_wait(smem_u32(&tile_free[b]), (uint32_t)(((i >> 1) & 1) ^ 1));
+      for (int base = dtid; base < P; base += NDT * 4) {
+        double x[4];
+        uint64_t w0[4], w1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w0[q] = w1[q] = 0;
+        for (int c = 0; c < dg.n_coords; ++c) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int pt = base + q * NDT;
+            const int64_t p = tile * P + pt;
+            x[q] = 0.0;
+            if (pt < P && p < src.npts) {
+              x[q] = load_coord(src, p, c);
+              if (!coord_in_domain(x[q])) {
+                atomicOr(err, 1);
+                x[q] = 0.0;
+              }
+            }
+          }
+          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+            const DigitEntry e = s_ent[e_i];
+            const double* thr = s_thr + e.thr_off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int v = greedy_digit_smem(x[q], thr, e.base);
+              const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
+              w0[q] += (e.word == 0) ? bb : 0ull;
+              w1[q] += (e.word == 1) ? bb : 0ull;
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int pt = base + q * NDT;
+          if (pt < P) words[b * P + pt] = make_ulonglong2(w0[q], w1[q]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tile_ready[b]));
+    }
+    return;
+  }
+
+  if (tid >= NTM) {
+    // ===== list warp: counting sort by class, one round ahead (double-buffered lists) =====
+    int64_t q = 0; // global round counter of this CTA
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int b = (int)(i & 1);
+      mbar_wait(smem_u32(&tile_ready[b]), (uint32_t)((i >> 1) & 1));
+      const ulonglong2* wt = words + b * P;
+      for (int r = 0; r < n_rounds; ++r, ++q) {
+        const int lb = (int)(q & 1);
+        uint16_t* list = lists + lb * LIST_CAP;
+        const int sites = min(spr, n_steps - r * spr);
+        int ncls = 1;
+        for (int k = 0; k < sites; ++k) ncls *= nsl;
+        const int pos0 = 1 + r * spr;
+        mbar_wait(smem_u32(&list_empty[lb]), (uint32_t)(((q >> 1) & 1) ^ 1));
+        // (word, shift) of the round's sites in the packed stream: uniform, hoisted
+        int s_w[4] = {0, 0, 0, 0}, s_sh[4] = {0, 0, 0, 0}, s_mul[4] = {0, 0, 0, 0};
+        {
+          int mul = 1;
+          for (int sI = 0; sI < sites && sI < 4; ++sI) {
+            const int pos = pos0 + sI;
+            const int wi = bits ? pos / per_word : 0;
+            s_w[sI] = wi;
+            s_sh[sI] = bits ? (pos - wi * per_word) * bits : 0;
+            s_mul[sI] = mul;
+            mul *= nsl;
+          }
+        }
+        auto class_of = [&](const ulonglong2& w) -> int {
+          int cls = 0;
+#pragma unroll
+          for (int sI = 0; sI < 4; ++sI)
+            cls += (int)(((s_w[sI] ? w.y : w.x) >> s_sh[sI]) & MASK) * s_mul[sI]; // s_mul == 0 beyond `sites`
+          return cls;
+        };
+        if (ncls <= 4 && sites <= 4) {
+          // ---- bitmap rank: lane j keeps the membership mask of points 32j..32j+31 per class; all
+          // ballots are independent across j, so the loop pipelines instead of serialising
+          uint32_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0;
+          uint64_t cache = 0; // 2 bits per j
+#pragma unroll 8
+          for (int j = 0; j < P / 32; ++j) {
+            const int cls = class_of(wt[j * 32 + lane]);
+            cache |= (uint64_t)cls << (2 * j);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, cls == 0);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, cls == 1);
+            const uint32_t m2 = __ballot_sync(0xffffffffu, cls == 2);
+            const uint32_t m3 = __ballot_sync(0xffffffffu, cls == 3);
+            if (lane == j) {
+              mk0 = m0; mk1 = m1; mk2 = m2; mk3 = m3;
+            }
+          }
+          int i0 = __popc(mk0), i1 = __popc(mk1), i2 = __popc(mk2), i3 = __popc(mk3);
+          const int n0 = i0, n1 = i1, n2 = i2, n3 = i3;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int a0 = __shfl_up_sync(0xffffffffu, i0, o), a1 = __shfl_up_sync(0xffffffffu, i1, o);
+            const int a2 = __shfl_up_sync(0xffffffffu, i2, o), a3 = __shfl_up_sync(0xffffffffu, i3, o);
+            if (lane >= o) {
+              i0 += a0; i1 += a1; i2 += a2; i3 += a3;
+            }
+          }
+          const int t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+          const int t2 = __shfl_sync(0xffffffffu, i2, 31), t3 = __shfl_sync(0xffffffffu, i3, 31);
+          const int st0 = 0, st1 = st0 + ((t0 + 7) & ~7), st2 = st1 + ((t1 + 7) & ~7), st3 = st2 + ((t2 + 7) & ~7);
+          const int total = st3 + ((t3 + 7) & ~7);
+          if (lane <= kMaxClasses)
+            meta[lb][lane] = lane == 0 ? st0 : (lane == 1 ? st1 : (lane == 2 ? st2 : (lane == 3 ? st3 : total)));
+          if (lane < 8) { // class padding -> scratch row
+            if ((t0 & 7) && lane >= (t0 & 7)) list[st0 + (t0 & ~7) + lane] = (uint16_t)P;
+            if ((t1 & 7) && lane >= (t1 & 7)) list[st1 + (t1 & ~7) + lane] = (uint16_t)P;
+            if ((t2 & 7) && lane >= (t2 & 7)) list[st2 + (t2 & ~7) + lane] = (uint16_t)P;
+            if ((t3 & 7) && lane >= (t3 & 7)) list[st3 + (t3 & ~7) + lane] = (uint16_t)P;
+          }
+          // slot base of word j per class = class start + points of the class in earlier words
+          const int b0 = st0 + i0 - n0, b1 = st1 + i1 - n1, b2 = st2 + i2 - n2, b3 = st3 + i3 - n3;
+          const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 8
+          for (int j = 0; j < P / 32; ++j) {
+            const int cls = (int)((cache >> (2 * j)) & 3);
+            const int B0 = __shfl_sync(0xffffffffu, b0, j), B1 = __shfl_sync(0xffffffffu, b1, j);
+            const int B2 = __shfl_sync(0xffffffffu, b2, j), B3 = __shfl_sync(0xffffffffu, b3, j);
+            const uint32_t M0 = __shfl_sync(0xffffffffu, mk0, j), M1 = __shfl_sync(0xffffffffu, mk1, j);
+            const uint32_t M2 = __shfl_sync(0xffffffffu, mk2, j), M3 = __shfl_sync(0xffffffffu, mk3, j);
+            const int B = cls == 0 ? B0 : (cls == 1 ? B1 : (cls == 2 ? B2 : B3));
+            const uint32_t M = cls == 0 ? M0 : (cls == 1 ? M1 : (cls == 2 ? M2 : M3));
+            list[B + __popc(M & lt)] = (uint16_t)(j * 32 + lane);
+          }
+        } else {
+          // pass 1: classes (cached 4 bits each) and per-class counts (lane c counts class c)
+          uint64_t cache0 = 0, cache1 = 0;
+          int mycnt = 0;
+          for (int j = 0; j < P / 32; ++j) {
+            int cls = 0;
+            if (sites <= 4) {
+              cls = class_of(wt[j * 32 + lane]);
+            } else {
+              const ulonglong2 w = wt[j * 32 + lane];
+              int mul = 1;
+              for (int s = 0; s < sites; ++s) {
+                cls += slice_at(w, pos0 + s) * mul;
+                mul *= nsl;
+              }
+            }
+            if (j < 16) cache0 |= (uint64_t)cls << (4 * j);
+            else cache1 |= (uint64_t)cls << (4 * (j - 16));
+            for (int c = 0; c < ncls; ++c) {
+              const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
+              if (lane == c) mycnt += __popc(m);
+            }
+          }
+          // class start rows (each class padded to a multiple of 8 rows)
+          const int padded = (lane < ncls) ? ((mycnt + 7) & ~7) : 0;
+          int incl = padded;
+  #pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+          }
+          const int mystart = incl - padded;
+          if (lane <= kMaxClasses) meta[lb][lane] = mystart; // lanes >= ncls hold the total
+          if (lane < ncls)
+            for (int k = mycnt; k < padded; ++k) list[mystart + k] = (uint16_t)P; // padding -> scratch row
+          // pass 2: slots
+          int run = mystart;
+          for (int j = 0; j < P / 32; ++j) {
+            const int cls = (int)(((j < 16) ? (cache0 >> (4 * j)) : (cache1 >> (4 * (j - 16)))) & 15);
+            int slot = 0;
+            for (int c = 0; c < ncls; ++c) {
+              const uint32_t m = __ballot_sync(0xffffffffu, cls == c);
+              const int base = __shfl_sync(0xffffffffu, run, c);
+              if (cls == c) slot = base + __popc(m & ((1u << lane) - 1u));
+              if (lane == c) run += __popc(m);
+            }
+            list[slot] = (uint16_t)(j * 32 + lane);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&list_full[lb]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tile_free[b]));
+    }
+    return;
+  }
+
+  // ===== MMA warps =====
+  const int warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t state_base = smem_u32(state_p);
+  const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(ch.frags);
+  const int64_t total_q = my_tiles * n_rounds;
+  auto issue_round = [&](int64_t qq) { // thread 0 only: B fragments of global round qq -> its ring slot
+    const int r = (int)(qq % n_rounds);
+    const uint32_t s = resident ? (uint32_t)r : (uint32_t)(qq % n_stage);
+    const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+    mbar_expect_tx(smem_u32(&ring_full[s]), bytes);
+    bulk_g2s(ring_base + s * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes, smem_u32(&ring_full[s]));
+  };
+  if (tid == 0) {
+    const int64_t first = resident ? min((int64_t)n_rounds, total_q) : min((int64_t)n_stage, total_q);
+    for (int64_t qq = 0; qq < first; ++qq) issue_round(qq);
+  }
+  double sum_re = 0.0, sum_im = 0.0;
+  int64_t q = 0;
+  for (int64_t i = 0; i < my_tiles; ++i) {
+    const int64_t tile = blockIdx.x + i * gridDim.x;
+    const int b = (int)(i & 1);
+    const ulonglong2* wt = words + b * P;
+    mbar_wait(smem_u32(&tile_ready[b]), (uint32_t)((i >> 1) & 1));
+    // ---- leaf: row(point) = L[d_0]
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int row = k * NTM + tid;
+      const double* L = ch.leaf + (size_t)slice_at(wt[row], 0) * CHI;
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
+    }
+    named_bar_sync(1, NTM);
+    // ---- rounds
+    for (int r = 0; r < n_rounds; ++r, ++q) {
+      const int lb = (int)(q & 1);
+      const uint16_t* list = lists + lb * LIST_CAP;
+      const int sites = min(spr, n_steps - r * spr);
+      int ncls = 1;
+      for (int k = 0; k < sites; ++k) ncls *= nsl;
+      mbar_wait(smem_u32(&list_full[lb]), (uint32_t)((q >> 1) & 1));
+      const int mystart = meta[lb][min(lane, kMaxClasses)];
+      const int total_rows = __shfl_sync(0xffffffffu, mystart, ncls);
+      const uint32_t s_use = resident ? (uint32_t)r : (uint32_t)(q % n_stage);
+      mbar_wait(smem_u32(&ring_full[s_use]), resident ? 0u : (uint32_t)((q / n_stage) & 1));
+      const uint32_t stage_base = ring_base + s_use * stage_stride + (uint32_t)lane * 8u;
+
+      const int n_groups = total_rows >> 3;
+      const int gpw = (n_groups + NMW - 1) / NMW;
+      int gi = warp * gpw;
+      const int gend = min(n_groups, gi + gpw);
+      while (gi < gend) {
+        const int row0 = gi << 3;
+        const uint32_t m = __ballot_sync(0xffffffffu, lane < ncls && mystart <= row0);
+        const int c = 31 - __clz(m);
+        const int cend = __shfl_sync(0xffffffffu, mystart, c + 1) >> 3;
+        const int nbat = min(GB, min(gend, cend) - gi);
+        if (nbat >= 4 && GB >= 4) process_batch<CHI, (GB >= 4 ? 4 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
+        else if (nbat == 3 && GB >= 3) process_batch<CHI, (GB >= 3 ? 3 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
+        else if (nbat == 2 && GB >= 2) process_batch<CHI, (GB >= 2 ? 2 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
+        else process_batch<CHI, 1>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
+        gi += max(1, min(nbat, GB));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&list_empty[lb]));
+      named_bar_sync(1, NTM); // rows change hands between rounds; the ring slot is free again
+      if (tid == 0 && !resident && q + n_stage < total_q) issue_round(q + n_stage);
+    }
+    // ---- root: out = row . R[d_{n-1}]
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int row = k * NTM + tid;
+      const int64_t p = tile * P + row;
+      double o0 = 0.0, o1 = 0.0;
+      if (ch.n_vertices > 1) {
+        const double* R0 = ch.root + (size_t)slice_at(wt[row], ch.n_vertices - 1) * CHI;
+        const double* R1 = R0 + (size_t)nsl * CHI;
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+          o0 = fma(v.x, __ldg(R0 + 2 * j), o0);
+          o0 = fma(v.y, __ldg(R0 + 2 * j + 1), o0);
+          if (ch.nout == 2) {
+            o1 = fma(v.x, __ldg(R1 + 2 * j), o1);
+            o1 = fma(v.y, __ldg(R1 + 2 * j + 1), o1);
+          }
+        }
+      } else {
+        o0 = lds64(row_chunk<CHI>(state_base, row, 0));
+        if (ch.nout == 2) o1 = lds64(row_chunk<CHI>(state_base, row, CPR / 2));
+      }
+      if (p < src.npts) {
+        if (out) {
+          if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+          else out[p] = o0;
+        }
+        sum_re += o0;
+        sum_im += o1;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&tile_free[b]));
+  }
+
+  if (do_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
+      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
+    }
+    if (lane == 0) {
+      red[0][warp] = sum_re;
+      red[1][warp] = sum_im;
+    }
+    named_bar_sync(1, NTM);
+    if (tid == 0) {
+      double x = 0.0, y = 0.0;
+      for (int w = 0; w < NMW; ++w) {
+        x += red[0][w];
+        y += red[1][w];
+      }
+      partial[2 * blockIdx.x] = x;
+      partial[2 * blockIdx.x + 1] = y;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 
 static int mma_width(int w) {
@@ -573,6 +985,37 @@ static int launch_mma_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
   return TTN_OK;
 }
 
+template <int CHI, int P, int NMW, int GB>
+static int launch_mma3_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial,
+                            int* n_partial, cudaStream_t s) {
+  const ChainMmaDev& c = p->cmma;
+  constexpr int LIST_CAP = P + 8 * kMaxClasses;
+  const size_t fixed = (size_t)(P + 8) * CHI * 8 + (size_t)2 * P * 16 + (size_t)2 * LIST_CAP * 2 + 128;
+  const size_t smem_max = 227 * 1024 - 12 * 1024; // static shared: barriers, digit tables, meta
+  const size_t stage = (size_t)c.spr * c.nsl * CHI * CHI * 8;
+  if (fixed + stage > smem_max) {
+    set_error("chain DMMA kernel: one round of site matrices does not fit in shared memory");
+    return TTN_ERR_UNSUPPORTED;
+  }
+  int n_stage = (int)std::min<size_t>((smem_max - fixed) / stage, (size_t)kMmaMaxStages);
+  int resident = 0;
+  if (c.n_rounds <= n_stage) {
+    n_stage = std::max(c.n_rounds, 1);
+    resident = 1;
+  }
+  const size_t smem = fixed + (size_t)n_stage * stage;
+  auto kern = chain_mma3_kernel<CHI, P, NMW, GB>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  const int64_t n_tiles = (src.npts + P - 1) / P;
+  const int grid = (int)std::min<int64_t>(n_tiles, p->sm_count);
+  const int do_sum = d_partial != nullptr;
+  kern<<<grid, NMW * 32 + 128, smem, s>>>(c, p->digits, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
+                                          (uint32_t)stage);
+  TTN_CUDA(cudaGetLastError());
+  *n_partial = do_sum ? grid : 0;
+  return TTN_OK;
+}
+
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                      int* n_partial, cudaStream_t s) {
   (void)st;
@@ -583,15 +1026,22 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     return TTN_ERR_UNSUPPORTED;
   }
   static const int variant = getenv("TTN_MMA_VARIANT") ? atoi(getenv("TTN_MMA_VARIANT")) : 0;
+  // v3 (warp-specialised) needs the digit tables to fit its static shared-memory copies
+  bool v3_ok = p->digits.n_sites <= kFeMaxSites && p->info.n_sites <= kFeMaxSites && p->fe_thr_len <= kFeMaxThr;
+  if (variant >= 1) v3_ok = false;
+  if (v3_ok) {
+    switch (p->cmma.chi) {
+      case 16: return launch_mma3_inst<16, 1024, 8, 4>(p, src, d_out, d_partial, n_partial, s);
+      case 32: return launch_mma3_inst<32, 512, 8, 2>(p, src, d_out, d_partial, n_partial, s);
+    }
+  }
   switch (p->cmma.chi) {
     case 8: return launch_mma_inst<8, 1024, 128, 2, 4>(p, src, d_out, d_partial, n_partial, s);
     case 16:
-      if (variant == 1) return launch_mma_inst<16, 1024, 256, 1, 4>(p, src, d_out, d_partial, n_partial, s);
-      if (variant == 2) return launch_mma_inst<16, 512, 128, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+      if (variant == 2) return launch_mma_inst<16, 1024, 256, 1, 4>(p, src, d_out, d_partial, n_partial, s);
       return launch_mma_inst<16, 512, 128, 2, 4>(p, src, d_out, d_partial, n_partial, s);
     case 32:
-      if (variant == 1) return launch_mma_inst<32, 448, 224, 1, 4>(p, src, d_out, d_partial, n_partial, s);
-      return launch_mma_inst<32, 192, 96, 2, 4>(p, src, d_out, d_partial, n_partial, s);
+      return launch_mma_inst<32, 448, 224, 1, 4>(p, src, d_out, d_partial, n_partial, s);
   }
   set_error("DMMA chain kernel: unsupported width");
   return TTN_ERR_UNSUPPORTED;

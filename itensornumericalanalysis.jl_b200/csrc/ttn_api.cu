@@ -154,6 +154,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   const int NC = d->is_complex ? 2 : 1;
   std::vector<double> tensors(reinterpret_cast<const double*>(d->tensors),
                               reinterpret_cast<const double*>(d->tensors) + d->tensor_ptr[n] * NC);
+  p->fe_thr_len = d->thr_ptr[d->n_sites];
   p->digits.n_coords = d->n_coords;
   p->digits.n_sites = d->n_sites;
   if ((rc = upload(p, coord_ptr, &p->digits.coord_ptr))) return rc;
@@ -187,7 +188,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   // planner: DMMA tiles once the (real-embedded) row is wide enough to fill them, the register
   // kernel for narrow chains, the generic kernel for everything that is not a chain
   const int width = (d->is_complex ? 2 : 1) * max_link;
-  if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
+  if (p->cmma_ok && width >= 12) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else I.auto_kernel = TTN_KERNEL_GENERIC;
