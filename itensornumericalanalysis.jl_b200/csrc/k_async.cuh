@@ -57,6 +57,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // D(8x8) += A(8x4) * B(4x8).  Fragments (PTX ISA, m8n8k4 .f64): lane = 4*g + t;
 //   A[row g][col t], B[row t][col g], C/D[row g][cols 2t, 2t+1].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+#ifdef TTN_NO_DMMA   // experiment: measure everything but the tensor work
+  c0 = a; c1 = b; return;
+#endif
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));

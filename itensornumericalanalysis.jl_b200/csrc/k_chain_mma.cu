@@ -794,6 +794,472 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
   }
 }
 
+// =====================================================================================
+// v5: warp-autonomous version.  Every MMA warp owns PW = 128 points end to end: digits (K1), leaf
+// rows, a warp-local counting sort per round (ballots only, no CTA barrier), gather -> DMMA ->
+// scatter on its private state rows, root.  The warps of a CTA share nothing but the TMA-fed
+// B-fragment ring (full/empty mbarriers), so they drift apart freely: while one warp sorts or
+// gathers, the other warp on its SMSP keeps the DMMA pipe busy (one warp alone can saturate it:
+// scripts/microbench/dmma_issue.cu).  Price: classes are padded to 8 rows per warp, not per CTA.
+template <int CHI, int NBAT>
+__device__ __forceinline__ void site_mma(double (&dst)[NBAT][CHI / 4], const double (&srcA)[NBAT][CHI / 4],
+                                         uint32_t bb) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+  double bf[KB * NB];
+#pragma unroll
+  for (int j = 0; j < KB * NB; ++j) bf[j] = lds64(bb + (uint32_t)(j * 32) * 8u);
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+    for (int j = 0; j < KB; ++j) dst[b][j] = 0.0;
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+    for (int nbp = 0; nbp < NB; ++nbp)
+#pragma unroll
+      for (int b = 0; b < NBAT; ++b) dmma884(dst[b][2 * nbp], dst[b][2 * nbp + 1], srcA[b][kb], bf[kb * NB + nbp]);
+}
+
+// One batch: NBAT 8-row groups of one class.  The two register tiles ping-pong between A and D
+// roles from site to site (the D fragment of one site is the A fragment of the next), so there
+// are no register moves between sites.
+template <int CHI, int NBAT>
+__device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&rows)[4], int tq,
+                                               uint32_t stage_base, const int (&boff)[4], int sites) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+  double t0[NBAT][KB], t1[NBAT][KB];
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
+      t0[b][2 * nb] = v.x;
+      t0[b][2 * nb + 1] = v.y;
+    }
+  }
+  int s = 0;
+  for (; s + 1 < sites; s += 2) {
+    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
+    site_mma<CHI, NBAT>(t0, t1, stage_base + (uint32_t)boff[s + 1]);
+  }
+  if (s < sites) {
+    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
+#pragma unroll
+    for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t1[b][2 * nb], t1[b][2 * nb + 1]);
+  } else {
+#pragma unroll
+    for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t0[b][2 * nb], t0[b][2 * nb + 1]);
+  }
+}
+
+// compact base-2 digit entry for the branch-free fast path (16 bytes -> one LDS.128)
+struct __align__(16) Digit2 {
+  double thr1;   // |index_value_to_scalar(ind, 1)|
+  uint32_t sh;   // shift inside the word
+  uint32_t wv;   // (word << 8) | stride
+};
+
+#ifdef TTN_PHASE_CLOCKS
+__device__ unsigned long long g_phase[8];
+#define PH_DECL long long ph_t = clock64(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
+#define PH_MARK(i) { const long long t_ = clock64(); ph_acc[i] += (unsigned long long)(t_ - ph_t); ph_t = t_; }
+#define PH_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 6; ++i_) atomicAdd(&g_phase[i_], ph_acc[i_]); atomicAdd(&g_phase[7], 1ull); }
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_FLUSH
+#endif
+
+template <int CHI, int NMW, int GB, bool B2>
+__global__ void __launch_bounds__(NMW * 32 + 32, 1)
+    chain_mma5_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
+                      double* __restrict__ partial, int do_sum, int n_stage, int resident,
+                      uint32_t stage_stride) {
+  constexpr int PW = 128;          // points per warp sub-tile
+  constexpr int PPL = PW / 32;     // points per lane
+  constexpr int ROWS = PW + 8;     // + scratch rows (class padding target = row PW)
+  constexpr int CPR = CHI / 2;
+  constexpr int LIST_CAP = PW + 8 * kMaxClasses;
+  constexpr int NT = NMW * 32;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kMmaMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMmaMaxStages];
+  __shared__ double red[2][NMW];
+  __shared__ DigitEntry s_ent[B2 ? 1 : kFeMaxSites];
+  __shared__ double s_thr[B2 ? 1 : kFeMaxThr];
+  __shared__ Digit2 s_d2[B2 ? kFeMaxSites : 1];
+  __shared__ int s_cptr[TTN_MAX_COORDS + 1];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < n_stage; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), NMW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i <= dg.n_coords; i += NT + 32) s_cptr[i] = dg.coord_ptr[i];
+  if (B2) {
+    for (int i = tid; i < dg.n_sites; i += NT + 32) {
+      const DigitEntry e = dg.entries[i];
+      Digit2 d2;
+      d2.thr1 = dg.thr[e.thr_off + 1];
+      d2.sh = (uint32_t)e.shift;
+      d2.wv = ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+      s_d2[i] = d2;
+    }
+  } else {
+    for (int i = tid; i < dg.n_sites; i += NT + 32) s_ent[i] = dg.entries[i];
+    int nthr = 0;
+    for (int i = 0; i < dg.n_sites; ++i) nthr = max(nthr, dg.entries[i].thr_off + dg.entries[i].base);
+    for (int i = tid; i < nthr; i += NT + 32) s_thr[i] = dg.thr[i];
+  }
+  // per-warp regions: state rows, then lists, then the shared ring
+  unsigned char* state_all = smem;
+  uint8_t* list_all = reinterpret_cast<uint8_t*>(smem + (size_t)NMW * ROWS * CHI * 8);
+  unsigned char* ring = reinterpret_cast<unsigned char*>(list_all) + NMW * 256;
+  ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~(uintptr_t)127);
+  static_assert(LIST_CAP <= 256, "list capacity");
+  for (int w = 0; w < NMW; ++w)
+    for (int i = tid; i < 8 * CHI; i += NT + 32)
+      reinterpret_cast<double*>(state_all + ((size_t)w * ROWS + PW) * CHI * 8)[i] = 0.0;
+  __syncthreads();
+
+  const int64_t n_sub = (src.npts + PW - 1) / PW;                 // sub-tiles in the launch
+  const int64_t stride = (int64_t)gridDim.x * NMW;
+  const int64_t n_iter = (n_sub + stride - 1) / stride;           // identical for every warp: ring lockstep
+  const int n_rounds = ch.n_rounds, spr = ch.spr, nsl = ch.nsl, n_steps = ch.n_steps;
+  const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
+  const uint32_t ring_base = smem_u32(ring);
+
+  if (tid >= NT) {
+    // ===== producer warp: one elected lane streams the rounds' B fragments =====
+    if (tid == NT && n_rounds > 0) {
+      const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(ch.frags);
+      if (resident) {
+        for (int r = 0; r < n_rounds; ++r) {
+          const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+          mbar_expect_tx(smem_u32(&full_bar[r]), bytes);
+          bulk_g2s(ring_base + (uint32_t)r * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
+                   smem_u32(&full_bar[r]));
+        }
+      } else {
+        uint32_t slot = 0, phase = 0;
+        for (int64_t it = 0; it < n_iter; ++it) {
+          for (int r = 0; r < n_rounds; ++r) {
+            const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+            mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
+            mbar_expect_tx(smem_u32(&full_bar[slot]), bytes);
+            bulk_g2s(ring_base + slot * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
+                     smem_u32(&full_bar[slot]));
+            if (++slot == (uint32_t)n_stage) {
+              slot = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== autonomous MMA warps =====
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t state_base = smem_u32(state_all + (size_t)warp * ROWS * CHI * 8);
+  uint8_t* list = list_all + warp * 256;
+  const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
+  const int bits = ch.bits, per_word = ch.per_word;
+  const uint32_t lt = (1u << lane) - 1u;
+  const bool pow2 = (nsl == 1) || (nsl == 2) || (nsl == 4); // slice index == bit field of the stream
+  double sum_re = 0.0, sum_im = 0.0;
+  uint32_t slot = 0, phase = 0;
+  PH_DECL
+
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t sub = (int64_t)blockIdx.x * NMW + warp + it * stride;
+    const bool live_sub = sub < n_sub;     // warp-uniform
+    uint64_t w0[PPL], w1[PPL], cw[PPL];
+    int in_word = 0;
+    if (live_sub) {
+      // ---- K1: digits of the lane's PPL points (interleaved for ILP)
+      double x[PPL];
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
+      for (int c = 0; c < dg.n_coords; ++c) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int64_t p = sub * PW + k * 32 + lane;
+          x[k] = 0.0;
+          if (p < src.npts) {
+            x[k] = load_coord(src, p, c);
+            if (!coord_in_domain(x[k])) {
+              atomicOr(err, 1);
+              x[k] = 0.0;
+            }
+          }
+        }
+        if (B2) {
+          // base 2: the greedy loop is one compare + one subtract (no divergence), 4 points in flight
+          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+            const Digit2 e = s_d2[e_i];
+            const uint32_t stride = e.wv & 0xffu;
+            const bool hi = (e.wv >> 8) != 0;
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) {
+              const bool ge = x[k] >= e.thr1;
+              x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
+              const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+              if (hi) w1[k] += bb;
+              else w0[k] += bb;
+            }
+          }
+        } else {
+          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+            const DigitEntry e = s_ent[e_i];
+            const double* thr = s_thr + e.thr_off;
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) {
+              const int v = greedy_digit_smem(x[k], thr, e.base);
+              const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
+              w0[k] += (e.word == 0) ? bb : 0ull;
+              w1[k] += (e.word == 1) ? bb : 0ull;
+            }
+          }
+        }
+      }
+      // ---- leaf rows
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = w0[k];
+        const int row = k * 32 + lane;
+        const double* L = ch.leaf + (size_t)(cw[k] & MASK) * CHI;
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
+      }
+    }
+    auto advance = [&]() {
+      const bool wrap = (++in_word == per_word);
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) cw[k] = wrap ? w1[k] : (cw[k] >> bits);
+      if (wrap) in_word = 0;
+    };
+    if (live_sub) advance();
+    __syncwarp();
+    PH_MARK(0)
+
+    for (int r = 0; r < n_rounds; ++r) {
+      const int sites = min(spr, n_steps - r * spr);
+      const uint32_t s_use = resident ? (uint32_t)r : slot;
+      if (live_sub) {
+        int ncls = 1;
+        for (int k = 0; k < sites; ++k) ncls *= nsl;
+        int cls[PPL];
+        if (pow2 && in_word + sites <= per_word) {
+          // slices are bit fields: the class is the next bits*sites bits of the stream
+          const int nb_ = bits * sites;
+          const uint64_t rmask = (1ull << nb_) - 1ull;
+          in_word += sites;
+          const bool wrap = in_word == per_word;
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            cls[k] = (int)(cw[k] & rmask);
+            cw[k] = wrap ? w1[k] : (cw[k] >> nb_);
+          }
+          if (wrap) in_word = 0;
+        } else {
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) cls[k] = 0;
+          int mul = 1;
+          for (int s = 0; s < sites; ++s) {
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) cls[k] += (int)(cw[k] & MASK) * mul;
+            mul *= nsl;
+            advance();
+          }
+        }
+        PH_MARK(5)
+        // ---- warp-local counting sort by class (each class padded to 8 rows), branch-free:
+        // match.any gives every lane the mask of its class-mates in a slice of 32 points; the
+        // per-class slice counts are summed warp-wide as packed bytes with redux.add.
+        // lane c ends up with the row count of class c.
+        int mycnt = 0;
+        {
+          uint32_t rank[PPL];
+          uint32_t pk[PPL][4]; // packed per-class counts of slice k: byte (c & 3) of word (c >> 2)
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            const uint32_t m = __match_any_sync(0xffffffffu, cls[k]);
+            rank[k] = __popc(m & lt);
+            const bool leader = (m & lt) == 0u;
+            const uint32_t contrib = leader ? ((uint32_t)__popc(m) << (8 * (cls[k] & 3))) : 0u;
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              pk[k][w] = (w * 4 < ncls) ? __reduce_add_sync(0xffffffffu, ((cls[k] >> 2) == w) ? contrib : 0u) : 0u;
+          }
+          // lane c: totals and padded exclusive start of class c
+          uint32_t tot_w[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            tot_w[w] = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) tot_w[w] += pk[k][w]; // <= 128 per byte: no carry
+          }
+          const int lw = (lane >> 2) & 3, lsh = 8 * (lane & 3);
+          mycnt = (lane < ncls) ? (int)((tot_w[lw] >> lsh) & 255u) : 0;
+          const int padded = (mycnt + 7) & ~7;
+          int incl = padded;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1) {
+            const int nn = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nn;
+          }
+          const int mystart = incl - padded;
+          for (int c0 = 0; c0 < ncls; c0 += 4) { // padding -> scratch row: lane = (class - c0) * 8 + i
+            const int pc = c0 + (lane >> 3), pi = lane & 7;
+            const int cn = __shfl_sync(0xffffffffu, mycnt, pc & 15), cs = __shfl_sync(0xffffffffu, mystart, pc & 15);
+            if (pc < ncls && (cn & 7) && pi >= (cn & 7)) list[cs + (cn & ~7) + pi] = (uint8_t)PW;
+          }
+          // every point: class start + earlier slices of its class + rank inside its slice
+          uint32_t before_w[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            const int st = __shfl_sync(0xffffffffu, mystart, cls[k]);
+            const int cw_ = (cls[k] >> 2) & 3, csh = 8 * (cls[k] & 3);
+            const uint32_t bw = cw_ == 0 ? before_w[0] : (cw_ == 1 ? before_w[1] : (cw_ == 2 ? before_w[2] : before_w[3]));
+            list[st + (int)((bw >> csh) & 255u) + (int)rank[k]] = (uint8_t)(k * 32 + lane);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) before_w[w] += pk[k][w];
+          }
+        }
+        __syncwarp();
+        PH_MARK(1)
+        mbar_wait(smem_u32(&full_bar[s_use]), resident ? 0u : phase);
+        PH_MARK(2)
+        const uint32_t stage_base = ring_base + s_use * stage_stride + (uint32_t)lane * 8u;
+        // ---- classes outermost: B offsets and group ranges are computed once per class; the row
+        // indices of the next batch are fetched under the current batch's DMMAs
+        int gi = 0;
+        int rows_nx[4];
+        for (int c = 0; c < ncls; ++c) {
+          const int n_c = __shfl_sync(0xffffffffu, mycnt, c);
+          const int gend = gi + ((n_c + 7) >> 3);
+          if (gi == gend) continue;
+          int boff[4] = {0, 0, 0, 0};
+          {
+            int crem = c;
+#pragma unroll
+            for (int si = 0; si < 4; ++si) {
+              if (si < sites) {
+                const int dd = pow2 ? (crem & (int)MASK) : (crem % nsl);
+                crem = pow2 ? (crem >> bits) : (crem / nsl);
+                boff[si] = (si * nsl + dd) * (CHI * CHI * 8);
+              }
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gi + b, gend - 1) << 3) + g];
+          while (gi < gend) {
+            const int nbat = min(GB, gend - gi);
+            int rows[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) rows[b] = rows_nx[b];
+            const int gnext = gi + nbat;
+            if (gnext < gend) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gnext + b, gend - 1) << 3) + g];
+            }
+            if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+            else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+            else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+            else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites);
+            gi = gnext;
+          }
+        }
+        PH_MARK(3)
+      } else {
+        mbar_wait(smem_u32(&full_bar[s_use]), resident ? 0u : phase); // keep the ring in lockstep
+      }
+      __syncwarp();
+      if (!resident) {
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[slot]));
+        if (++slot == (uint32_t)n_stage) {
+          slot = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+
+    // ---- root: out = row . R[d_{n-1}]
+    if (live_sub) {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int row = k * 32 + lane;
+        const int64_t p = sub * PW + row;
+        double o0 = 0.0, o1 = 0.0;
+        if (ch.n_vertices > 1) {
+          const double* R0 = ch.root + (size_t)(cw[k] & MASK) * CHI;
+          const double* R1 = R0 + (size_t)nsl * CHI;
+#pragma unroll
+          for (int j = 0; j < CPR; ++j) {
+            const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+            o0 = fma(v.x, __ldg(R0 + 2 * j), o0);
+            o0 = fma(v.y, __ldg(R0 + 2 * j + 1), o0);
+            if (ch.nout == 2) {
+              o1 = fma(v.x, __ldg(R1 + 2 * j), o1);
+              o1 = fma(v.y, __ldg(R1 + 2 * j + 1), o1);
+            }
+          }
+        } else {
+          o0 = lds64(row_chunk<CHI>(state_base, row, 0));
+          if (ch.nout == 2) o1 = lds64(row_chunk<CHI>(state_base, row, CPR / 2));
+        }
+        if (p < src.npts) {
+          if (out) {
+            if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+            else out[p] = o0;
+          }
+          sum_re += o0;
+          sum_im += o1;
+        }
+      }
+      __syncwarp();
+      PH_MARK(4)
+    }
+  }
+  PH_FLUSH
+
+  if (do_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
+      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
+    }
+    if (lane == 0) {
+      red[0][warp] = sum_re;
+      red[1][warp] = sum_im;
+    }
+    named_bar_sync(1, NT);
+    if (tid == 0) {
+      double xx = 0.0, yy = 0.0;
+      for (int w = 0; w < NMW; ++w) {
+        xx += red[0][w];
+        yy += red[1][w];
+      }
+      partial[2 * blockIdx.x] = xx;
+      partial[2 * blockIdx.x + 1] = yy;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 
 static int mma_width(int w) {
@@ -1016,6 +1482,37 @@ static int launch_mma3_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
   return TTN_OK;
 }
 
+template <int CHI, int NMW, int GB, bool B2>
+static int launch_mma5_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial,
+                            int* n_partial, cudaStream_t s) {
+  const ChainMmaDev& c = p->cmma;
+  constexpr int PW = 128, ROWS = PW + 8;
+  const size_t fixed = (size_t)NMW * ROWS * CHI * 8 + (size_t)NMW * 256 + 128;
+  const size_t smem_max = 227 * 1024 - 12 * 1024; // static shared: barriers, digit tables
+  const size_t stage = (size_t)c.spr * c.nsl * CHI * CHI * 8;
+  if (fixed + stage > smem_max) {
+    set_error("chain DMMA kernel: one round of site matrices does not fit in shared memory");
+    return TTN_ERR_UNSUPPORTED;
+  }
+  int n_stage = (int)std::min<size_t>((smem_max - fixed) / stage, (size_t)kMmaMaxStages);
+  int resident = 0;
+  if (c.n_rounds <= n_stage) {
+    n_stage = std::max(c.n_rounds, 1);
+    resident = 1;
+  }
+  const size_t smem = fixed + (size_t)n_stage * stage;
+  auto kern = chain_mma5_kernel<CHI, NMW, GB, B2>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  const int64_t n_sub = (src.npts + PW - 1) / PW;
+  const int grid = (int)std::min<int64_t>((n_sub + NMW - 1) / NMW, p->sm_count);
+  const int do_sum = d_partial != nullptr;
+  kern<<<grid, NMW * 32 + 32, smem, s>>>(c, p->digits, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
+                                         (uint32_t)stage);
+  TTN_CUDA(cudaGetLastError());
+  *n_partial = do_sum ? grid : 0;
+  return TTN_OK;
+}
+
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                      int* n_partial, cudaStream_t s) {
   (void)st;
@@ -1028,7 +1525,17 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   static const int variant = getenv("TTN_MMA_VARIANT") ? atoi(getenv("TTN_MMA_VARIANT")) : 0;
   // v3 (warp-specialised) needs the digit tables to fit its static shared-memory copies
   bool v3_ok = p->digits.n_sites <= kFeMaxSites && p->info.n_sites <= kFeMaxSites && p->fe_thr_len <= kFeMaxThr;
-  if (variant >= 1) v3_ok = false;
+  if (variant >= 1 && variant != 5) v3_ok = false;
+  if (v3_ok && variant == 5) {
+    switch (p->cmma.chi) {
+      case 8:
+        return p->all_base2 ? launch_mma5_inst<8, 8, 4, true>(p, src, d_out, d_partial, n_partial, s)
+                            : launch_mma5_inst<8, 8, 4, false>(p, src, d_out, d_partial, n_partial, s);
+      case 16:
+        return p->all_base2 ? launch_mma5_inst<16, 8, 4, true>(p, src, d_out, d_partial, n_partial, s)
+                            : launch_mma5_inst<16, 8, 4, false>(p, src, d_out, d_partial, n_partial, s);
+    }
+  }
   if (v3_ok) {
     switch (p->cmma.chi) {
       case 16: return launch_mma3_inst<16, 1024, 8, 4>(p, src, d_out, d_partial, n_partial, s);
@@ -1046,5 +1553,14 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   set_error("DMMA chain kernel: unsupported width");
   return TTN_ERR_UNSUPPORTED;
 }
+
+#ifdef TTN_PHASE_CLOCKS
+int debug_phase_clocks(unsigned long long* out8, int reset) {
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  TTN_CUDA(cudaMemcpyFromSymbol(out8, g_phase, sizeof(z)));
+  if (reset) TTN_CUDA(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+  return TTN_OK;
+}
+#endif
 
 } // namespace ttn

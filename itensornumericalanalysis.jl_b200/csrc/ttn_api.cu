@@ -155,6 +155,8 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   std::vector<double> tensors(reinterpret_cast<const double*>(d->tensors),
                               reinterpret_cast<const double*>(d->tensors) + d->tensor_ptr[n] * NC);
   p->fe_thr_len = d->thr_ptr[d->n_sites];
+  p->all_base2 = true;
+  for (int s = 0; s < d->n_sites; ++s) p->all_base2 = p->all_base2 && d->site_dim[s] == 2;
   p->digits.n_coords = d->n_coords;
   p->digits.n_sites = d->n_sites;
   if ((rc = upload(p, coord_ptr, &p->digits.coord_ptr))) return rc;
@@ -387,6 +389,9 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
 
 } // namespace ttn
 
+#ifdef TTN_PHASE_CLOCKS
+namespace ttn { int debug_phase_clocks(unsigned long long* out8, int reset); }
+#endif
 using namespace ttn;
 
 extern "C" {
@@ -527,6 +532,10 @@ int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coo
   if (herr) return fail(TTN_ERR_DOMAIN, "a coordinate is negative or NaN");
   return TTN_OK;
 }
+
+#ifdef TTN_PHASE_CLOCKS
+int ttn_debug_phase_clocks(unsigned long long* out8, int reset) { return ttn::debug_phase_clocks(out8, reset); }
+#endif
 
 int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops) {
   if (!dfma_tflops || !dmma_tflops) return fail(TTN_ERR_INVALID, "null argument");

@@ -131,6 +131,7 @@ struct ttn_plan {
   bool chain_ok = false;
   ttn::ChainMmaDev cmma{};
   bool cmma_ok = false;
+  bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int* d_err = nullptr;    // domain-error flag
   double* d_sum = nullptr; // (re, im)
