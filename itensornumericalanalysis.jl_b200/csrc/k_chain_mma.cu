@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
       const int64_t p = tile * P + row;
       double o0 = 0.0, o1 = 0.0;
       if (ch.n_vertices > 1) {
-        const double* R0 = ch.root + (size_t)slice_at(wt[row], ch.n_vertices - 1) * CHI;
+        const double* R0 = ch.root + (size_t)slice_at(wt[row], ch.root_pos) * CHI;
         const double* R1 = R0 + (size_t)nsl * CHI;
 #pragma unroll
         for (int j = 0; j < CPR; ++j) {
@@ -876,7 +876,7 @@ __device__ unsigned long long g_phase[8];
 #define PH_FLUSH
 #endif
 
-template <int CHI, int NMW, int GB, bool B2>
+template <int CHI, int NMW, int GB, bool B2, int NSLT, int SPRT>
 __global__ void __launch_bounds__(NMW * 32 + 32, 1)
     chain_mma5_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                       double* __restrict__ partial, int do_sum, int n_stage, int resident,
@@ -936,7 +936,10 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
   const int64_t n_sub = (src.npts + PW - 1) / PW;                 // sub-tiles in the launch
   const int64_t stride = (int64_t)gridDim.x * NMW;
   const int64_t n_iter = (n_sub + stride - 1) / stride;           // identical for every warp: ring lockstep
-  const int n_rounds = ch.n_rounds, spr = ch.spr, nsl = ch.nsl, n_steps = ch.n_steps;
+  // NSLT / SPRT != 0: slices per vertex and sites per round are compile-time constants (the host
+  // pads the chain with identity sites so that every round is full), which lets the compiler
+  // unroll the class and site loops and drop every division from the hot path
+  const int n_rounds = ch.n_rounds, spr = SPRT ? SPRT : ch.spr, nsl = NSLT ? NSLT : ch.nsl, n_steps = ch.n_steps;
   const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
   const uint32_t ring_base = smem_u32(ring);
 
@@ -946,7 +949,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
       const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(ch.frags);
       if (resident) {
         for (int r = 0; r < n_rounds; ++r) {
-          const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+          const uint32_t bytes = (uint32_t)(SPRT ? SPRT : min(spr, n_steps - r * spr)) * site_bytes;
           mbar_expect_tx(smem_u32(&full_bar[r]), bytes);
           bulk_g2s(ring_base + (uint32_t)r * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
                    smem_u32(&full_bar[r]));
@@ -955,7 +958,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
         uint32_t slot = 0, phase = 0;
         for (int64_t it = 0; it < n_iter; ++it) {
           for (int r = 0; r < n_rounds; ++r) {
-            const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+            const uint32_t bytes = (uint32_t)(SPRT ? SPRT : min(spr, n_steps - r * spr)) * site_bytes;
             mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
             mbar_expect_tx(smem_u32(&full_bar[slot]), bytes);
             bulk_g2s(ring_base + slot * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
@@ -977,7 +980,8 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
   const uint32_t state_base = smem_u32(state_all + (size_t)warp * ROWS * CHI * 8);
   uint8_t* list = list_all + warp * 256;
   const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
-  const int bits = ch.bits, per_word = ch.per_word;
+  const int bits = NSLT ? (NSLT <= 1 ? 0 : (NSLT <= 2 ? 1 : 2)) : ch.bits;
+  const int per_word = NSLT ? (NSLT <= 1 ? (1 << 30) : 64 / (NSLT <= 2 ? 1 : 2)) : ch.per_word;
   const uint32_t lt = (1u << lane) - 1u;
   const bool pow2 = (nsl == 1) || (nsl == 2) || (nsl == 4); // slice index == bit field of the stream
   double sum_re = 0.0, sum_im = 0.0;
@@ -1057,7 +1061,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
     PH_MARK(0)
 
     for (int r = 0; r < n_rounds; ++r) {
-      const int sites = min(spr, n_steps - r * spr);
+      const int sites = SPRT ? SPRT : min(spr, n_steps - r * spr);
       const uint32_t s_use = resident ? (uint32_t)r : slot;
       if (live_sub) {
         int ncls = 1;
@@ -1184,6 +1188,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
             gi = gnext;
           }
         }
+      
         PH_MARK(3)
       } else {
         mbar_wait(smem_u32(&full_bar[s_use]), resident ? 0u : phase); // keep the ring in lockstep
@@ -1279,13 +1284,38 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     maxchi = std::max(maxchi, d->link_dim[v]);
     maxsl = std::max(maxsl, p->nslices[v]);
   }
-  const int H = cplx ? std::max(4, mma_width(2 * maxchi) / 2) : 0; // complex: row = [re(H) | im(H)]
   const int CHI = cplx ? mma_width(2 * maxchi) : mma_width(maxchi);
+  const int H = CHI / 2; // complex: row = [re(H) | im(H)]
   if (CHI == 0 || maxsl > 4) return TTN_OK;
   const int NSL = maxsl;
   const int bits = NSL <= 1 ? 0 : (NSL <= 2 ? 1 : 2);
   const int per_word = bits == 0 ? (1 << 30) : 64 / bits;
-  const int n_words = bits == 0 ? 0 : (n + per_word - 1) / per_word;
+
+  // sites per round: as many as keep the class count <= 4 (binary digits: 2 sites -> 4 classes)
+  int spr = 1;
+  while (true) {
+    int cls = 1;
+    for (int k = 0; k < spr + 1; ++k) cls *= NSL;
+    if (NSL <= 1 || cls > 4 || spr >= 4) break;
+    ++spr;
+  }
+  if (NSL <= 1) spr = 2;
+  if (const char* e = getenv("TTN_MMA_SPR")) spr = std::max(1, atoi(e));
+  {
+    int cls = 1;
+    for (int k = 0; k < spr; ++k) cls *= std::max(NSL, 1);
+    while (cls > kMaxClasses && spr > 1) {
+      --spr;
+      cls /= NSL;
+    }
+  }
+  // the chain is padded with identity sites (slice bits always 0) up to a whole number of rounds,
+  // so that every round has exactly `spr` sites
+  const int n_steps = n >= 2 ? n - 2 : 0;
+  const int n_steps_p = (n_steps + spr - 1) / spr * spr;
+  const int root_pos = n >= 2 ? 1 + n_steps_p : 0;
+  const int n_pos = root_pos + 1;
+  const int n_words = bits == 0 ? 0 : (n_pos + per_word - 1) / per_word;
   if (n_words > 2) return TTN_OK;
 
   std::vector<int> order(n), pos_of(n);
@@ -1296,16 +1326,16 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       if (pos > 0) v = p->child[p->child_ptr[v]];
     }
     for (int pos = 0; pos < n; ++pos) pos_of[order[pos]] = pos;
+    if (n >= 2) pos_of[order[n - 1]] = root_pos;
   }
   const double* T = reinterpret_cast<const double*>(d->tensors);
   auto elem = [&](int v, int64_t idx, double* re, double* im) {
     *re = T[(d->tensor_ptr[v] + idx) * NC];
     *im = cplx ? T[(d->tensor_ptr[v] + idx) * NC + 1] : 0.0;
   };
-  const int n_steps = n >= 2 ? n - 2 : 0;
   const int nout = cplx ? 2 : 1;
   std::vector<double> leaf((size_t)NSL * CHI, 0.0), root((size_t)nout * NSL * CHI, 0.0);
-  std::vector<double> frags((size_t)std::max(n_steps, 1) * NSL * CHI * CHI, 0.0);
+  std::vector<double> frags((size_t)std::max(n_steps_p, 1) * NSL * CHI * CHI, 0.0);
   {
     const int v = order[0], b = d->link_dim[v];
     for (int s = 0; s < p->nslices[v]; ++s)
@@ -1331,10 +1361,15 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       }
   }
   std::vector<double> E((size_t)CHI * CHI);
-  for (int t = 0; t < n_steps; ++t) {
-    const int v = order[t + 1], a = d->link_dim[order[t]], b = d->link_dim[v];
-    for (int s = 0; s < p->nslices[v]; ++s) {
+  for (int t = 0; t < n_steps_p; ++t) {
+    const bool dummy = t >= n_steps;
+    const int v = dummy ? -1 : order[t + 1];
+    const int a = dummy ? 0 : d->link_dim[order[t]], b = dummy ? 0 : d->link_dim[v];
+    for (int s = 0; s < (dummy ? NSL : p->nslices[v]); ++s) {
       std::fill(E.begin(), E.end(), 0.0);
+      if (dummy) {
+        for (int i = 0; i < CHI; ++i) E[(size_t)i * CHI + i] = 1.0;
+      }
       for (int i = 0; i < a; ++i)
         for (int j = 0; j < b; ++j) {
           double re, im;
@@ -1370,38 +1405,23 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
 
   ChainMmaDev& c = p->cmma;
   c.n_vertices = n;
-  c.n_steps = n_steps;
+  c.n_steps = n_steps_p;
   c.nsl = NSL;
   c.chi = CHI;
   c.nout = nout;
   c.bits = bits;
   c.per_word = per_word;
   c.n_words = n_words;
-  // sites per round: as many as keep the class count <= 4 (binary digits: 2 sites -> 4 classes)
-  int spr = 1;
-  while (true) {
-    int cls = 1;
-    for (int k = 0; k < spr + 1; ++k) cls *= NSL;
-    if (NSL <= 1 || cls > 4 || spr >= 4) break;
-    ++spr;
-  }
-  if (NSL <= 1) spr = 2;
-  if (const char* e = getenv("TTN_MMA_SPR")) spr = std::max(1, atoi(e));
-  {
-    int cls = 1;
-    for (int k = 0; k < spr; ++k) cls *= std::max(NSL, 1);
-    while (cls > kMaxClasses && spr > 1) {
-      --spr;
-      cls /= NSL;
-    }
-  }
+  c.root_pos = root_pos;
   c.spr = spr;
-  c.n_rounds = (n_steps + spr - 1) / spr;
+  c.n_rounds = n_steps_p / spr;
   c.leaf = d_leaf;
   c.root = d_root;
   c.frags = d_frags;
 
-  // (word, shift) of every digit entry (same convention as the register chain kernel)
+  // the DMMA kernels get their own copy of the digit table: (word, shift) follow THEIR packed
+  // stream positions (identity padding shifts the root)
+  p->digits_mma = p->digits;
   if (d->n_sites > 0) {
     std::vector<DigitEntry> ent(d->n_sites);
     TTN_CUDA(cudaMemcpy(ent.data(), p->digits.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
@@ -1410,8 +1430,11 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       e.word = bits ? pos / per_word : 0;
       e.shift = bits ? (pos % per_word) * bits : 0;
     }
-    TTN_CUDA(cudaMemcpy(const_cast<DigitEntry*>(p->digits.entries), ent.data(), sizeof(DigitEntry) * d->n_sites,
-                        cudaMemcpyHostToDevice));
+    DigitEntry* d_ent;
+    TTN_CUDA(cudaMalloc(&d_ent, sizeof(DigitEntry) * d->n_sites));
+    p->allocs.push_back(d_ent);
+    TTN_CUDA(cudaMemcpy(d_ent, ent.data(), sizeof(DigitEntry) * d->n_sites, cudaMemcpyHostToDevice));
+    p->digits_mma.entries = d_ent;
   }
   p->cmma_ok = true;
   return TTN_OK;
@@ -1444,7 +1467,7 @@ static int launch_mma_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
   const int64_t n_tiles = (src.npts + P - 1) / P;
   const int grid = (int)std::min<int64_t>((n_tiles + NH - 1) / NH, p->sm_count);
   const int do_sum = d_partial != nullptr;
-  kern<<<grid, NTH * NH + 32 * NH, smem, s>>>(c, p->digits, src, d_out, p->d_err, d_partial, do_sum, n_stage,
+  kern<<<grid, NTH * NH + 32 * NH, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum, n_stage,
                                                resident, (uint32_t)stage, (uint32_t)half_bytes);
   TTN_CUDA(cudaGetLastError());
   *n_partial = do_sum ? grid : 0;
@@ -1475,14 +1498,14 @@ static int launch_mma3_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
   const int64_t n_tiles = (src.npts + P - 1) / P;
   const int grid = (int)std::min<int64_t>(n_tiles, p->sm_count);
   const int do_sum = d_partial != nullptr;
-  kern<<<grid, NMW * 32 + 128, smem, s>>>(c, p->digits, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
+  kern<<<grid, NMW * 32 + 128, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
                                           (uint32_t)stage);
   TTN_CUDA(cudaGetLastError());
   *n_partial = do_sum ? grid : 0;
   return TTN_OK;
 }
 
-template <int CHI, int NMW, int GB, bool B2>
+template <int CHI, int NMW, int GB, bool B2, int NSLT, int SPRT>
 static int launch_mma5_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial,
                             int* n_partial, cudaStream_t s) {
   const ChainMmaDev& c = p->cmma;
@@ -1501,12 +1524,12 @@ static int launch_mma5_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
     resident = 1;
   }
   const size_t smem = fixed + (size_t)n_stage * stage;
-  auto kern = chain_mma5_kernel<CHI, NMW, GB, B2>;
+  auto kern = chain_mma5_kernel<CHI, NMW, GB, B2, NSLT, SPRT>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const int64_t n_sub = (src.npts + PW - 1) / PW;
   const int grid = (int)std::min<int64_t>((n_sub + NMW - 1) / NMW, p->sm_count);
   const int do_sum = d_partial != nullptr;
-  kern<<<grid, NMW * 32 + 32, smem, s>>>(c, p->digits, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
+  kern<<<grid, NMW * 32 + 32, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum, n_stage, resident,
                                          (uint32_t)stage);
   TTN_CUDA(cudaGetLastError());
   *n_partial = do_sum ? grid : 0;
@@ -1525,16 +1548,22 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   static const int variant = getenv("TTN_MMA_VARIANT") ? atoi(getenv("TTN_MMA_VARIANT")) : 0;
   // v3 (warp-specialised) needs the digit tables to fit its static shared-memory copies
   bool v3_ok = p->digits.n_sites <= kFeMaxSites && p->info.n_sites <= kFeMaxSites && p->fe_thr_len <= kFeMaxThr;
-  if (variant >= 1 && variant != 5) v3_ok = false;
-  if (v3_ok && variant == 5) {
-    switch (p->cmma.chi) {
-      case 8:
-        return p->all_base2 ? launch_mma5_inst<8, 8, 4, true>(p, src, d_out, d_partial, n_partial, s)
-                            : launch_mma5_inst<8, 8, 4, false>(p, src, d_out, d_partial, n_partial, s);
-      case 16:
-        return p->all_base2 ? launch_mma5_inst<16, 8, 4, true>(p, src, d_out, d_partial, n_partial, s)
-                            : launch_mma5_inst<16, 8, 4, false>(p, src, d_out, d_partial, n_partial, s);
+  if (variant == 1 || variant == 2) v3_ok = false;
+  if (v3_ok && variant != 3 && (p->cmma.chi == 8 || p->cmma.chi == 16)) {
+    // v5 (warp-autonomous).  Fast instances: binary digits with 2 sites per round, or two binary
+    // digits per vertex (4 slices) with 1 site per round; everything else takes the generic one.
+    const ChainMmaDev& c = p->cmma;
+    const bool full_rounds = c.n_steps % std::max(c.spr, 1) == 0;
+    const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2 && full_rounds;
+    const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
+    if (c.chi == 8) {
+      if (f22) return launch_mma5_inst<8, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+      if (f41) return launch_mma5_inst<8, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+      return launch_mma5_inst<8, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
     }
+    if (f22) return launch_mma5_inst<16, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+    if (f41) return launch_mma5_inst<16, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+    return launch_mma5_inst<16, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
   }
   if (v3_ok) {
     switch (p->cmma.chi) {

@@ -190,7 +190,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   // planner: DMMA tiles once the (real-embedded) row is wide enough to fill them, the register
   // kernel for narrow chains, the generic kernel for everything that is not a chain
   const int width = (d->is_complex ? 2 : 1) * max_link;
-  if (p->cmma_ok && width >= 12) I.auto_kernel = TTN_KERNEL_DMMA;
+  if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else I.auto_kernel = TTN_KERNEL_GENERIC;

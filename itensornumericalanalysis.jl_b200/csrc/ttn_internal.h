@@ -95,6 +95,7 @@ struct ChainMmaDev {
   int32_t chi;      // real row width (2*chi for complex networks, embedded), padded: 8, 16 or 32
   int32_t nout;     // 1 (real) or 2 (re, im)
   int32_t bits, per_word, n_words;
+  int32_t root_pos; // position of the root in the packed slice stream (after identity padding)
   const double* leaf;  // [nsl][chi]
   const double* root;  // [nout][nsl][chi]
   const double* frags; // [n_steps][nsl][chi*chi], B-fragment order
@@ -126,6 +127,7 @@ struct ttn_plan {
   // device memory
   std::vector<void*> allocs;
   ttn::DigitTable digits{};
+  ttn::DigitTable digits_mma{}; // same table, (word, shift) for the DMMA kernels' stream layout
   ttn::TreeDev tree{};
   ttn::ChainDev chain{};
   bool chain_ok = false;
