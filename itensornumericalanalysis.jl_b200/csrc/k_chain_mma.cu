@@ -382,6 +382,71 @@ __global__ void __launch_bounds__(NTH * NH + 32 * NH, 1)
   }
 }
 
+template <int CHI, int NBAT>
+__device__ __forceinline__ void site_mma(double (&dst)[NBAT][CHI / 4], const double (&srcA)[NBAT][CHI / 4],
+                                         uint32_t bb) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+    for (int j = 0; j < KB; ++j) dst[b][j] = 0.0;
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+    double bf[NB];
+#pragma unroll
+    for (int nbp = 0; nbp < NB; ++nbp) bf[nbp] = lds64(bb + (uint32_t)((kb * NB + nbp) * 32) * 8u);
+#pragma unroll
+    for (int nbp = 0; nbp < NB; ++nbp)
+#pragma unroll
+      for (int b = 0; b < NBAT; ++b) dmma884(dst[b][2 * nbp], dst[b][2 * nbp + 1], srcA[b][kb], bf[nbp]);
+  }
+}
+
+// One batch: NBAT 8-row groups of one class.  The two register tiles ping-pong between A and D
+// roles from site to site (the D fragment of one site is the A fragment of the next), so there
+// are no register moves between sites.
+template <int CHI, int NBAT>
+__device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&rows)[4], int tq,
+                                               uint32_t stage_base, const int (&boff)[4], int sites) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+  double t0[NBAT][KB], t1[NBAT][KB];
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
+      t0[b][2 * nb] = v.x;
+      t0[b][2 * nb + 1] = v.y;
+    }
+  }
+  int s = 0;
+  for (; s + 1 < sites; s += 2) {
+    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
+    site_mma<CHI, NBAT>(t0, t1, stage_base + (uint32_t)boff[s + 1]);
+  }
+  if (s < sites) {
+    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
+#pragma unroll
+    for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t1[b][2 * nb], t1[b][2 * nb + 1]);
+  } else {
+#pragma unroll
+    for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t0[b][2 * nb], t0[b][2 * nb + 1]);
+  }
+}
+
+// compact base-2 digit entry for the branch-free fast path (16 bytes -> one LDS.128)
+struct __align__(16) Digit2 {
+  double thr1;   // |index_value_to_scalar(ind, 1)|
+  uint32_t sh;   // shift inside the word
+  uint32_t wv;   // (word << 8) | stride
+};
+
 // =====================================================================================
 // v3: warp-specialised version of the scheme above.  The MMA warps do nothing but
 // gather -> DMMA -> scatter; everything else runs concurrently on front-end warps:
@@ -405,7 +470,7 @@ __device__ __forceinline__ int greedy_digit_smem(double& x, const double* thr, i
   return v;
 }
 
-template <int CHI, int P, int NMW, int GB>
+template <int CHI, int P, int NMW, int GB, bool B2, int NSLT, int SPRT>
 __global__ void __launch_bounds__(NMW * 32 + 128, 1)
     chain_mma3_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                       double* __restrict__ partial, int do_sum, int n_stage, int resident,
@@ -422,8 +487,9 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
   __shared__ __align__(8) uint64_t list_full[2], list_empty[2], tile_ready[2], tile_free[2];
   __shared__ double red[2][NMW];
   __shared__ int meta[2][kMaxClasses + 2];
-  __shared__ DigitEntry s_ent[kFeMaxSites];
-  __shared__ double s_thr[kFeMaxThr];
+  __shared__ DigitEntry s_ent[B2 ? 1 : kFeMaxSites];
+  __shared__ double s_thr[B2 ? 1 : kFeMaxThr];
+  __shared__ Digit2 s_d2[B2 ? kFeMaxSites : 1];
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
 
   unsigned char* state_p = smem;                                                    // (P + 8) rows
@@ -445,9 +511,18 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   for (int i = tid; i < 8 * CHI; i += NTM + 128) reinterpret_cast<double*>(state_p + (size_t)P * CHI * 8)[i] = 0.0;
-  for (int i = tid; i < dg.n_sites; i += NTM + 128) s_ent[i] = dg.entries[i];
   for (int i = tid; i <= dg.n_coords; i += NTM + 128) s_cptr[i] = dg.coord_ptr[i];
-  {
+  if (B2) {
+    for (int i = tid; i < dg.n_sites; i += NTM + 128) {
+      const DigitEntry e = dg.entries[i];
+      Digit2 d2;
+      d2.thr1 = dg.thr[e.thr_off + 1];
+      d2.sh = (uint32_t)e.shift;
+      d2.wv = ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+      s_d2[i] = d2;
+    }
+  } else {
+    for (int i = tid; i < dg.n_sites; i += NTM + 128) s_ent[i] = dg.entries[i];
     int nthr = 0; // thr[] length = max over entries of thr_off + base
     for (int i = 0; i < dg.n_sites; ++i) nthr = max(nthr, dg.entries[i].thr_off + dg.entries[i].base);
     for (int i = tid; i < nthr; i += NTM + 128) s_thr[i] = dg.thr[i];
@@ -455,11 +530,13 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
   __syncthreads();
 
   const int64_t n_tiles = (src.npts + P - 1) / P;
-  const int n_rounds = ch.n_rounds, spr = ch.spr, nsl = ch.nsl, n_steps = ch.n_steps;
+  const int n_rounds = ch.n_rounds, spr = SPRT ? SPRT : ch.spr, nsl = NSLT ? NSLT : ch.nsl, n_steps = ch.n_steps;
   const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
   const uint32_t ring_base = smem_u32(ring);
   const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
-  const int bits = ch.bits, per_word = ch.per_word;
+  const int bits = NSLT ? (NSLT <= 1 ? 0 : (NSLT <= 2 ? 1 : 2)) : ch.bits;
+  const int per_word = NSLT ? (NSLT <= 1 ? (1 << 30) : 64 / (NSLT <= 2 ? 1 : 2)) : ch.per_word;
+  const bool pow2 = (nsl == 1) || (nsl == 2) || (nsl == 4);
   const int lane = tid & 31;
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -497,15 +574,31 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
               }
             }
           }
-          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
-            const DigitEntry e = s_ent[e_i];
-            const double* thr = s_thr + e.thr_off;
+          if (B2) {
+            for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+              const Digit2 e = s_d2[e_i];
+              const uint32_t stride = e.wv & 0xffu;
+              const bool hi = (e.wv >> 8) != 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int v = greedy_digit_smem(x[q], thr, e.base);
-              const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
-              w0[q] += (e.word == 0) ? bb : 0ull;
-              w1[q] += (e.word == 1) ? bb : 0ull;
+              for (int q = 0; q < 4; ++q) {
+                const bool ge = x[q] >= e.thr1;
+                x[q] = __dsub_rn(x[q], ge ? e.thr1 : 0.0);
+                const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+                if (hi) w1[q] += bb;
+                else w0[q] += bb;
+              }
+            }
+          } else {
+            for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+              const DigitEntry e = s_ent[e_i];
+              const double* thr = s_thr + e.thr_off;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int v = greedy_digit_smem(x[q], thr, e.base);
+                const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
+                w0[q] += (e.word == 0) ? bb : 0ull;
+                w1[q] += (e.word == 1) ? bb : 0ull;
+              }
             }
           }
         }
@@ -531,7 +624,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
       for (int r = 0; r < n_rounds; ++r, ++q) {
         const int lb = (int)(q & 1);
         uint16_t* list = lists + lb * LIST_CAP;
-        const int sites = min(spr, n_steps - r * spr);
+        const int sites = SPRT ? SPRT : min(spr, n_steps - r * spr);
         int ncls = 1;
         for (int k = 0; k < sites; ++k) ncls *= nsl;
         const int pos0 = 1 + r * spr;
@@ -676,7 +769,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
   auto issue_round = [&](int64_t qq) { // thread 0 only: B fragments of global round qq -> its ring slot
     const int r = (int)(qq % n_rounds);
     const uint32_t s = resident ? (uint32_t)r : (uint32_t)(qq % n_stage);
-    const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
+    const uint32_t bytes = (uint32_t)(SPRT ? SPRT : min(spr, n_steps - r * spr)) * site_bytes;
     mbar_expect_tx(smem_u32(&ring_full[s]), bytes);
     bulk_g2s(ring_base + s * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes, smem_u32(&ring_full[s]));
   };
@@ -704,7 +797,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
     for (int r = 0; r < n_rounds; ++r, ++q) {
       const int lb = (int)(q & 1);
       const uint16_t* list = lists + lb * LIST_CAP;
-      const int sites = min(spr, n_steps - r * spr);
+      const int sites = SPRT ? SPRT : min(spr, n_steps - r * spr);
       int ncls = 1;
       for (int k = 0; k < sites; ++k) ncls *= nsl;
       mbar_wait(smem_u32(&list_full[lb]), (uint32_t)((q >> 1) & 1));
@@ -716,19 +809,43 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
 
       const int n_groups = total_rows >> 3;
       const int gpw = (n_groups + NMW - 1) / NMW;
-      int gi = warp * gpw;
-      const int gend = min(n_groups, gi + gpw);
-      while (gi < gend) {
-        const int row0 = gi << 3;
-        const uint32_t m = __ballot_sync(0xffffffffu, lane < ncls && mystart <= row0);
-        const int c = 31 - __clz(m);
-        const int cend = __shfl_sync(0xffffffffu, mystart, c + 1) >> 3;
-        const int nbat = min(GB, min(gend, cend) - gi);
-        if (nbat >= 4 && GB >= 4) process_batch<CHI, (GB >= 4 ? 4 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else if (nbat == 3 && GB >= 3) process_batch<CHI, (GB >= 3 ? 3 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else if (nbat == 2 && GB >= 2) process_batch<CHI, (GB >= 2 ? 2 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else process_batch<CHI, 1>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        gi += max(1, min(nbat, GB));
+      const int gw0 = warp * gpw, gw1 = min(n_groups, gw0 + gpw);
+      int rows_nx[4];
+      for (int c = 0; c < ncls; ++c) { // classes outermost: B offsets once per class, no divisions
+        const int cs = __shfl_sync(0xffffffffu, mystart, c) >> 3, ce = __shfl_sync(0xffffffffu, mystart, c + 1) >> 3;
+        int gi = max(cs, gw0);
+        const int gend = min(ce, gw1);
+        if (gi >= gend) continue;
+        int boff[4] = {0, 0, 0, 0};
+        {
+          int crem = c;
+#pragma unroll
+          for (int si = 0; si < 4; ++si) {
+            if (si < sites) {
+              const int dd = pow2 ? (crem & (int)MASK) : (crem % nsl);
+              crem = pow2 ? (crem >> bits) : (crem / nsl);
+              boff[si] = (si * nsl + dd) * (CHI * CHI * 8);
+            }
+          }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gi + b, gend - 1) << 3) + g];
+        while (gi < gend) {
+          const int nbat = min(GB, gend - gi);
+          int rows[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) rows[b] = rows_nx[b];
+          const int gnext = gi + nbat;
+          if (gnext < gend) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gnext + b, gend - 1) << 3) + g];
+          }
+          if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+          else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+          else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites);
+          else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites);
+          gi = gnext;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&list_empty[lb]));
@@ -801,70 +918,6 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
 // B-fragment ring (full/empty mbarriers), so they drift apart freely: while one warp sorts or
 // gathers, the other warp on its SMSP keeps the DMMA pipe busy (one warp alone can saturate it:
 // scripts/microbench/dmma_issue.cu).  Price: classes are padded to 8 rows per warp, not per CTA.
-template <int CHI, int NBAT>
-__device__ __forceinline__ void site_mma(double (&dst)[NBAT][CHI / 4], const double (&srcA)[NBAT][CHI / 4],
-                                         uint32_t bb) {
-  constexpr int NB = CHI / 8, KB = CHI / 4;
-  double bf[KB * NB];
-#pragma unroll
-  for (int j = 0; j < KB * NB; ++j) bf[j] = lds64(bb + (uint32_t)(j * 32) * 8u);
-#pragma unroll
-  for (int b = 0; b < NBAT; ++b)
-#pragma unroll
-    for (int j = 0; j < KB; ++j) dst[b][j] = 0.0;
-#pragma unroll
-  for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-    for (int nbp = 0; nbp < NB; ++nbp)
-#pragma unroll
-      for (int b = 0; b < NBAT; ++b) dmma884(dst[b][2 * nbp], dst[b][2 * nbp + 1], srcA[b][kb], bf[kb * NB + nbp]);
-}
-
-// One batch: NBAT 8-row groups of one class.  The two register tiles ping-pong between A and D
-// roles from site to site (the D fragment of one site is the A fragment of the next), so there
-// are no register moves between sites.
-template <int CHI, int NBAT>
-__device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&rows)[4], int tq,
-                                               uint32_t stage_base, const int (&boff)[4], int sites) {
-  constexpr int NB = CHI / 8, KB = CHI / 4;
-  double t0[NBAT][KB], t1[NBAT][KB];
-#pragma unroll
-  for (int b = 0; b < NBAT; ++b) {
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
-      t0[b][2 * nb] = v.x;
-      t0[b][2 * nb + 1] = v.y;
-    }
-  }
-  int s = 0;
-  for (; s + 1 < sites; s += 2) {
-    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
-    site_mma<CHI, NBAT>(t0, t1, stage_base + (uint32_t)boff[s + 1]);
-  }
-  if (s < sites) {
-    site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
-#pragma unroll
-    for (int b = 0; b < NBAT; ++b)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t1[b][2 * nb], t1[b][2 * nb + 1]);
-  } else {
-#pragma unroll
-    for (int b = 0; b < NBAT; ++b)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t0[b][2 * nb], t0[b][2 * nb + 1]);
-  }
-}
-
-// compact base-2 digit entry for the branch-free fast path (16 bytes -> one LDS.128)
-struct __align__(16) Digit2 {
-  double thr1;   // |index_value_to_scalar(ind, 1)|
-  uint32_t sh;   // shift inside the word
-  uint32_t wv;   // (word << 8) | stride
-};
-
 #ifdef TTN_PHASE_CLOCKS
 __device__ unsigned long long g_phase[8];
 #define PH_DECL long long ph_t = clock64(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -1474,7 +1527,7 @@ static int launch_mma_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
   return TTN_OK;
 }
 
-template <int CHI, int P, int NMW, int GB>
+template <int CHI, int P, int NMW, int GB, bool B2, int NSLT, int SPRT>
 static int launch_mma3_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial,
                             int* n_partial, cudaStream_t s) {
   const ChainMmaDev& c = p->cmma;
@@ -1493,7 +1546,7 @@ static int launch_mma3_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
     resident = 1;
   }
   const size_t smem = fixed + (size_t)n_stage * stage;
-  auto kern = chain_mma3_kernel<CHI, P, NMW, GB>;
+  auto kern = chain_mma3_kernel<CHI, P, NMW, GB, B2, NSLT, SPRT>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   const int64_t n_tiles = (src.npts + P - 1) / P;
   const int grid = (int)std::min<int64_t>(n_tiles, p->sm_count);
@@ -1566,9 +1619,17 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     return launch_mma5_inst<16, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
   }
   if (v3_ok) {
-    switch (p->cmma.chi) {
-      case 16: return launch_mma3_inst<16, 1024, 8, 4>(p, src, d_out, d_partial, n_partial, s);
-      case 32: return launch_mma3_inst<32, 512, 8, 2>(p, src, d_out, d_partial, n_partial, s);
+    const ChainMmaDev& c = p->cmma;
+    const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2;
+    const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
+    switch (c.chi) {
+      case 16:
+        if (f22) return launch_mma3_inst<16, 1024, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+        return launch_mma3_inst<16, 1024, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
+      case 32:
+        if (f22) return launch_mma3_inst<32, 512, 8, 3, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+        if (f41) return launch_mma3_inst<32, 512, 8, 3, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+        return launch_mma3_inst<32, 512, 8, 2, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
     }
   }
   switch (p->cmma.chi) {
