@@ -67,7 +67,10 @@ enum {
   TTN_KERNEL_GENERIC = 1, /* any tree, any dims: thread-per-point, messages in HBM scratch */
   TTN_KERNEL_CHAIN = 2,   /* MPS-shaped networks: per-point state in registers, site matrices
                              streamed through a shared-memory ring by bulk async copies (TMA) */
-  TTN_KERNEL_DMMA = 3     /* large bond dimension: points grouped by digit, FP64 DMMA tiles */
+  TTN_KERNEL_DMMA = 3,    /* chains up to width 32: points grouped by digit, FP64 DMMA tiles, state in
+                             shared memory */
+  TTN_KERNEL_GEMM = 4     /* wide chains (width 33..256, e.g. complex chi = 128): per-site class-grouped FP64
+                             DMMA GEMM with gathered rows, state in HBM/L2 */
 };
 
 /*

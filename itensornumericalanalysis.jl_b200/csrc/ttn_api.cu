@@ -179,6 +179,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
 
   if ((rc = build_chain(p, d))) return rc;
   if ((rc = build_chain_mma(p, d))) return rc;
+  if ((rc = build_chain_gemm(p, d))) return rc;
 
   ttn_info& I = p->info;
   I.n_vertices = n;
@@ -193,10 +194,11 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
+  else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
   else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
-                        (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0);
+                        (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0) | (p->cgemm_ok ? (1 << TTN_KERNEL_GEMM) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
@@ -212,6 +214,8 @@ static void destroy_plan(ttn_plan* p) {
     if (st.d_out) cudaFree(st.d_out);
     if (st.d_work) cudaFree(st.d_work);
     if (st.d_partial) cudaFree(st.d_partial);
+    if (st.d_gemm) cudaFree(st.d_gemm);
+    if (st.d_partial2) cudaFree(st.d_partial2);
     if (st.k0) cudaEventDestroy(st.k0);
     if (st.k1) cudaEventDestroy(st.k1);
     if (st.s) cudaStreamDestroy(st.s);
@@ -225,8 +229,14 @@ static void destroy_plan(ttn_plan* p) {
 }
 
 static int run_kernel(ttn_plan* p, int kernel, Stream& st, const CoordSource& src, double* d_out,
-                      double* d_partial, int* n_partial) {
+                      double* d_partial, int* n_partial, int* extra_launches) {
   switch (kernel) {
+    case TTN_KERNEL_GEMM: {
+      int nl = 0;
+      const int rc = launch_chain_gemm(p, st, src, d_out, d_partial, n_partial, st.s, &nl);
+      *extra_launches += nl - 1;
+      return rc;
+    }
     case TTN_KERNEL_GENERIC: return launch_generic(p, st, src, d_out, d_partial, n_partial, st.s);
     case TTN_KERNEL_CHAIN: return launch_chain(p, st, src, d_out, d_partial, n_partial, st.s);
     case TTN_KERNEL_DMMA: return launch_chain_mma(p, st, src, d_out, d_partial, n_partial, st.s);
@@ -267,6 +277,8 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
+  if (kernel == TTN_KERNEL_GEMM && !p->cgemm_ok)
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GEMM: network is not a chain with 32 < (real-embedded) width <= 256 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_DMMA: network is not a chain with chi <= 32 (real) / 16 (complex), <= 4 slices per vertex and <= 128 slice bits");
   const bool coords_host = !base.grid && opts->coords_mem == TTN_MEM_HOST;
@@ -339,7 +351,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     cudaEventCreate(&ev[2 * ci + 1]);
     cudaEventRecord(ev[2 * ci], st.s);
     int n_partial = 0;
-    rc = run_kernel(p, kernel, st, src, d_out, do_sum ? st.d_partial : nullptr, &n_partial);
+    rc = run_kernel(p, kernel, st, src, d_out, do_sum ? st.d_partial : nullptr, &n_partial, &opts->n_launches);
     if (rc) break;
     opts->n_launches += 1;
     if (do_sum) {

@@ -101,6 +101,15 @@ struct ChainMmaDev {
   const double* frags; // [n_steps][nsl][chi*chi], B-fragment order
 };
 
+// wide chains as per-site grouped GEMMs (k_chain_gemm.cu)
+struct ChainGemmDev {
+  int32_t n_vertices, n_steps, nsl, W, nout;
+  const double* leaf;            // [nsl][W]
+  const double* root;            // [nout][nsl][W]
+  const double* frags;           // [n_steps][nsl][W*W], B-fragment order
+  const int32_t* pos_of_vertex;  // chain position of every vertex
+};
+
 struct Stream {
   cudaStream_t s = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
@@ -111,6 +120,10 @@ struct Stream {
   size_t work_bytes = 0;
   double* d_partial = nullptr; // per-CTA partial sums (reduce_sum)
   size_t partial_cap = 0;
+  void* d_gemm = nullptr;      // GEMM-path workspace (state ping-pong, slices, lists)
+  size_t gemm_bytes = 0;
+  double* d_partial2 = nullptr;
+  size_t partial2_bytes = 0;
 };
 
 } // namespace ttn
@@ -133,6 +146,8 @@ struct ttn_plan {
   bool chain_ok = false;
   ttn::ChainMmaDev cmma{};
   bool cmma_ok = false;
+  ttn::ChainGemmDev cgemm{};
+  bool cgemm_ok = false;
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int* d_err = nullptr;    // domain-error flag
@@ -153,6 +168,9 @@ int launch_sum_partials(ttn_plan* p, const double* d_partial, int n_partial, int
                         double* d_sum, cudaStream_t s);
 int build_chain(ttn_plan* p, const ttn_desc* d);
 int build_chain_mma(ttn_plan* p, const ttn_desc* d);
+int build_chain_gemm(ttn_plan* p, const ttn_desc* d);
+int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                      int* n_partial, cudaStream_t s, int* n_launches);
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
                      double* d_partial, int* n_partial, cudaStream_t s);
 bool chain_supported(int chi, int nsl, bool cplx);

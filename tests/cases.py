@@ -65,6 +65,10 @@ def real_cases():
     g = t.named_grid((8, 1))
     s = t.continuous_siteinds(g, map_dimension=2)
     out.append(("mps2d_chi32", t.rand_itn(s, link_space=32, rng=10, normalise=True), [1, 2], 4))
+    # wide chain: chi = 48 -> GEMM-regime kernel (width padded to 128)
+    g = t.named_grid((6, 1))
+    s = t.continuous_siteinds(g, map_dimension=2)
+    out.append(("mps2d_chi48_gemm", t.rand_itn(s, link_space=48, rng=13, normalise=True), [1, 2], 3))
     # single vertex, two vertices
     g = t.named_grid((1, 1))
     s = t.continuous_siteinds(g)
@@ -98,6 +102,11 @@ def complex_cases():
     g = t.named_grid((6, 1))
     s = t.complex_continuous_siteinds(g, map_dimension=2)
     out.append(("cplx_default2d", t.rand_itn(s, link_space=16, rng=23, eltype=complex, normalise=True), [1, 2], 3))
+    # BASELINE config 5 layout (complex MPS, Real+Imag index per vertex, phys dim 4) at chi = 40:
+    # real-embedded width 80 -> GEMM-regime kernel
+    g = t.named_grid((5, 1))
+    s = t.complex_continuous_siteinds(g, map_dimension=2)
+    out.append(("cplx_cfg5_chi40_gemm", t.rand_itn(s, link_space=40, rng=25, eltype=complex, normalise=True), [1, 2], 3))
     # complex tree
     g = t.named_comb_tree((3, 3))
     s = t.complex_continuous_siteinds(g, map_dimension=3)

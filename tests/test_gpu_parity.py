@@ -30,7 +30,7 @@ def coords_of(packed, pts):
 
 def kernels_for(plan):
     avail = plan.info()["kernels_available"]
-    return [n for n in ("generic", "chain", "dmma") if avail & (1 << _capi.KERNEL_IDS[n])]
+    return [n for n in ("generic", "chain", "dmma", "gemm") if avail & (1 << _capi.KERNEL_IDS[n])]
 
 
 ALL_CASES = [(c, False) for c in cases.real_cases()] + [(c, True) for c in cases.complex_cases()]
@@ -70,6 +70,9 @@ def test_chain_cases_really_use_the_chain_kernel():
         assert info["auto_kernel"] in (_capi.TTN_KERNEL_CHAIN, _capi.TTN_KERNEL_DMMA), n
         assert info["kernels_available"] & (1 << _capi.TTN_KERNEL_CHAIN), n
         assert info["kernels_available"] & (1 << _capi.TTN_KERNEL_DMMA), n
+    for n in ("mps2d_chi48_gemm", "cplx_cfg5_chi40_gemm"):
+        _, f, dims, _ = names[n]
+        assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GEMM, n
     for n in ("comb3x4_chi4", "bintree4_chi5", "cplx_comb3x3"):
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GENERIC, n
