@@ -48,7 +48,12 @@ def build_workload(config: int):
     if config == 4:
         s = t.continuous_siteinds(t.named_grid((28, 1)), map_dimension=2)
         f = t.rand_itn(s, link_space=32, rng=20264, normalise=True)
-        return f, 2, 2 ** 28, "cfg4: 2-D interleaved MPS 28 sites, chi=32, full 16384^2 grid"
+        return f, 2, 2 ** 26, "cfg4 shape: 2-D interleaved MPS 28 sites, chi=32, real, 2^26 random points/GPU"
+    if config == 5:
+        s = t.complex_continuous_siteinds(t.named_grid((40, 1)), map_dimension=2)
+        f = t.rand_itn(s, link_space=128, rng=20265, eltype=complex, normalise=True)
+        return f, 4, 2 ** 21, ("cfg5 shape: complex 2-D MPS, 40 vertices with a Real and an Imag binary index each "
+                               "(physical dim 4), chi=128 complex, 2^21 random complex points/GPU")
     if config == 1:
         s = t.continuous_siteinds(t.named_grid((20, 1)))
         f = t.sin_itn(s, k=2.0, a=0.3, c=1.1)
@@ -157,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=2, help="2 (default, BASELINE configs[1]), 4, 5 or 1")
     ap.add_argument("--points", type=float, default=0, help="override points per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
