@@ -69,6 +69,8 @@ enum {
                              streamed through a shared-memory ring by bulk async copies (TMA) */
   TTN_KERNEL_DMMA = 3,    /* chains up to width 32: points grouped by digit, FP64 DMMA tiles, state in
                              shared memory */
+  TTN_KERNEL_TREE = 5,    /* real trees with <= 2 children per vertex, chi <= 64 (binary trees, combs): vertex by
+                             vertex over a chunk, degree-3 vertices as Khatri-Rao FP64 DMMA GEMMs */
   TTN_KERNEL_GEMM = 4     /* wide chains (width 33..256, e.g. complex chi = 128): per-site class-grouped FP64
                              DMMA GEMM with gathered rows, state in HBM/L2 */
 };

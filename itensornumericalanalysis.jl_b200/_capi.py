@@ -12,8 +12,8 @@ TTN_ABI_VERSION = 1
 TTN_OK, TTN_ERR_INVALID, TTN_ERR_DOMAIN, TTN_ERR_CUDA, TTN_ERR_UNSUPPORTED, TTN_ERR_NOMEM = range(6)
 TTN_LAYOUT_AOS, TTN_LAYOUT_SOA = 0, 1
 TTN_MEM_HOST, TTN_MEM_DEVICE = 0, 1
-TTN_KERNEL_AUTO, TTN_KERNEL_GENERIC, TTN_KERNEL_CHAIN, TTN_KERNEL_DMMA, TTN_KERNEL_GEMM = 0, 1, 2, 3, 4
-KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm"}
+TTN_KERNEL_AUTO, TTN_KERNEL_GENERIC, TTN_KERNEL_CHAIN, TTN_KERNEL_DMMA, TTN_KERNEL_GEMM, TTN_KERNEL_TREE = range(6)
+KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm", 5: "tree"}
 KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 
 

@@ -1,0 +1,443 @@
+// K7 — trees with at most two children per vertex and bond dimension up to 64 (BASELINE config 3:
+// binary tree, chi = 64): the network is contracted VERTEX BY VERTEX over a chunk of PC points, the
+// messages M_v[PC][W] living in HBM/L2 (one vertex's slices stay L2-resident while the
+// whole chunk streams through it).  Per vertex, for the points that selected slice d:
+//   leaf            M_v[p]    = T_v[d]                                   (row copy)
+//   one child  c    M_v[p,:]  = M_c[p,:] * T_v[d]            (W x W)      grouped GEMM, K = W
+//   two children    M_v[p,n]  = sum_{a,b} M_a[p,a] M_b[p,b] T_v[d][a,b,n]  Khatri-Rao GEMM, K = W^2:
+//                   the A operand M_a[p,a]*M_b[p,b] is never materialised — each lane multiplies
+//                   its M_a value (held in a register for a whole `a`) into the M_b fragment it
+//                   loads from shared memory (one DMUL per 4..16 DMMAs)
+//   root            value = full contraction with a parent dimension of 1  (small dot kernels)
+// CTA tile: 128 rows x W columns; both child row blocks stay in shared memory for the whole K loop,
+// only the tensor T_v[d] (B operand, fragment order) streams through a 3-stage cp.async ring.
+// This is exactly the flop rule of SURVEY §8(d): 2*W^3 per degree-3 vertex (+2*W^2 absorbed).
+#include <algorithm>
+#include <cstring>
+
+#include "k_async.cuh"
+#include "k_digits.cuh"
+
+namespace ttn {
+
+constexpr int TBM = 128, TBK = 16, TSTAGES = 3;
+
+__device__ __forceinline__ void t_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void t_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void t_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void tree_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, int pc, int n_vertices,
+                                   uint8_t* __restrict__ slices, int* err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pc) return;
+  const int64_t p = p0 + i;
+  for (int v = 0; v < n_vertices; ++v) slices[(size_t)v * pc + i] = 0;
+  if (p >= src.npts) return;
+  for (int c = 0; c < dg.n_coords; ++c) {
+    double x = load_coord(src, p, c);
+    if (!coord_in_domain(x)) {
+      atomicOr(err, 1);
+      x = 0.0;
+    }
+    for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
+      const DigitEntry e = dg.entries[k];
+      const int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+      slices[(size_t)e.vertex * pc + i] += (uint8_t)(v * e.stride);
+    }
+  }
+}
+
+// one block per vertex: counting sort of the chunk by the slice selected at that vertex
+__global__ void __launch_bounds__(1024)
+    tree_classify_kernel(const uint8_t* __restrict__ slices, int pc, const int32_t* __restrict__ nslices,
+                         uint32_t* __restrict__ lists, int* __restrict__ cls_off, int* __restrict__ tile_off) {
+  const int v = blockIdx.x;
+  const int nsl = nslices[v];
+  const uint8_t* sl = slices + (size_t)v * pc;
+  uint32_t* list = lists + (size_t)v * pc;
+  __shared__ int cnt[8], cursor[8];
+  if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (nsl > 1)
+    for (int i = threadIdx.x; i < pc; i += blockDim.x) atomicAdd(&cnt[sl[i]], 1);
+  else if (threadIdx.x == 0) cnt[0] = pc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0, trun = 0;
+    for (int c = 0; c < nsl; ++c) {
+      cursor[c] = run;
+      cls_off[v * 9 + c] = run;
+      tile_off[v * 9 + c] = trun;
+      run += cnt[c];
+      trun += (cnt[c] + TBM - 1) / TBM;
+    }
+    for (int c = nsl; c <= 8; ++c) {
+      cls_off[v * 9 + c] = run;
+      tile_off[v * 9 + c] = trun;
+    }
+  }
+  __syncthreads();
+  if (nsl > 1) {
+    for (int i = threadIdx.x; i < pc; i += blockDim.x) list[atomicAdd(&cursor[sl[i]], 1)] = (uint32_t)i;
+  } else {
+    for (int i = threadIdx.x; i < pc; i += blockDim.x) list[i] = (uint32_t)i;
+  }
+}
+
+__global__ void tree_leaf_kernel(const uint8_t* __restrict__ sl, int pc, const double* __restrict__ T, int W,
+                                 double* __restrict__ M) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // one double2 per thread
+  const int per_row = W / 2;
+  if (idx >= (int64_t)pc * per_row) return;
+  const int i = (int)(idx / per_row), j = (int)(idx % per_row);
+  reinterpret_cast<double2*>(M)[idx] = *reinterpret_cast<const double2*>(T + (size_t)sl[i] * W + 2 * j);
+}
+
+// M_v[rows of class d] = KhatriRao(M_a, M_b)[rows] * T_d   (NCH == 2)   or   M_c[rows] * T_d (NCH == 1)
+// frags[d][kb][nb][lane] = T_d[k = 4 kb + (lane & 3)][n = 8 nb + (lane >> 2)],  k = a * W + b.
+template <int W, int NCH>
+__global__ void __launch_bounds__(256, 1)
+    tree_vertex_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb, double* __restrict__ Mout,
+                       const uint32_t* __restrict__ list, const int* __restrict__ cls_off,
+                       const int* __restrict__ tile_off, const double* __restrict__ frags, int nsl) {
+  constexpr int RS = W + 4;            // row stride (doubles) of the child blocks in shared memory
+  constexpr int NT = W / 16;           // 8-column tiles per warp (warp tile 32 x W/2)
+  constexpr int KTOT = (NCH == 2) ? W * W : W;
+  constexpr int NKC = KTOT / TBK;
+  constexpr int BCHUNKS = W / TBK;     // K chunks per value of `a`
+  constexpr int B_STAGE_D = TBK * W;   // doubles per B stage (TBK/4 k-blocks x W/8 n-blocks x 32 lanes)
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* Sa = reinterpret_cast<double*>(smem);          // [TBM][RS]  (NCH == 2 only)
+  double* Sb = Sa + (NCH == 2 ? TBM * RS : 0);           // [TBM][RS]  second child, or the only child
+  double* Bs = Sb + TBM * RS;                            // [TSTAGES][B_STAGE_D]
+  __shared__ uint32_t rowid[TBM];
+
+  const int tile = blockIdx.x;
+  int c = -1;
+  for (int k = 0; k < nsl; ++k)
+    if (tile >= tile_off[k] && tile < tile_off[k + 1]) c = k;
+  if (c < 0) return;
+  const int mblk = tile - tile_off[c];
+  const int row0 = cls_off[c] + mblk * TBM, row_end = cls_off[c + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < TBM) rowid[tid] = list[min(row0 + tid, row_end - 1)];
+  __syncthreads();
+
+  const double* E = frags + (size_t)c * KTOT * W;
+  const uint32_t bs_base = smem_u32(Bs);
+  auto load_B = [&](int stage, int kc) {
+    const double* srcp = E + (size_t)kc * B_STAGE_D;
+#pragma unroll
+    for (int q = 0; q < B_STAGE_D / 2 / 256; ++q)
+      t_cp_async16(bs_base + (uint32_t)(stage * B_STAGE_D + (tid + q * 256) * 2) * 8u, srcp + (tid + q * 256) * 2);
+    if (B_STAGE_D / 2 < 256 && tid < B_STAGE_D / 2)
+      t_cp_async16(bs_base + (uint32_t)(stage * B_STAGE_D + tid * 2) * 8u, srcp + tid * 2);
+  };
+  // group 0: the child row blocks (gathered) + the first B stage
+  {
+    constexpr int CPR = W / 2; // 16-byte chunks per row
+    for (int ch = tid; ch < TBM * CPR; ch += 256) {
+      const int r = ch / CPR, cc = ch % CPR;
+      t_cp_async16(smem_u32(Sb) + (uint32_t)(r * RS + cc * 2) * 8u, Mb + (size_t)rowid[r] * W + cc * 2);
+      if (NCH == 2) t_cp_async16(smem_u32(Sa) + (uint32_t)(r * RS + cc * 2) * 8u, Ma + (size_t)rowid[r] * W + cc * 2);
+    }
+    load_B(0, 0);
+    t_cp_async_commit();
+    if (NKC > 1) {
+      load_B(1, 1);
+      t_cp_async_commit();
+    }
+  }
+
+  const int wm = warp & 3, wn = warp >> 2; // 4 x 2 warps, warp tile 32 x (W / 2)
+  const int g = lane >> 2, t = lane & 3;
+  double acc[4][NT][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const uint32_t sa_base = smem_u32(Sa), sb_base = smem_u32(Sb);
+  double ma[4] = {1.0, 1.0, 1.0, 1.0};
+
+  for (int kc = 0; kc < NKC; ++kc) {
+    if (kc + 2 < NKC) {
+      load_B((kc + 2) % TSTAGES, kc + 2);
+      t_cp_async_commit();
+      t_cp_async_wait<2>();
+    } else if (kc + 1 < NKC) {
+      t_cp_async_wait<1>();
+    } else {
+      t_cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int a = kc / BCHUNKS, b0 = (kc % BCHUNKS) * TBK;
+    if (NCH == 2 && (kc % BCHUNKS) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ma[i] = lds64(sa_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + a) * 8u);
+    }
+    const uint32_t b_st = bs_base + (uint32_t)((kc % TSTAGES) * B_STAGE_D) * 8u;
+#pragma unroll
+    for (int k4 = 0; k4 < TBK / 4; ++k4) {
+      double af[4], bf[NT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double mb = lds64(sb_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + b0 + k4 * 4 + t) * 8u);
+        af[i] = (NCH == 2) ? ma[i] * mb : mb;
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = lds64(b_st + (uint32_t)((k4 * (W / 8) + wn * NT + j) * 32 + lane) * 8u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm * 32 + i * 8 + g;
+    if (row0 + r < row_end) {
+      double* dst = Mout + (size_t)rowid[r] * W + wn * (W / 2) + 2 * t;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) *reinterpret_cast<double2*>(dst + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
+// root: parent dimension 1.  One warp per point.
+//   NCH == 2: value = sum_a M_a[a] * (sum_b T_d[a][b] M_b[b]);  NCH == 1: value = sum_a M_c[a] T_d[a];  NCH == 0: T_d.
+__global__ void tree_root_kernel(int nch, const double* __restrict__ Ma, const double* __restrict__ Mb,
+                                 const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
+                                 const double* __restrict__ T, int W, double* __restrict__ out,
+                                 double* __restrict__ partial, int do_sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  double v = 0.0;
+  bool live = false;
+  if (warp < pc && p0 + warp < npts) {
+    live = true;
+    const int d = sl[warp];
+    if (nch == 0) {
+      v = T[d];
+    } else if (nch == 1) {
+      const double* Td = T + (size_t)d * W;
+      for (int a = lane; a < W; a += 32) v = fma(Mb[(size_t)warp * W + a], __ldg(Td + a), v);
+    } else {
+      const double* Td = T + (size_t)d * W * W;
+      const double* mb = Mb + (size_t)warp * W;
+      for (int a = lane; a < W; a += 32) {
+        double s = 0.0;
+        for (int b = 0; b < W; ++b) s = fma(__ldg(Td + (size_t)a * W + b), mb[b], s);
+        v = fma(Ma[(size_t)warp * W + a], s, v);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0 && out) out[p0 + warp] = v;
+  }
+  if (do_sum) {
+    __shared__ double sh[8];
+    if (lane == 0) sh[threadIdx.x >> 5] = live ? v : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sh[k];
+      partial[2 * blockIdx.x] = a;
+      partial[2 * blockIdx.x + 1] = 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
+  p->tgemm_ok = false;
+  const int n = d->n_vertices;
+  if (d->is_complex || n < 2) return TTN_OK; // real networks only (for now)
+  int maxchi = 1;
+  for (int v = 0; v < n; ++v) {
+    maxchi = std::max(maxchi, d->link_dim[v]);
+    if (p->child_ptr[v + 1] - p->child_ptr[v] > 2 || p->nslices[v] > 8) return TTN_OK;
+  }
+  if (maxchi > 64) return TTN_OK;
+  const int W = maxchi <= 16 ? 16 : (maxchi <= 32 ? 32 : 64);
+  TreeGemmDev& g = p->tgemm;
+  g.n_vertices = n;
+  g.W = W;
+  g.root = d->root;
+  const double* T = reinterpret_cast<const double*>(d->tensors);
+  p->tg_frag_off.assign(n, 0);
+  std::vector<double> blob;
+  for (int v = 0; v < n; ++v) {
+    const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
+    const int ns = p->nslices[v];
+    const bool is_root = v == d->root;
+    const int pdim = d->link_dim[v];
+    const int ca = nch >= 1 ? d->link_dim[p->child[p->child_ptr[v]]] : 1;
+    const int cb = nch == 2 ? d->link_dim[p->child[p->child_ptr[v] + 1]] : 1;
+    p->tg_frag_off[v] = (int64_t)blob.size();
+    const double* Tv = T + d->tensor_ptr[v];
+    if (is_root) {
+      // plain padded layout [slice][a][b] (b only for two children), parent dim 1
+      const size_t per = nch == 2 ? (size_t)W * W : (nch == 1 ? (size_t)W : 1);
+      std::vector<double> R(per * ns, 0.0);
+      for (int s = 0; s < ns; ++s) {
+        if (nch == 0) R[s] = Tv[s];
+        else if (nch == 1)
+          for (int a = 0; a < ca; ++a) R[(size_t)s * W + a] = Tv[(size_t)s * ca + a];
+        else
+          for (int a = 0; a < ca; ++a)
+            for (int b = 0; b < cb; ++b) R[((size_t)s * W + a) * W + b] = Tv[((size_t)s * ca + a) * cb + b];
+      }
+      blob.insert(blob.end(), R.begin(), R.end());
+    } else if (nch == 0) {
+      std::vector<double> L((size_t)ns * W, 0.0);
+      for (int s = 0; s < ns; ++s)
+        for (int j = 0; j < pdim; ++j) L[(size_t)s * W + j] = Tv[(size_t)s * pdim + j];
+      blob.insert(blob.end(), L.begin(), L.end());
+    } else {
+      // fragment order over K = (a, b) (or a) and N = parent index
+      const int K = nch == 2 ? W * W : W;
+      std::vector<double> E((size_t)K * W), F((size_t)ns * K * W, 0.0);
+      for (int s = 0; s < ns; ++s) {
+        std::fill(E.begin(), E.end(), 0.0);
+        if (nch == 2) {
+          for (int a = 0; a < ca; ++a)
+            for (int b = 0; b < cb; ++b)
+              for (int q = 0; q < pdim; ++q)
+                E[((size_t)a * W + b) * W + q] = Tv[(((size_t)s * ca + a) * cb + b) * pdim + q];
+        } else {
+          for (int a = 0; a < ca; ++a)
+            for (int q = 0; q < pdim; ++q) E[(size_t)a * W + q] = Tv[((size_t)s * ca + a) * pdim + q];
+        }
+        double* Fs = F.data() + (size_t)s * K * W;
+        for (int kb = 0; kb < K / 4; ++kb)
+          for (int nb = 0; nb < W / 8; ++nb)
+            for (int ln = 0; ln < 32; ++ln)
+              Fs[((size_t)kb * (W / 8) + nb) * 32 + ln] = E[(size_t)(4 * kb + (ln & 3)) * W + 8 * nb + (ln >> 2)];
+      }
+      blob.insert(blob.end(), F.begin(), F.end());
+    }
+  }
+  double* d_blob;
+  TTN_CUDA(cudaMalloc(&d_blob, std::max<size_t>(blob.size(), 2) * 8));
+  p->allocs.push_back(d_blob);
+  TTN_CUDA(cudaMemcpy(d_blob, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice));
+  g.blob = d_blob;
+  int32_t* d_ns;
+  TTN_CUDA(cudaMalloc(&d_ns, sizeof(int32_t) * n));
+  p->allocs.push_back(d_ns);
+  TTN_CUDA(cudaMemcpy(d_ns, p->nslices.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+  g.nslices = d_ns;
+  p->tgemm_ok = true;
+  return TTN_OK;
+}
+
+template <int W, int NCH>
+static int launch_vertex(const double* Ma, const double* Mb, double* Mout, const uint32_t* list, const int* cls_off,
+                         const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s) {
+  constexpr size_t smem = ((size_t)(NCH == 2 ? 2 : 1) * TBM * (W + 4) + (size_t)TSTAGES * TBK * W) * 8;
+  auto kern = tree_vertex_kernel<W, NCH>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = pc / TBM + nsl;
+  kern<<<grid, 256, smem, s>>>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl);
+  TTN_CUDA(cudaGetLastError());
+  return TTN_OK;
+}
+
+template <int W>
+static int launch_vertex_w(int nch, const double* Ma, const double* Mb, double* Mout, const uint32_t* list,
+                           const int* cls_off, const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s) {
+  return nch == 2 ? launch_vertex<W, 2>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s)
+                  : launch_vertex<W, 1>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s);
+}
+
+int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                     int* n_partial, cudaStream_t s, int* n_launches) {
+  *n_partial = 0;
+  if (src.npts == 0) return TTN_OK;
+  if (!p->tgemm_ok) {
+    set_error("tree GEMM kernel requested but the network is not a real tree with <= 2 children per vertex and chi <= 64");
+    return TTN_ERR_UNSUPPORTED;
+  }
+  const TreeGemmDev& g = p->tgemm;
+  const int n = g.n_vertices, W = g.W;
+  const int PC = (int)std::min<int64_t>(1 << 16, (src.npts + TBM - 1) / TBM * TBM);
+  const size_t msg_b = (size_t)PC * W * 8;
+  const size_t slices_b = ((size_t)n * PC + 255) / 256 * 256;
+  const size_t lists_b = (size_t)n * PC * 4;
+  const size_t offs_b = (size_t)n * 9 * 4 * 2 + 256;
+  const size_t need = (size_t)n * msg_b + slices_b + lists_b + offs_b;
+  if (st.gemm_bytes < need) {
+    if (st.d_gemm) cudaFree(st.d_gemm);
+    st.d_gemm = nullptr;
+    st.gemm_bytes = 0;
+    TTN_CUDA(cudaMalloc(&st.d_gemm, need));
+    st.gemm_bytes = need;
+  }
+  unsigned char* base = reinterpret_cast<unsigned char*>(st.d_gemm);
+  double* msgs = reinterpret_cast<double*>(base);
+  uint8_t* slices = base + (size_t)n * msg_b;
+  uint32_t* lists = reinterpret_cast<uint32_t*>(slices + slices_b);
+  int* cls_off = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lists) + lists_b);
+  int* tile_off = cls_off + (size_t)n * 9 + 16;
+  const int do_sum = d_partial != nullptr;
+  const int64_t n_chunks = (src.npts + PC - 1) / PC;
+  const int root_blocks = (PC * 32 + 255) / 256;
+  double* big_partial = nullptr;
+  if (do_sum) {
+    const size_t needp = sizeof(double) * 2 * (size_t)n_chunks * root_blocks;
+    if (st.partial2_bytes < needp) {
+      if (st.d_partial2) cudaFree(st.d_partial2);
+      st.d_partial2 = nullptr;
+      st.partial2_bytes = 0;
+      TTN_CUDA(cudaMalloc(&st.d_partial2, needp));
+      st.partial2_bytes = needp;
+    }
+    big_partial = st.d_partial2;
+  }
+  auto M = [&](int v) { return msgs + (size_t)v * PC * W; };
+  for (int64_t ck = 0; ck < n_chunks; ++ck) {
+    const int64_t p0 = ck * PC;
+    tree_digits_kernel<<<(PC + 255) / 256, 256, 0, s>>>(p->digits, src, p0, PC, n, slices, p->d_err);
+    tree_classify_kernel<<<n, 1024, 0, s>>>(slices, PC, g.nslices, lists, cls_off, tile_off);
+    *n_launches += 2;
+    for (int oi = 0; oi < n; ++oi) {
+      const int v = p->post[oi];
+      const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
+      const double* blob = g.blob + p->tg_frag_off[v];
+      const int ca = nch >= 1 ? p->child[p->child_ptr[v]] : -1;
+      const int cb = nch == 2 ? p->child[p->child_ptr[v] + 1] : -1;
+      if (v == g.root) {
+        tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
+                                                     slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out,
+                                                     do_sum ? big_partial + 2 * ck * root_blocks : nullptr, do_sum);
+      } else if (nch == 0) {
+        tree_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices + (size_t)v * PC, PC, blob, W, M(v));
+      } else {
+        const double* Ma = nch == 2 ? M(ca) : nullptr;
+        const double* Mb = nch == 2 ? M(cb) : M(ca);
+        int rc;
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
+        if (rc) return rc;
+      }
+      *n_launches += 1;
+    }
+    TTN_CUDA(cudaGetLastError());
+  }
+  if (do_sum) {
+    int rc = launch_sum_partials(p, big_partial, (int)(n_chunks * root_blocks), 1, d_partial, s);
+    if (rc) return rc;
+    *n_launches += 1;
+  }
+  *n_partial = do_sum ? 1 : 0;
+  return TTN_OK;
+}
+
+} // namespace ttn

@@ -180,6 +180,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   if ((rc = build_chain(p, d))) return rc;
   if ((rc = build_chain_mma(p, d))) return rc;
   if ((rc = build_chain_gemm(p, d))) return rc;
+  if (!p->is_chain && (rc = build_tree_gemm(p, d))) return rc;
 
   ttn_info& I = p->info;
   I.n_vertices = n;
@@ -195,10 +196,12 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
+  else if (p->tgemm_ok && max_link >= 12) I.auto_kernel = TTN_KERNEL_TREE;
   else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
-                        (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0) | (p->cgemm_ok ? (1 << TTN_KERNEL_GEMM) : 0);
+                        (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0) | (p->cgemm_ok ? (1 << TTN_KERNEL_GEMM) : 0) |
+                        (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
@@ -231,6 +234,12 @@ static void destroy_plan(ttn_plan* p) {
 static int run_kernel(ttn_plan* p, int kernel, Stream& st, const CoordSource& src, double* d_out,
                       double* d_partial, int* n_partial, int* extra_launches) {
   switch (kernel) {
+    case TTN_KERNEL_TREE: {
+      int nl = 0;
+      const int rc = launch_tree_gemm(p, st, src, d_out, d_partial, n_partial, st.s, &nl);
+      *extra_launches += nl - 1;
+      return rc;
+    }
     case TTN_KERNEL_GEMM: {
       int nl = 0;
       const int rc = launch_chain_gemm(p, st, src, d_out, d_partial, n_partial, st.s, &nl);
@@ -277,6 +286,8 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
+  if (kernel == TTN_KERNEL_TREE && !p->tgemm_ok)
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a real tree with <= 2 children per vertex, chi <= 64 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_GEMM && !p->cgemm_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GEMM: network is not a chain with 32 < (real-embedded) width <= 256 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)

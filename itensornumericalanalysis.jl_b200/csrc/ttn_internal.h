@@ -110,6 +110,13 @@ struct ChainGemmDev {
   const int32_t* pos_of_vertex;  // chain position of every vertex
 };
 
+// trees with <= 2 children per vertex as per-vertex (Khatri-Rao) GEMMs (k_tree_gemm.cu)
+struct TreeGemmDev {
+  int32_t n_vertices, W, root;
+  const double* blob;       // per-vertex images: leaf rows / B-fragment tensors / padded root tensor
+  const int32_t* nslices;   // [n_vertices]
+};
+
 struct Stream {
   cudaStream_t s = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;
@@ -148,6 +155,9 @@ struct ttn_plan {
   bool cmma_ok = false;
   ttn::ChainGemmDev cgemm{};
   bool cgemm_ok = false;
+  ttn::TreeGemmDev tgemm{};
+  bool tgemm_ok = false;
+  std::vector<int64_t> tg_frag_off;
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int* d_err = nullptr;    // domain-error flag
@@ -169,6 +179,9 @@ int launch_sum_partials(ttn_plan* p, const double* d_partial, int n_partial, int
 int build_chain(ttn_plan* p, const ttn_desc* d);
 int build_chain_mma(ttn_plan* p, const ttn_desc* d);
 int build_chain_gemm(ttn_plan* p, const ttn_desc* d);
+int build_tree_gemm(ttn_plan* p, const ttn_desc* d);
+int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                     int* n_partial, cudaStream_t s, int* n_launches);
 int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                       int* n_partial, cudaStream_t s, int* n_launches);
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,

@@ -39,6 +39,11 @@ def real_cases():
     dv = [with_site[i::3] for i in range(3)]
     s = t.continuous_siteinds(g, dv)
     out.append(("bintree4_chi5", t.rand_itn(s, link_space=5, rng=4, normalise=True), [1, 2, 3], 5))
+    # binary tree depth 5, chi = 20 (BASELINE config 3 layout; selects the tree GEMM kernel, W = 32)
+    g = t.named_binary_tree(5)
+    with_site = g.vertices()[1:]
+    s = t.continuous_siteinds(g, [with_site[i::3] for i in range(3)])
+    out.append(("bintree5_chi20_tree", t.rand_itn(s, link_space=20, rng=14, normalise=True), [1, 2, 3], 10))
     # random labelled trees (test/test_realitensorfunction.jl:129), arbitrary degree
     for seed in (5, 6):
         g = t.uniform_tree(9, rng=seed).rename_vertices(lambda v: (v, 1))

@@ -30,7 +30,7 @@ def coords_of(packed, pts):
 
 def kernels_for(plan):
     avail = plan.info()["kernels_available"]
-    return [n for n in ("generic", "chain", "dmma", "gemm") if avail & (1 << _capi.KERNEL_IDS[n])]
+    return [n for n in ("generic", "chain", "dmma", "gemm", "tree") if avail & (1 << _capi.KERNEL_IDS[n])]
 
 
 ALL_CASES = [(c, False) for c in cases.real_cases()] + [(c, True) for c in cases.complex_cases()]
@@ -76,6 +76,11 @@ def test_chain_cases_really_use_the_chain_kernel():
     for n in ("comb3x4_chi4", "bintree4_chi5", "cplx_comb3x3"):
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GENERIC, n
+    for n in ("bintree4_chi5", "bintree5_chi20_tree"):   # real, <= 2 children: tree GEMM path available
+        _, f, dims, _ = names[n]
+        assert f.plan(dims).info()["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE), n
+    _, f, dims, _ = names["bintree5_chi20_tree"]
+    assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_TREE
 
 
 @pytest.mark.parametrize("spec", GOLD["value_cases"], ids=lambda s: s["name"])

@@ -70,8 +70,9 @@ def test_oracle_vs_host_digits_and_dense(case):
         m = f.indsnetworkmap.calculate_ind_values(list(p), dims)
         assert [m[i] for i in packed.site_inds] == [int(x) for x in row]
     ref = orc.evaluate(packed, pts, orc.ORACLE_LD)
-    dense = orc.dense_evaluate(f, pts, dims)
-    assert orc.error_metric(dense, ref).max() < 1e-10
+    if len(packed.site_dim) <= 16:  # dense brute force (cf. build_full_rank_tensor, src/utils.jl:28-39) for L <= 16
+        dense = orc.dense_evaluate(f, pts, dims)
+        assert orc.error_metric(dense, ref).max() < 1e-10
     assert orc.error_metric(orc.evaluate(packed, pts, orc.ORACLE_F64), ref).max() < 1e-12
     bp = orc.evaluate(packed, pts, orc.ORACLE_BP)
     assert orc.error_metric(bp, ref).max() < 1e-9  # BP's exp(sum log) is the less accurate order
