@@ -399,7 +399,10 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
   }
   const ChainGemmDev& c = p->cgemm;
   const int W = c.W, n_pos = c.n_vertices;
-  const int PC = 1 << 16; // points per chunk: ~7 waves of 128x128 tiles per site at W = 256
+  // points per chunk: (PC/128 + nsl) * (W/128) tiles per site should fill a whole number of waves
+  const int nnb = W / GBN;
+  const int waves = nnb == 2 ? 7 : 4;
+  const int PC = (waves * p->sm_count / nnb - 8) * GBM;
   // workspace: two state buffers, slices, lists, offsets
   const size_t state_b = (size_t)PC * W * 8;
   const size_t slices_b = ((size_t)n_pos * PC + 255) / 256 * 256;
