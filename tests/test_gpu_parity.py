@@ -217,3 +217,61 @@ def test_fp64_peak_measurement():
     _capi.check(_capi.lib().ttn_measure_fp64_peak(0, C.byref(dfma), C.byref(dmma)))
     print(f"measured FP64 peaks: DFMA {dfma.value:.1f} TFLOP/s, DMMA {dmma.value:.1f} TFLOP/s")
     assert 5.0 < dfma.value < 100.0 and 1.0 < dmma.value < 200.0
+
+
+def test_full_size_config2_linearity_on_device():
+    """BASELINE configs[1] at its full size (10^8 points, device resident): linearity
+    (f + g)(x) == f(x) + g(x) with f + g evaluated by a different kernel instance (chi = 32)."""
+    import torch
+    g = t.named_comb_tree((2, 30))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    f1 = t.rand_itn(s, link_space=16, rng=17, normalise=True)
+    f2 = t.rand_itn(s, link_space=16, rng=18, normalise=True)
+    n = 100_000_000
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(5)
+    x = torch.rand((n, 2), dtype=torch.float64, device="cuda:0", generator=gen)
+    outs = []
+    for f in (f1, f2, f1 + f2):
+        o = torch.empty(n, dtype=torch.float64, device="cuda:0")
+        f.plan().evaluate_device(x.data_ptr(), n, o.data_ptr())
+        outs.append(o)
+    a, b, c = outs
+    ref = a + b
+    rms = torch.sqrt(torch.mean(ref * ref))
+    err = (c - ref).abs() / torch.maximum(ref.abs(), 1e-3 * rms)
+    # 99.99 % of 10^8 points within 1e-12; the extreme tail is FP64 cancellation noise (DESIGN "Accuracy")
+    assert torch.quantile(err[:: 16], 0.9999).item() < TOL
+    assert err.max().item() < 5e-11
+    # a host-evaluated slice is bitwise identical to the device-resident run
+    sl = slice(12_345_678, 12_345_678 + 100_000)
+    host, _ = f1.plan().evaluate_host(x[sl].cpu().numpy())
+    assert (host == a[sl].cpu().numpy()).all()
+
+
+def test_full_grid_config4_quadrature_identity():
+    """BASELINE config 4 at full size: the 2-D interleaved chi = 32 MPS evaluated on the whole
+    16384 x 16384 grid (grid_points generated on the device, no coordinate bytes), summed on the GPU,
+    against integrate(fitn; take_sum=true) (src/integration.jl:6-17) = the chain of (A[0] + A[1])."""
+    L = 28
+    s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=2)
+    f = t.rand_itn(s, link_space=32, rng=19, normalise=True)
+    n = 2 ** (L // 2)
+    xs = s.grid_points(n, 1)
+    assert len(xs) == n and xs[1] == 2.0 ** -(L // 2)
+    plan = f.plan()
+    _, o = plan.evaluate_grid([xs[1], xs[1]], [n, n], want_values=False, reduce_sum=True)
+    # integrate identity on the CPU in extended precision
+    tn = f.itensornetwork
+    verts = tn.vertices()
+    vec = None
+    for i, v in enumerate(verts):
+        site = f.indsnetworkmap[v][0]
+        links = [tn.link(v, u) for u in tn.graph.neighbors(v)]
+        left = [l for l in links if i > 0 and l == tn.link(v, verts[i - 1])]
+        right = [l for l in links if i < len(verts) - 1 and l == tn.link(v, verts[i + 1])]
+        arr = tn[v].permute([site] + left + right).array.astype(np.longdouble).sum(axis=0)
+        vec = arr if vec is None else vec @ arr
+    want = float(vec)
+    assert abs(o.sum_out[0] - want) <= 1e-10 * max(abs(want), 1.0) * 2 ** 14  # sum of 2^28 O(1) terms
+    print(f"grid sum {o.sum_out[0]!r} vs integrate identity {want!r}; kernel {o.kernel_ms:.1f} ms")
