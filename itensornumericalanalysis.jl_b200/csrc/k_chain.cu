@@ -378,11 +378,7 @@ static int launch_inst(ttn_plan* p, const CoordSource& src, double* d_out, doubl
   }
   const size_t smem = (size_t)n_stage * STAGE;
   auto kern = chain_kernel<CHI, NSL, CPLX, NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget)));
-    attr_set = true;
-  }
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_budget)));
   const int64_t n_tiles = (src.npts + NT - 1) / NT;
   const int grid = (int)std::min<int64_t>(n_tiles, p->sm_count);
   const int do_sum = d_partial != nullptr;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(1024)
   const int site = blockIdx.x; // middle site index t (position t + 1)
   const uint8_t* sl = slices + (size_t)(site + 1) * pc;
   uint32_t* list = lists + (size_t)site * pc;
-  __shared__ int cnt[8], start[8], cursor[8];
+  __shared__ int cnt[8], cursor[8];
   if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < pc; i += blockDim.x) atomicAdd(&cnt[sl[i]], 1);
@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) {
     int run = 0, trun = 0;
     for (int c = 0; c < nsl; ++c) {
-      start[c] = run;
       cursor[c] = run;
       cls_off[site * 8 + c] = run;
       tile_off[site * 8 + c] = trun;
@@ -378,11 +377,7 @@ static int launch_site(const double* Sin, double* Sout, const uint32_t* list, co
                        const double* frags, int nsl, int pc, cudaStream_t s) {
   constexpr size_t smem = (size_t)GSTAGES * (GBM * GA_STRIDE + (GBK / 4) * (GBN / 8) * 32) * 8;
   auto kern = gemm_site_kernel<W>;
-  static bool attr = false;
-  if (!attr) {
-    TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (pc / GBM + nsl) * (W / GBN); // upper bound on the number of tiles
   kern<<<grid, 256, smem, s>>>(Sin, Sout, list, cls_off, tile_off, frags, nsl);
   TTN_CUDA(cudaGetLastError());

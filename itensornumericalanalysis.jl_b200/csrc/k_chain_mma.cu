@@ -694,11 +694,11 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
 #pragma unroll 8
           for (int j = 0; j < P / 32; ++j) {
             const int cls = (int)((cache >> (2 * j)) & 3);
-            const int B0 = __shfl_sync(0xffffffffu, b0, j), B1 = __shfl_sync(0xffffffffu, b1, j);
-            const int B2 = __shfl_sync(0xffffffffu, b2, j), B3 = __shfl_sync(0xffffffffu, b3, j);
+            const int pb0 = __shfl_sync(0xffffffffu, b0, j), pb1 = __shfl_sync(0xffffffffu, b1, j);
+            const int pb2 = __shfl_sync(0xffffffffu, b2, j), pb3 = __shfl_sync(0xffffffffu, b3, j);
             const uint32_t M0 = __shfl_sync(0xffffffffu, mk0, j), M1 = __shfl_sync(0xffffffffu, mk1, j);
             const uint32_t M2 = __shfl_sync(0xffffffffu, mk2, j), M3 = __shfl_sync(0xffffffffu, mk3, j);
-            const int B = cls == 0 ? B0 : (cls == 1 ? B1 : (cls == 2 ? B2 : B3));
+            const int B = cls == 0 ? pb0 : (cls == 1 ? pb1 : (cls == 2 ? pb2 : pb3));
             const uint32_t M = cls == 0 ? M0 : (cls == 1 ? M1 : (cls == 2 ? M2 : M3));
             list[B + __popc(M & lt)] = (uint16_t)(j * 32 + lane);
           }

@@ -3,7 +3,7 @@
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["TTN_MMA_VARIANT"] = "5"
+os.environ.pop("TTN_MMA_VARIANT", None)
 import itna_b200 as t
 from itna_b200 import _capi
 _capi.LIB_PATH = os.path.join(ROOT, "scripts", "microbench", os.environ.get("TTN_DBG_LIB", "libttneval_dbg.so"))
