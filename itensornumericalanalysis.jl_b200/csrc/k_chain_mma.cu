@@ -407,11 +407,12 @@ __device__ __forceinline__ void site_mma(double (&dst)[NBAT][CHI / 4], const dou
 // are no register moves between sites.
 template <int CHI, int NBAT>
 __device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&rows)[4], int tq,
-                                               uint32_t stage_base, const int (&boff)[4], int sites) {
+                                               uint32_t stage_base, const int (&boff)[4], int sites, int pad_row) {
   constexpr int NB = CHI / 8, KB = CHI / 4;
   double t0[NBAT][KB], t1[NBAT][KB];
 #pragma unroll
   for (int b = 0; b < NBAT; ++b) {
+    // class padding slots read the scratch row (all zeros, never written: the stores below skip it)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
@@ -428,15 +429,19 @@ __device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&
     site_mma<CHI, NBAT>(t1, t0, stage_base + (uint32_t)boff[s]);
 #pragma unroll
     for (int b = 0; b < NBAT; ++b)
+      if (rows[b] != pad_row) {
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t1[b][2 * nb], t1[b][2 * nb + 1]);
+        for (int nb = 0; nb < NB; ++nb)
+          sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t1[b][2 * nb], t1[b][2 * nb + 1]);
+      }
   } else {
 #pragma unroll
     for (int b = 0; b < NBAT; ++b)
+      if (rows[b] != pad_row) {
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
-        sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t0[b][2 * nb], t0[b][2 * nb + 1]);
+        for (int nb = 0; nb < NB; ++nb)
+          sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), t0[b][2 * nb], t0[b][2 * nb + 1]);
+      }
   }
 }
 
@@ -840,10 +845,10 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
 #pragma unroll
             for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gnext + b, gend - 1) << 3) + g];
           }
-          if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-          else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-          else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-          else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites);
+          if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites, P);
+          else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites, P);
+          else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites, P);
+          else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites, P);
           gi = gnext;
         }
       }
@@ -1234,10 +1239,10 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
 #pragma unroll
               for (int b = 0; b < 4; ++b) rows_nx[b] = (int)list[(min(gnext + b, gend - 1) << 3) + g];
             }
-            if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-            else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-            else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites);
-            else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites);
+            if (nbat >= 4 && GB >= 4) process_batch5<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, stage_base, boff, sites, PW);
+            else if (nbat == 3 && GB >= 3) process_batch5<CHI, (GB >= 3 ? 3 : 1)>(state_base, rows, tq, stage_base, boff, sites, PW);
+            else if (nbat == 2 && GB >= 2) process_batch5<CHI, (GB >= 2 ? 2 : 1)>(state_base, rows, tq, stage_base, boff, sites, PW);
+            else process_batch5<CHI, 1>(state_base, rows, tq, stage_base, boff, sites, PW);
             gi = gnext;
           }
         }
