@@ -23,6 +23,7 @@
 // Complex networks are embedded as real ones of twice the width: row = [re | im],
 // M -> [[Re, Im], [-Im, Re]]: exactly the 8 flops per complex MAC of the flop rule.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "k_async.cuh"
@@ -1069,7 +1070,24 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
             }
           }
         }
-        if (B2) {
+        if (B2 && ch.run_L[c] > 0) {
+          // whole coordinate at once: digits = bits of floor(x * 2^L) (exact; see build_chain_mma),
+          // placed as one run of L consecutive stream positions
+          const int L = ch.run_L[c], plow = ch.run_plow[c];
+          const double scale = ch.run_scale[c];
+          const bool rev = ch.run_rev[c] != 0;
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+            if (rev) q = __brevll(q) >> (64 - L);
+            if (plow < 64) {
+              w0[k] += q << plow;
+              if (plow + L > 64) w1[k] += q >> (64 - plow);
+            } else {
+              w1[k] += q << (plow - 64);
+            }
+          }
+        } else if (B2) {
           // base 2: the greedy loop is one compare + one subtract (no divergence), 4 points in flight
           for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
             const Digit2 e = s_d2[e_i];
@@ -1493,6 +1511,42 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     p->allocs.push_back(d_ent);
     TTN_CUDA(cudaMemcpy(d_ent, ent.data(), sizeof(DigitEntry) * d->n_sites, cudaMemcpyHostToDevice));
     p->digits_mma.entries = d_ent;
+  }
+  // K1 "run" fast path per coordinate slot.  Conditions (all checked here, bitwise):
+  //   every site index of the slot is binary, its vertex carries no other site index (1 bit per
+  //   chain position), the digit numbers are exactly 1..L with thresholds exactly 2^-k, L <= 63, and
+  //   the digits sit on CONSECUTIVE chain positions in increasing or decreasing order.
+  // Then the greedy loop (abstractindexmap.jl:121-138) yields digit k = bit (L-k) of floor(x * 2^L):
+  // x >= 2^-k ? subtract : keep is exact in binary floating point (the subtraction clears the leading
+  // bit), the scaling by 2^L is exact, and x >= 1 saturates to all ones exactly as the loop does.
+  for (int cidx = 0; cidx < TTN_MAX_COORDS; ++cidx) c.run_L[cidx] = 0;
+  if (bits == 1) {
+    std::vector<int32_t> cptr(d->n_coords + 1);
+    std::vector<DigitEntry> ent(std::max(d->n_sites, 1));
+    TTN_CUDA(cudaMemcpy(cptr.data(), p->digits_mma.coord_ptr, sizeof(int32_t) * (d->n_coords + 1), cudaMemcpyDeviceToHost));
+    if (d->n_sites > 0)
+      TTN_CUDA(cudaMemcpy(ent.data(), p->digits_mma.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
+    for (int cidx = 0; cidx < d->n_coords; ++cidx) {
+      const int L = cptr[cidx + 1] - cptr[cidx];
+      if (L < 1 || L > 63) continue;
+      bool ok = true;
+      int step = 0, first_pos = -1;
+      for (int k = 0; k < L && ok; ++k) {
+        const DigitEntry& e = ent[cptr[cidx] + k];
+        const int pos = e.word * per_word + e.shift;
+        ok = ok && e.base == 2 && e.stride == 1 && p->nslices[e.vertex] == 2;
+        ok = ok && d->site_digit[e.site] == k + 1 && d->thr[e.thr_off + 1] == std::ldexp(1.0, -(k + 1));
+        if (k == 0) first_pos = pos;
+        else if (k == 1) step = pos - first_pos;
+        if (k >= 1) ok = ok && (pos - first_pos == step * k);
+      }
+      if (L == 1) step = 1;
+      if (!ok || (step != 1 && step != -1)) continue;
+      c.run_L[cidx] = L;
+      c.run_rev[cidx] = step == 1 ? 1 : 0;
+      c.run_plow[cidx] = step == 1 ? first_pos : first_pos - (L - 1);
+      c.run_scale[cidx] = std::ldexp(1.0, L);
+    }
   }
   p->cmma_ok = true;
   return TTN_OK;

@@ -96,6 +96,11 @@ struct ChainMmaDev {
   int32_t nout;     // 1 (real) or 2 (re, im)
   int32_t bits, per_word, n_words;
   int32_t root_pos; // position of the root in the packed slice stream (after identity padding)
+  // per coordinate slot: "run" fast path of K1 (see build_chain_mma): L == 0 -> use the table loop
+  int32_t run_L[TTN_MAX_COORDS];     // number of binary digits
+  int32_t run_plow[TTN_MAX_COORDS];  // lowest stream position of the run
+  int32_t run_rev[TTN_MAX_COORDS];   // 1: digit 1 at the LOWEST position (bit-reversed placement)
+  double run_scale[TTN_MAX_COORDS];  // 2^L
   const double* leaf;  // [nsl][chi]
   const double* root;  // [nout][nsl][chi]
   const double* frags; // [n_steps][nsl][chi*chi], B-fragment order

@@ -275,3 +275,27 @@ def test_full_grid_config4_quadrature_identity():
     want = float(vec)
     assert abs(o.sum_out[0] - want) <= 1e-10 * max(abs(want), 1.0) * 2 ** 14  # sum of 2^28 O(1) terms
     print(f"grid sum {o.sum_out[0]!r} vs integrate identity {want!r}; kernel {o.kernel_ms:.1f} ms")
+
+
+def test_digit_run_fast_path_edge_cases():
+    """The DMMA chain kernel replaces the greedy loop by bits of floor(x * 2^L) when a coordinate's
+    binary digits sit on consecutive chain positions (comb teeth, config 2 layout).  Any digit
+    mismatch changes the value by O(1); exercise the boundaries of every digit, denormals, x >= 1."""
+    L = 30
+    g = t.named_comb_tree((2, L))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, L + 1)] for i in (1, 2)])
+    f = t.rand_itn(s, link_space=16, rng=21, normalise=True)
+    plan = f.plan()
+    assert plan.info()["auto_kernel"] == _capi.TTN_KERNEL_DMMA
+    xs = [0.0, -0.0, 5e-324, 2.0 ** -1074, 2.0 ** -31, 2.0 ** -30, np.nextafter(2.0 ** -30, 1), 1 - 2.0 ** -53,
+          1 - 2.0 ** -30, np.nextafter(1 - 2.0 ** -30, 0), 1.0, 1.0 + 2.0 ** -52, 7.25, 1e300, 0.1, 1 / 3, 2 / 3]
+    for k in range(1, L + 1):
+        xs += [2.0 ** -k, np.nextafter(2.0 ** -k, 0), np.nextafter(2.0 ** -k, 1), 1 - 2.0 ** -k]
+    xs = np.array(xs)
+    pts = np.stack([xs, xs[::-1]], axis=1)
+    pts = np.concatenate([pts, np.stack([xs, np.roll(xs, 7)], axis=1)])
+    ref = orc.evaluate(plan.packed, pts, orc.ORACLE_LD)
+    assert (plan.digits_host(pts) == orc.digits(plan.packed, pts)).all()
+    for k in ("dmma", "chain", "generic"):
+        got, _ = plan.evaluate_host(pts, kernel=k)
+        assert orc.error_metric(got, ref).max() < TOL, k
