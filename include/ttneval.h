@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TTN_ABI_VERSION 1
+#define TTN_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------ */
 enum {
@@ -59,6 +59,16 @@ enum {
 enum {
   TTN_MEM_HOST = 0,  /* host pointers; H2D / D2H copies happen inside the call */
   TTN_MEM_DEVICE = 1 /* device pointers on the plan's device; no copies */
+};
+
+/* ---- fused quadrature functionals: what is accumulated over the evaluated points.
+ * With the grid generator these generalise integrate() (src/integration.jl:6-32) to functionals a
+ * pure contraction cannot express. */
+enum {
+  TTN_REDUCE_NONE = 0,
+  TTN_REDUCE_SUM = 1,      /* sum_p f(p)                      (integrate(...; take_sum=true)) */
+  TTN_REDUCE_ABS2 = 2,     /* sum_p |f(p)|^2                  -> sum_out[0] */
+  TTN_REDUCE_WEIGHTED = 3  /* sum_p w[p] * f(p), w real, one weight per point (opts->weights) */
 };
 
 /* ---- kernel selection --------------------------------------------------- */
@@ -131,8 +141,8 @@ typedef struct ttn_opts {
   int32_t coords_mem;   /* TTN_MEM_* */
   int32_t out_mem;      /* TTN_MEM_* */
   int32_t kernel;       /* TTN_KERNEL_* (AUTO = planner's choice) */
-  int32_t reduce_sum;   /* 0: write one value per point to out; 1: also/only accumulate the sum
-                           of all values into sum_out (out may then be NULL) */
+  int32_t reduce_sum;   /* TTN_REDUCE_*: 0 = write one value per point to out; otherwise also/only accumulate
+                           the chosen functional into sum_out (out may then be NULL) */
   int64_t chunk_points; /* 0 = auto; host-memory calls are pipelined in chunks of this many points */
   /* outputs */
   double sum_out[2];    /* (re, im) of the sum when reduce_sum != 0 */
@@ -141,6 +151,10 @@ typedef struct ttn_opts {
   float total_ms;       /* device time of the whole call incl. copies (events) */
   int32_t kernel_used;  /* TTN_KERNEL_* actually run */
   int32_t n_launches;   /* kernels launched by this call */
+  /* inputs (appended in ABI 2) */
+  const double* weights; /* TTN_REDUCE_WEIGHTED: npts weights, in the memory space weights_mem */
+  int32_t weights_mem;   /* TTN_MEM_* */
+  int32_t reserved_;
 } ttn_opts;
 
 /* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:

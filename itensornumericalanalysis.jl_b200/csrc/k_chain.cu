@@ -206,8 +206,7 @@ __global__ void __launch_bounds__(NT + 32, 1)
           out[p] = vr;
         }
       }
-      sum_re += vr;
-      sum_im += vi;
+      accumulate_point(src, p, vr, vi, sum_re, sum_im);
     }
   }
 

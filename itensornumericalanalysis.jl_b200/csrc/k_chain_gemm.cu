@@ -93,7 +93,7 @@ __global__ void gemm_leaf_kernel(const uint8_t* __restrict__ slices, int pc, con
 __global__ void gemm_root_kernel(const uint8_t* __restrict__ slices_root, int pc, int64_t p0, int64_t npts,
                                  const double* __restrict__ root, int W, int nsl, int nout, int n_vertices,
                                  const double* __restrict__ S, double* __restrict__ out, double* __restrict__ partial,
-                                 int do_sum) {
+                                 int do_sum, CoordSource src) {
   // one warp per point
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   double o0 = 0.0, o1 = 0.0;
@@ -126,8 +126,10 @@ __global__ void gemm_root_kernel(const uint8_t* __restrict__ slices_root, int pc
     __shared__ double sh[2][8];
     const int w = threadIdx.x >> 5;
     if (lane == 0) {
-      sh[0][w] = live ? o0 : 0.0;
-      sh[1][w] = live ? o1 : 0.0;
+      double a0 = 0.0, a1 = 0.0;
+      if (live) accumulate_point(src, p0 + warp, o0, o1, a0, a1);
+      sh[0][w] = a0;
+      sh[1][w] = a1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -453,7 +455,7 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
     }
     gemm_root_kernel<<<root_blocks, 256, 0, s>>>(slices + (size_t)(n_pos - 1) * pc, pc, p0, src.npts, c.root, W, c.nsl,
                                                  c.nout, c.n_vertices, Sin, d_out, do_sum ? big_partial + 2 * ck * root_blocks : nullptr,
-                                                 do_sum);
+                                                 do_sum, src);
     *n_launches += 1;
     TTN_CUDA(cudaGetLastError());
   }

@@ -352,8 +352,7 @@ __global__ void __launch_bounds__(NTH * NH + 32 * NH, 1)
           if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
           else out[p] = o0;
         }
-        sum_re += o0;
-        sum_im += o1;
+        accumulate_point(src, p, o0, o1, sum_re, sum_im);
       }
     }
     // the next tile's leaf writes touch only rows owned by the writing thread, and the list /
@@ -886,8 +885,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
           if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
           else out[p] = o0;
         }
-        sum_re += o0;
-        sum_im += o1;
+        accumulate_point(src, p, o0, o1, sum_re, sum_im);
       }
     }
     __syncwarp();
@@ -1308,8 +1306,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
             if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
             else out[p] = o0;
           }
-          sum_re += o0;
-          sum_im += o1;
+          accumulate_point(src, p, o0, o1, sum_re, sum_im);
         }
       }
       __syncwarp();

@@ -38,6 +38,22 @@ __device__ __forceinline__ int greedy_digit(double& x, const double* __restrict_
   return v;
 }
 
+// Fused quadrature functional of one evaluated point.
+__device__ __forceinline__ void accumulate_point(const CoordSource& src, int64_t p, double vr, double vi, double& sr,
+                                                 double& si) {
+  if (src.reduce_mode == TTN_REDUCE_ABS2) {
+    sr = fma(vr, vr, sr);
+    sr = fma(vi, vi, sr);
+  } else if (src.reduce_mode == TTN_REDUCE_WEIGHTED) {
+    const double w = __ldg(src.weights + p);
+    sr = fma(w, vr, sr);
+    si = fma(w, vi, si);
+  } else {
+    sr += vr;
+    si += vi;
+  }
+}
+
 // Domain check: the reference never terminates for x < 0 or NaN; we flag it.
 __device__ __forceinline__ bool coord_in_domain(double x) { return x >= 0.0; }
 

@@ -128,8 +128,7 @@ __global__ void __launch_bounds__(256)
         out[p] = vr;
       }
     }
-    sum_re += vr;
-    sum_im += vi;
+    accumulate_point(src, p, vr, vi, sum_re, sum_im);
   }
   if (do_sum) {
     __shared__ double sh[2][256];

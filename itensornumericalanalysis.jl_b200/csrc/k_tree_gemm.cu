@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256, 1)
 __global__ void tree_root_kernel(int nch, const double* __restrict__ Ma, const double* __restrict__ Mb,
                                  const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
                                  const double* __restrict__ T, int W, double* __restrict__ out,
-                                 double* __restrict__ partial, int do_sum) {
+                                 double* __restrict__ partial, int do_sum, CoordSource src) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   double v = 0.0;
   bool live = false;
@@ -241,7 +241,11 @@ __global__ void tree_root_kernel(int nch, const double* __restrict__ Ma, const d
   }
   if (do_sum) {
     __shared__ double sh[8];
-    if (lane == 0) sh[threadIdx.x >> 5] = live ? v : 0.0;
+    if (lane == 0) {
+      double a0 = 0.0, a1 = 0.0;
+      if (live) accumulate_point(src, p0 + warp, v, 0.0, a0, a1);
+      sh[threadIdx.x >> 5] = a0;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       double a = 0;
@@ -416,7 +420,7 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
       if (v == g.root) {
         tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
                                                      slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out,
-                                                     do_sum ? big_partial + 2 * ck * root_blocks : nullptr, do_sum);
+                                                     do_sum ? big_partial + 2 * ck * root_blocks : nullptr, do_sum, src);
       } else if (nch == 0) {
         tree_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices + (size_t)v * PC, PC, blob, W, M(v));
       } else {

@@ -215,6 +215,7 @@ static void destroy_plan(ttn_plan* p) {
     if (st.s) cudaStreamSynchronize(st.s);
     if (st.d_coords) cudaFree(st.d_coords);
     if (st.d_out) cudaFree(st.d_out);
+    if (st.d_weights) cudaFree(st.d_weights);
     if (st.d_work) cudaFree(st.d_work);
     if (st.d_partial) cudaFree(st.d_partial);
     if (st.d_gemm) cudaFree(st.d_gemm);
@@ -265,6 +266,9 @@ static int ensure_stream_buffers(ttn_plan* p, Stream& st, int64_t chunk, bool ne
     st.cap_points = 0;
     TTN_CUDA(cudaMalloc(&st.d_coords, std::max<size_t>(16, sizeof(double) * (size_t)chunk * std::max(p->info.n_coords, 1))));
     TTN_CUDA(cudaMalloc(&st.d_out, sizeof(double) * (size_t)chunk * NC));
+    if (st.d_weights) cudaFree(st.d_weights);
+    st.d_weights = nullptr;
+    TTN_CUDA(cudaMalloc(&st.d_weights, sizeof(double) * (size_t)chunk));
     st.cap_points = chunk;
   }
   const size_t pc = (size_t)2 * (p->sm_count * 8 + 8);
@@ -294,7 +298,10 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_DMMA: network is not a chain with chi <= 32 (real) / 16 (complex), <= 4 slices per vertex and <= 128 slice bits");
   const bool coords_host = !base.grid && opts->coords_mem == TTN_MEM_HOST;
   const bool out_host = out != nullptr && opts->out_mem == TTN_MEM_HOST;
-  const bool do_sum = opts->reduce_sum != 0;
+  const bool do_sum = opts->reduce_sum != TTN_REDUCE_NONE;
+  if (opts->reduce_sum < 0 || opts->reduce_sum > TTN_REDUCE_WEIGHTED) return fail(TTN_ERR_INVALID, "bad reduce mode");
+  if (opts->reduce_sum == TTN_REDUCE_WEIGHTED && !opts->weights) return fail(TTN_ERR_INVALID, "TTN_REDUCE_WEIGHTED needs opts->weights");
+  const bool weights_host = opts->reduce_sum == TTN_REDUCE_WEIGHTED && opts->weights_mem == TTN_MEM_HOST;
   opts->sum_out[0] = opts->sum_out[1] = 0.0;
   opts->kernel_ms = opts->total_ms = 0.f;
   opts->kernel_used = kernel;
@@ -309,7 +316,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
 
   int64_t chunk = npts;
   int n_chunks = 1;
-  if (coords_host || out_host) {
+  if (coords_host || out_host || weights_host) {
     chunk = opts->chunk_points > 0 ? opts->chunk_points : (int64_t)1 << 22;
     chunk = std::min(chunk, npts);
     n_chunks = (int)((npts + chunk - 1) / chunk);
@@ -324,15 +331,25 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       if (e) cudaEventDestroy(e);
   };
   int rc = TTN_OK;
-  const int n_streams = (coords_host || out_host) ? 3 : 1;
+  const int n_streams = (coords_host || out_host || weights_host) ? 3 : 1;
   for (int ci = 0; ci < n_chunks && rc == TTN_OK; ++ci) {
     Stream& st = p->streams[ci % n_streams];
     const int64_t first = (int64_t)ci * chunk;
     const int64_t m = std::min(chunk, npts - first);
-    rc = ensure_stream_buffers(p, st, (coords_host || out_host) ? chunk : 1, coords_host, out_host);
+    rc = ensure_stream_buffers(p, st, (coords_host || out_host || weights_host) ? chunk : 1, coords_host, out_host);
     if (rc) break;
     CoordSource src = base;
     src.npts = m;
+    src.reduce_mode = opts->reduce_sum;
+    src.weights = nullptr;
+    if (opts->reduce_sum == TTN_REDUCE_WEIGHTED) {
+      if (weights_host) {
+        cudaMemcpyAsync(st.d_weights, opts->weights + first, sizeof(double) * m, cudaMemcpyHostToDevice, st.s);
+        src.weights = st.d_weights;
+      } else {
+        src.weights = opts->weights + first;
+      }
+    }
     if (base.grid) {
       src.first = base.first + first;
     } else if (coords_host) {

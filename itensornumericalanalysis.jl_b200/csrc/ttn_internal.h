@@ -55,6 +55,8 @@ struct CoordSource {
   int64_t first;        // grid: linear index of point 0 of this launch
   double step[TTN_MAX_COORDS];
   int64_t count[TTN_MAX_COORDS];
+  int32_t reduce_mode;   // TTN_REDUCE_* (what the kernels accumulate per point)
+  const double* weights; // TTN_REDUCE_WEIGHTED: device pointer, one weight per point of this launch
 };
 
 // ---- generic tree program (device) ---------------------------------------------------
@@ -127,6 +129,7 @@ struct Stream {
   cudaEvent_t k0 = nullptr, k1 = nullptr;
   double* d_coords = nullptr;
   double* d_out = nullptr;
+  double* d_weights = nullptr;
   int64_t cap_points = 0;
   double* d_work = nullptr; // generic-kernel workspace
   size_t work_bytes = 0;

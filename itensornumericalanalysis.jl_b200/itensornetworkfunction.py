@@ -60,12 +60,12 @@ class Plan:
         o = _capi.ttn_opts()
         o.coords_mem, o.out_mem = coords_mem, out_mem
         o.kernel = _capi.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel or 0)
-        o.reduce_sum = int(bool(reduce_sum))
+        o.reduce_sum = _capi.REDUCE_IDS[reduce_sum] if not isinstance(reduce_sum, (int, np.integer)) or isinstance(reduce_sum, bool) else int(reduce_sum)
         o.chunk_points = int(chunk_points)
         return o
 
     def evaluate_host(self, coords, layout=_capi.TTN_LAYOUT_AOS, kernel="auto", reduce_sum=False,
-                      want_values=True, chunk_points=0, out=None):
+                      want_values=True, chunk_points=0, out=None, weights=None):
         """coords: float64 array, (npts, n_coords) for AOS or (n_coords, npts) for SOA."""
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         nc = self.packed.n_coords
@@ -79,6 +79,11 @@ class Plan:
         elif want_values:
             out = np.empty(npts, dtype=dt)
         o = self._opts(kernel, reduce_sum, chunk_points=chunk_points)
+        if weights is not None:
+            weights = np.ascontiguousarray(weights, dtype=np.float64)
+            if weights.size != npts:
+                raise ValueError("weights must hold one real weight per point")
+            o.weights, o.weights_mem = weights.ctypes.data_as(C.c_void_p), _capi.TTN_MEM_HOST
         rc = _capi.lib().ttn_evaluate(
             self._h, coords.ctypes.data_as(C.c_void_p), npts, nc, layout,
             out.ctypes.data_as(C.c_void_p) if out is not None else None, C.byref(o))
@@ -239,18 +244,21 @@ def _points_to_coords(fitn, xs, dims):
 
 
 def evaluate(fitn: ITensorNetworkFunction, xs, dims=None, *, alg=None, device=0, kernel="auto",
-             reduce=None, return_opts=False):
+             reduce=None, weights=None, return_opts=False):
     """Evaluate `fitn` at one point or at a batch of points (see module docstring).
 
     reduce=None  -> values;  reduce="sum" -> the sum over all points (grid quadrature,
-    cf. integrate(...; take_sum=true), src/integration.jl:6-17).
+    cf. integrate(...; take_sum=true), src/integration.jl:6-17); reduce="abs2" -> sum |f|^2;
+    reduce="weighted" -> sum_p weights[p] * f(p) (fused quadrature functionals).
     `alg` is accepted for signature compatibility ("bp" and "exact" coincide on trees).
     """
     coords, dims, single = _points_to_coords(fitn, xs, dims)
     plan = fitn.plan(dims, device=device)
-    out, o = plan.evaluate_host(coords, kernel=kernel, reduce_sum=(reduce == "sum"),
-                                want_values=(reduce != "sum"))
-    if reduce == "sum":
+    out, o = plan.evaluate_host(coords, kernel=kernel, reduce_sum=reduce, want_values=(reduce is None),
+                                weights=weights)
+    if reduce == "abs2":
+        res = o.sum_out[0]
+    elif reduce is not None:
         res = complex(o.sum_out[0], o.sum_out[1]) if plan.packed.is_complex else o.sum_out[0]
     elif single:
         res = out[0].item()

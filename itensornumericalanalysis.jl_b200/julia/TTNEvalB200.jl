@@ -23,7 +23,7 @@ using NamedGraphs.GraphsExtensions: is_tree, leaf_vertices
 
 const LIBTTNEVAL = get(ENV, "LIBTTNEVAL", "libttneval.so")
 
-const TTN_ABI_VERSION = Int32(1)
+const TTN_ABI_VERSION = Int32(2)
 const TTN_LAYOUT_AOS = Int32(0)   # coords[c + n_coords*p]: a Julia (n_coords x npts) Matrix
 const TTN_MEM_HOST = Int32(0)
 
@@ -60,9 +60,12 @@ mutable struct TTNOpts
   total_ms::Float32
   kernel_used::Int32
   n_launches::Int32
+  weights::Ptr{Float64}
+  weights_mem::Int32
+  reserved_::Int32
 end
 TTNOpts(; reduce_sum=false) =
-  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, reduce_sum ? 1 : 0, 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0)
+  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, reduce_sum ? 1 : 0, 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, C_NULL, TTN_MEM_HOST, 0)
 
 "Flat arrays of one packed network; keeps everything the C side points at alive."
 struct PackedNetwork

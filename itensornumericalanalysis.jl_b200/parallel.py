@@ -22,7 +22,7 @@ def _default_evaluator(fitn, dims, device):
     plan = fitn.plan(dims, device=device)
 
     def run(coords, want_sum):
-        out, o = plan.evaluate_host(coords, reduce_sum=want_sum, want_values=not want_sum)
+        out, o = plan.evaluate_host(coords, reduce_sum=bool(want_sum), want_values=not want_sum)
         return out, complex(o.sum_out[0], o.sum_out[1])
 
     return run, plan.packed.is_complex

@@ -299,3 +299,28 @@ def test_digit_run_fast_path_edge_cases():
     for k in ("dmma", "chain", "generic"):
         got, _ = plan.evaluate_host(pts, kernel=k)
         assert orc.error_metric(got, ref).max() < TOL, k
+
+
+@pytest.mark.parametrize("which", ["mps2d_chi8", "mps2d_chi32", "mps2d_chi48_gemm", "bintree5_chi20_tree", "sin_qtt20",
+                                   "cplx_2site"])
+def test_fused_quadrature_functionals(which):
+    """sum |f|^2 and weighted sums fused into the evaluation kernels, every kernel."""
+    allc = {c[0]: (c, False) for c in cases.real_cases()}
+    allc.update({c[0]: (c, True) for c in cases.complex_cases()})
+    (name, f, dims, L), cplx = allc[which]
+    rng = np.random.default_rng(31)
+    pts = cases.complex_points(L, len(dims), rng, 700) if cplx else cases.edge_points(L, len(dims), rng, 900)
+    plan = f.plan(dims)
+    coords = coords_of(plan.packed, pts)
+    w = rng.standard_normal(len(coords))
+    for k in kernels_for(plan):
+        vals, _ = plan.evaluate_host(coords, kernel=k)
+        _, o = plan.evaluate_host(coords, kernel=k, reduce_sum="abs2", want_values=False, chunk_points=257)
+        want = float(np.sum(np.abs(vals) ** 2))
+        assert abs(o.sum_out[0] - want) <= 1e-12 * want, (k, "abs2")
+        _, o = plan.evaluate_host(coords, kernel=k, reduce_sum="weighted", weights=w, want_values=False, chunk_points=300)
+        got = complex(o.sum_out[0], o.sum_out[1])
+        want = complex(np.sum(w * vals))
+        assert abs(got - want) <= 1e-12 * float(np.sum(np.abs(w * vals))), (k, "weighted")
+    # public API
+    assert abs(t.evaluate(f, pts, dims, reduce="abs2") - float(np.sum(np.abs(vals) ** 2))) <= 1e-12 * float(np.sum(np.abs(vals) ** 2))
