@@ -199,6 +199,13 @@ int ttn_evaluate(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_c
  * (identity: sum over all b^L points == integrate(fitn; take_sum=true), src/integration.jl:6-17). */
 int ttn_evaluate_grid(ttn_plan* plan, const ttn_grid* grid, void* out_or_null, ttn_opts* opts);
 
+/* Evaluation at given index settings — the inner loop of TCI (ext/ITensorNumericalAnalysisTCIExt/tci_util.jl:21-55
+ * evaluates candidate pivots / fibres one index setting at a time) and the batched form of
+ * project() + scalar() (src/itensornetworkfunction.jl:84-106) without the coordinate -> digit step.
+ * index_values[p * n_sites + s] (uint8) = value of site index s of the description, 0 <= value < site_dim[s];
+ * memory space = opts->coords_mem.  Out-of-range values return TTN_ERR_INVALID. */
+int ttn_evaluate_indices(ttn_plan* plan, const uint8_t* index_values, int64_t npts, void* out, ttn_opts* opts);
+
 /* Digit decomposition only — batched calculate_ind_values (realindexmap.jl:67-76).
  * digits_out[p * n_sites + s] (uint8) = value chosen for site index s of the description. */
 int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coords,

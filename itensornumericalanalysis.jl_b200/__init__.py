@@ -14,7 +14,7 @@ from .indexmaps import (Index, IndsNetwork, RealIndexMap, ComplexIndexMap, IndsN
                         real_continuous_siteinds, complex_continuous_siteinds,
                         default_dimension_vertices, digit_siteinds, complex_digit_siteinds)
 from .network import Tensor, TensorNetwork, random_tensornetwork, add, multiply
-from .itensornetworkfunction import (ITensorNetworkFunction, evaluate, batched_ind_values, Plan,
+from .itensornetworkfunction import (ITensorNetworkFunction, evaluate, evaluate_indices, batched_ind_values, Plan,
                                      default_contraction_alg)
 from .elementary_functions import (const_itn, exp_itn, cosh_itn, sinh_itn, tanh_itn, cos_itn,
                                    sin_itn, rand_itn, delta_p, const_itensornetwork,

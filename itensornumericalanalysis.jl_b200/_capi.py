@@ -88,6 +88,7 @@ class ttn_info(C.Structure):
 
 EXPORTS = [
     "ttn_plan_create", "ttn_plan_destroy", "ttn_plan_info", "ttn_evaluate", "ttn_evaluate_grid",
+    "ttn_evaluate_indices",
     "ttn_digits", "ttn_measure_fp64_peak", "ttn_last_error", "ttn_device_count",
     "ttn_abi_version",
 ]
@@ -122,6 +123,8 @@ def lib():
     L.ttn_evaluate.restype = C.c_int
     L.ttn_evaluate_grid.argtypes = [vp, C.POINTER(ttn_grid), vp, C.POINTER(ttn_opts)]
     L.ttn_evaluate_grid.restype = C.c_int
+    L.ttn_evaluate_indices.argtypes = [vp, vp, C.c_int64, vp, C.POINTER(ttn_opts)]
+    L.ttn_evaluate_indices.restype = C.c_int
     L.ttn_digits.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, C.POINTER(ttn_opts)]
     L.ttn_digits.restype = C.c_int
     L.ttn_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]

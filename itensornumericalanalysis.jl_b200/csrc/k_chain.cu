@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(NT + 32, 1)
         }
         for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
           const DigitEntry e = dg.entries[k];
-          const int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+          const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
           const uint64_t b = (uint64_t)(v * e.stride) << e.shift;
           w0 += (e.word == 0) ? b : 0ull;
           w1 += (e.word == 1) ? b : 0ull;

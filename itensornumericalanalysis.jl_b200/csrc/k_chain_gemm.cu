@@ -42,7 +42,7 @@ __global__ void gemm_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, i
     }
     for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
       const DigitEntry e = dg.entries[k];
-      const int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+      const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
       slices[(size_t)pos_of_vertex[e.vertex] * pc + i] += (uint8_t)(v * e.stride);
     }
   }

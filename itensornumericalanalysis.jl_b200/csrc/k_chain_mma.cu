@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(NTH * NH + 32 * NH, 1)
           }
           for (int e_i = dg.coord_ptr[c]; e_i < dg.coord_ptr[c + 1]; ++e_i) {
             const DigitEntry e = dg.entries[e_i];
-            const int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+            const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
             const uint64_t b = (uint64_t)(v * e.stride) << e.shift;
             w0[k] += (e.word == 0) ? b : 0ull;
             w1[k] += (e.word == 1) ? b : 0ull;
@@ -449,7 +449,7 @@ __device__ __forceinline__ void process_batch5(uint32_t state_base, const int (&
 struct __align__(16) Digit2 {
   double thr1;   // |index_value_to_scalar(ind, 1)|
   uint32_t sh;   // shift inside the word
-  uint32_t wv;   // (word << 8) | stride
+  uint32_t wv;   // (site << 16) | (word << 8) | stride
 };
 
 // =====================================================================================
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
       Digit2 d2;
       d2.thr1 = dg.thr[e.thr_off + 1];
       d2.sh = (uint32_t)e.shift;
-      d2.wv = ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+      d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
       s_d2[i] = d2;
     }
   } else {
@@ -583,10 +583,11 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
             for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
               const Digit2 e = s_d2[e_i];
               const uint32_t stride = e.wv & 0xffu;
-              const bool hi = (e.wv >> 8) != 0;
+              const bool hi = ((e.wv >> 8) & 0xffu) != 0;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const bool ge = x[q] >= e.thr1;
+                const bool ge = src.digits ? (given_digit(src, tile * P + base + q * NDT, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                           : (x[q] >= e.thr1);
                 x[q] = __dsub_rn(x[q], ge ? e.thr1 : 0.0);
                 const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
                 if (hi) w1[q] += bb;
@@ -599,7 +600,8 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
               const double* thr = s_thr + e.thr_off;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const int v = greedy_digit_smem(x[q], thr, e.base);
+                const int v = src.digits ? given_digit(src, tile * P + base + q * NDT, dg.n_sites, e.site, e.base, err)
+                                         : greedy_digit_smem(x[q], thr, e.base);
                 const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
                 w0[q] += (e.word == 0) ? bb : 0ull;
                 w1[q] += (e.word == 1) ? bb : 0ull;
@@ -970,7 +972,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
       Digit2 d2;
       d2.thr1 = dg.thr[e.thr_off + 1];
       d2.sh = (uint32_t)e.shift;
-      d2.wv = ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+      d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
       s_d2[i] = d2;
     }
   } else {
@@ -1068,7 +1070,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
             }
           }
         }
-        if (B2 && ch.run_L[c] > 0) {
+        if (B2 && ch.run_L[c] > 0 && !src.digits) {
           // whole coordinate at once: digits = bits of floor(x * 2^L) (exact; see build_chain_mma),
           // placed as one run of L consecutive stream positions
           const int L = ch.run_L[c], plow = ch.run_plow[c];
@@ -1090,10 +1092,11 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
           for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
             const Digit2 e = s_d2[e_i];
             const uint32_t stride = e.wv & 0xffu;
-            const bool hi = (e.wv >> 8) != 0;
+            const bool hi = ((e.wv >> 8) & 0xffu) != 0;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-              const bool ge = x[k] >= e.thr1;
+              const bool ge = src.digits ? (given_digit(src, sub * PW + k * 32 + lane, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                         : (x[k] >= e.thr1);
               x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
               const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
               if (hi) w1[k] += bb;
@@ -1106,7 +1109,8 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
             const double* thr = s_thr + e.thr_off;
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-              const int v = greedy_digit_smem(x[k], thr, e.base);
+              const int v = src.digits ? given_digit(src, sub * PW + k * 32 + lane, dg.n_sites, e.site, e.base, err)
+                                       : greedy_digit_smem(x[k], thr, e.base);
               const uint64_t bb = (uint64_t)(v * e.stride) << e.shift;
               w0[k] += (e.word == 0) ? bb : 0ull;
               w1[k] += (e.word == 1) ? bb : 0ull;

@@ -12,6 +12,7 @@
 namespace ttn {
 
 __device__ __forceinline__ double load_coord(const CoordSource& src, int64_t p, int c) {
+  if (src.digits) return 0.0; // index-setting mode: no coordinates
   if (src.grid) {
     // grid_points (src/IndexMaps/realindexmap.jl:78-86): x = i * (a / b^L); Cartesian product over
     // the coordinate slots, slot 0 slowest.
@@ -35,6 +36,18 @@ __device__ __forceinline__ int greedy_digit(double& x, const double* __restrict_
     t = __ldg(thr + v);
   }
   x = __dsub_rn(x, t);
+  return v;
+}
+
+// Index-setting mode (the inner loop of TCI): the caller supplies the value of every
+// site index; out-of-range values are flagged (bit 1 of *err) instead of indexing past a tensor.
+__device__ __forceinline__ int given_digit(const CoordSource& src, int64_t p, int n_sites, int site, int base, int* err) {
+  if (p >= src.npts) return 0; // padding points of the last tile
+  int v = src.digits[p * n_sites + site];
+  if (v >= base) {
+    atomicOr(err, 2);
+    v = 0;
+  }
   return v;
 }
 

@@ -27,7 +27,7 @@ __global__ void digits_kernel(DigitTable dg, CoordSource src, uint8_t* __restric
     }
     for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
       DigitEntry e = dg.entries[k];
-      int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+      int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
       out[p * dg.n_sites + e.site] = (uint8_t)v;
     }
   }
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256)
       }
       for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
         DigitEntry e = dg.entries[k];
-        int v = greedy_digit(x, dg.thr + e.thr_off, e.base);
+        int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
         sl[(int64_t)e.vertex * T] += v * e.stride;
       }
     }

@@ -216,6 +216,7 @@ static void destroy_plan(ttn_plan* p) {
     if (st.d_coords) cudaFree(st.d_coords);
     if (st.d_out) cudaFree(st.d_out);
     if (st.d_weights) cudaFree(st.d_weights);
+    if (st.d_digits) cudaFree(st.d_digits);
     if (st.d_work) cudaFree(st.d_work);
     if (st.d_partial) cudaFree(st.d_partial);
     if (st.d_gemm) cudaFree(st.d_gemm);
@@ -281,7 +282,8 @@ static int ensure_stream_buffers(ttn_plan* p, Stream& st, int64_t chunk, bool ne
 }
 
 // Shared driver of ttn_evaluate / ttn_evaluate_grid.
-static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, void* out, ttn_opts* opts) {
+static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, void* out, ttn_opts* opts,
+                         const uint8_t* digits = nullptr) {
   std::lock_guard<std::mutex> lock(p->mu);
   TTN_CUDA(cudaSetDevice(p->device));
   const auto wall0 = std::chrono::steady_clock::now();
@@ -297,6 +299,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_DMMA: network is not a chain with chi <= 32 (real) / 16 (complex), <= 4 slices per vertex and <= 128 slice bits");
   const bool coords_host = !base.grid && opts->coords_mem == TTN_MEM_HOST;
+  const int n_sites = std::max(p->info.n_sites, 1);
   const bool out_host = out != nullptr && opts->out_mem == TTN_MEM_HOST;
   const bool do_sum = opts->reduce_sum != TTN_REDUCE_NONE;
   if (opts->reduce_sum < 0 || opts->reduce_sum > TTN_REDUCE_WEIGHTED) return fail(TTN_ERR_INVALID, "bad reduce mode");
@@ -309,7 +312,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
   if (!out && !do_sum) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
   if (npts == 0) return TTN_OK;
-  if (!base.grid && !coords) return fail(TTN_ERR_INVALID, "coords is NULL");
+  if (!base.grid && !coords && !digits) return fail(TTN_ERR_INVALID, "coords is NULL");
 
   TTN_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->streams[0].s));
   TTN_CUDA(cudaStreamSynchronize(p->streams[0].s));
@@ -350,7 +353,21 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
         src.weights = opts->weights + first;
       }
     }
-    if (base.grid) {
+    if (digits) {
+      if (coords_host) {
+        if (!st.d_digits || st.digits_cap < (size_t)chunk * n_sites) {
+          if (st.d_digits) cudaFree(st.d_digits);
+          st.d_digits = nullptr;
+          TTN_CUDA(cudaMalloc(&st.d_digits, (size_t)chunk * n_sites));
+          st.digits_cap = (size_t)chunk * n_sites;
+        }
+        cudaMemcpyAsync(st.d_digits, digits + (size_t)first * p->info.n_sites, (size_t)m * p->info.n_sites,
+                        cudaMemcpyHostToDevice, st.s);
+        src.digits = st.d_digits;
+      } else {
+        src.digits = digits + (size_t)first * p->info.n_sites;
+      }
+    } else if (base.grid) {
       src.first = base.first + first;
     } else if (coords_host) {
       if (base.layout == TTN_LAYOUT_AOS) {
@@ -407,7 +424,9 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     opts->kernel_ms = total;
     int herr = 0;
     cudaMemcpy(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost);
-    if (herr)
+    if (herr & 2)
+      rc = fail(TTN_ERR_INVALID, "an index value is out of range for its site index");
+    else if (herr)
       rc = fail(TTN_ERR_DOMAIN,
                 "a coordinate is negative or NaN (the reference's digit loop, abstractindexmap.jl:121-138, does not terminate on such input)");
     if (do_sum && rc == TTN_OK) {
@@ -532,6 +551,17 @@ int ttn_evaluate_grid(ttn_plan* plan, const ttn_grid* grid, void* out_or_null, t
   if (grid->first < 0 || grid->npts < 0 || grid->first + grid->npts > total)
     return fail(TTN_ERR_INVALID, "grid range exceeds the number of grid points");
   return evaluate_impl(plan, src, nullptr, out_or_null, opts);
+}
+
+int ttn_evaluate_indices(ttn_plan* plan, const uint8_t* index_values, int64_t npts, void* out, ttn_opts* opts) {
+  if (!plan || !opts) return fail(TTN_ERR_INVALID, "null argument");
+  if (npts > 0 && !index_values) return fail(TTN_ERR_INVALID, "index_values is NULL");
+  if (plan->info.n_sites == 0) return fail(TTN_ERR_INVALID, "the network has no site indices");
+  CoordSource src{};
+  src.npts = npts;
+  src.n_coords = plan->info.n_coords;
+  src.layout = TTN_LAYOUT_AOS;
+  return evaluate_impl(plan, src, nullptr, out, opts, index_values);
 }
 
 int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coords, int32_t layout,

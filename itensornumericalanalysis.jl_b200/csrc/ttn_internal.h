@@ -55,6 +55,7 @@ struct CoordSource {
   int64_t first;        // grid: linear index of point 0 of this launch
   double step[TTN_MAX_COORDS];
   int64_t count[TTN_MAX_COORDS];
+  const uint8_t* digits; // index-setting mode (ttn_evaluate_indices): digits[p * n_sites + site], else nullptr
   int32_t reduce_mode;   // TTN_REDUCE_* (what the kernels accumulate per point)
   const double* weights; // TTN_REDUCE_WEIGHTED: device pointer, one weight per point of this launch
 };
@@ -130,6 +131,8 @@ struct Stream {
   double* d_coords = nullptr;
   double* d_out = nullptr;
   double* d_weights = nullptr;
+  uint8_t* d_digits = nullptr;
+  size_t digits_cap = 0;
   int64_t cap_points = 0;
   double* d_work = nullptr; // generic-kernel workspace
   size_t work_bytes = 0;

@@ -124,6 +124,20 @@ class Plan:
         _capi.check(_capi.lib().ttn_evaluate_grid(self._h, C.byref(g), ptr, C.byref(o)))
         return out, o
 
+    def evaluate_indices_host(self, index_values, kernel="auto", reduce_sum=False, want_values=True):
+        """index_values: uint8 array (npts, n_sites), columns in the order of packed.site_inds."""
+        iv = np.ascontiguousarray(index_values, dtype=np.uint8)
+        ns = len(self.packed.site_dim)
+        if iv.ndim != 2 or iv.shape[1] != ns:
+            raise ValueError(f"index_values must have {ns} columns (one per site index)")
+        npts = iv.shape[0]
+        out = np.empty(npts, dtype=np.complex128 if self.packed.is_complex else np.float64) if want_values else None
+        o = self._opts(kernel, reduce_sum)
+        _capi.check(_capi.lib().ttn_evaluate_indices(self._h, iv.ctypes.data_as(C.c_void_p), npts,
+                                                     out.ctypes.data_as(C.c_void_p) if out is not None else None,
+                                                     C.byref(o)))
+        return out, o
+
     def digits_host(self, coords, layout=_capi.TTN_LAYOUT_AOS):
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         nc = self.packed.n_coords
@@ -267,6 +281,19 @@ def evaluate(fitn: ITensorNetworkFunction, xs, dims=None, *, alg=None, device=0,
     return (res, o) if return_opts else res
 
 
+def evaluate_indices(fitn: ITensorNetworkFunction, ind_to_ind_value_maps, *, device=0, kernel="auto"):
+    """Batched project() + scalar() at given index settings (the inner loop of TCI).
+    `ind_to_ind_value_maps`: a list of {Index: value} dictionaries (what calculate_ind_values
+    returns), or a uint8 array (npts, n_sites) whose columns follow plan.packed.site_inds."""
+    plan = fitn.plan(device=device)
+    sites = plan.packed.site_inds
+    if isinstance(ind_to_ind_value_maps, np.ndarray):
+        iv = ind_to_ind_value_maps
+    else:
+        iv = np.array([[m[i] for i in sites] for m in ind_to_ind_value_maps], dtype=np.uint8).reshape(-1, len(sites))
+    return plan.evaluate_indices_host(iv, kernel=kernel)[0]
+
+
 def batched_ind_values(fitn, xs, dims=None, device=0):
     """Batched calculate_ind_values on the GPU: returns (digits[npts, n_sites], site_inds)."""
     coords, dims, _ = _points_to_coords(fitn, xs, dims)
@@ -274,5 +301,5 @@ def batched_ind_values(fitn, xs, dims=None, device=0):
     return plan.digits_host(coords), plan.packed.site_inds
 
 
-__all__ = ["ITensorNetworkFunction", "evaluate", "batched_ind_values", "Plan",
+__all__ = ["ITensorNetworkFunction", "evaluate", "evaluate_indices", "batched_ind_values", "Plan",
            "default_contraction_alg", "RealIndsNetworkMap", "ComplexIndsNetworkMap"]

@@ -324,3 +324,32 @@ def test_fused_quadrature_functionals(which):
         assert abs(got - want) <= 1e-12 * float(np.sum(np.abs(w * vals))), (k, "weighted")
     # public API
     assert abs(t.evaluate(f, pts, dims, reduce="abs2") - float(np.sum(np.abs(vals) ** 2))) <= 1e-12 * float(np.sum(np.abs(vals) ** 2))
+
+
+@pytest.mark.parametrize("which", ["mps2d_chi8", "comb2x6_chi16", "mps2d_chi32", "mps2d_chi48_gemm", "bintree5_chi20_tree",
+                                   "base3_mps", "unitree9_s5", "cplx_2site", "cplx_default2d"])
+def test_evaluate_at_index_settings(which):
+    """batched evaluation at given index settings (TCI fibres / pivots), every kernel.
+    Feeding back the digits of a set of points must reproduce evaluate() at those points bit for bit."""
+    allc = {c[0]: (c, False) for c in cases.real_cases()}
+    allc.update({c[0]: (c, True) for c in cases.complex_cases()})
+    (name, f, dims, L), cplx = allc[which]
+    rng = np.random.default_rng(41)
+    pts = cases.complex_points(L, len(dims), rng, 500) if cplx else cases.edge_points(L, len(dims), rng, 600)
+    plan = f.plan(dims)
+    coords = coords_of(plan.packed, pts)
+    digits = plan.digits_host(coords)
+    for k in kernels_for(plan):
+        vals, _ = plan.evaluate_host(coords, kernel=k)
+        got, o = plan.evaluate_indices_host(digits, kernel=k)
+        assert (got == vals).all(), k
+    # dictionary form (what calculate_ind_values returns), public API
+    if dims == f.indexmap.dimensions():
+        maps = [f.indsnetworkmap.calculate_ind_values(list(p), dims) for p in pts[:5]]
+        auto_vals, _ = plan.evaluate_host(coords[:5])
+        assert (t.evaluate_indices(f, maps) == auto_vals).all()
+    bad = digits.copy()
+    bad[3, 0] = 200
+    with pytest.raises(_capi.TTNError) as e:
+        plan.evaluate_indices_host(bad)
+    assert e.value.code == _capi.TTN_ERR_INVALID
