@@ -81,6 +81,8 @@ enum {
                              shared memory */
   TTN_KERNEL_TREE = 5,    /* real trees with <= 2 children per vertex, chi <= 64 (binary trees, combs): vertex by
                              vertex over a chunk, degree-3 vertices as Khatri-Rao FP64 DMMA GEMMs */
+  TTN_KERNEL_GRID = 6,    /* ttn_evaluate_grid on a FULL dyadic grid of a binary chain: prefix-shared level-by-level
+                             expansion (~L/2 times fewer flops than independent points) */
   TTN_KERNEL_GEMM = 4     /* wide chains (width 33..256, e.g. complex chi = 128): per-site class-grouped FP64
                              DMMA GEMM with gathered rows, state in HBM/L2 */
 };
@@ -155,6 +157,9 @@ typedef struct ttn_opts {
   const double* weights; /* TTN_REDUCE_WEIGHTED: npts weights, in the memory space weights_mem */
   int32_t weights_mem;   /* TTN_MEM_* */
   int32_t reserved_;
+  /* output */
+  double flops_executed; /* FP64 flops the kernels of this call executed (= flops_per_point * npts, except for
+                            TTN_KERNEL_GRID, whose prefix sharing executes far fewer) */
 } ttn_opts;
 
 /* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:

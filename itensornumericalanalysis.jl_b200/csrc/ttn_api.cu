@@ -180,6 +180,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   if ((rc = build_chain(p, d))) return rc;
   if ((rc = build_chain_mma(p, d))) return rc;
   if ((rc = build_chain_gemm(p, d))) return rc;
+  if ((rc = build_grid_share(p, d))) return rc;
   if (!p->is_chain && (rc = build_tree_gemm(p, d))) return rc;
 
   ttn_info& I = p->info;
@@ -201,7 +202,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
                         (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0) | (p->cgemm_ok ? (1 << TTN_KERNEL_GEMM) : 0) |
-                        (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0);
+                        (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0) | (p->gshare_ok ? (1 << TTN_KERNEL_GRID) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
@@ -289,6 +290,61 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   const auto wall0 = std::chrono::steady_clock::now();
   const int NC = p->info.is_complex ? 2 : 1;
   const int64_t npts = base.npts;
+  // full dyadic grid of a binary chain: prefix-shared expansion (one pass over the whole grid)
+  if (base.grid && (opts->kernel == TTN_KERNEL_AUTO || opts->kernel == TTN_KERNEL_GRID) && grid_share_applicable(p, base) &&
+      !(opts->reduce_sum == TTN_REDUCE_WEIGHTED && opts->weights_mem == TTN_MEM_HOST)) {
+    opts->sum_out[0] = opts->sum_out[1] = 0.0;
+    opts->kernel_used = TTN_KERNEL_GRID;
+    opts->n_launches = 0;
+    const bool do_sum_g = opts->reduce_sum != TTN_REDUCE_NONE;
+    if (!out && !do_sum_g) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
+    Stream& st = p->streams[0];
+    int rc = ensure_stream_buffers(p, st, 1, false, false);
+    if (rc) return rc;
+    double* d_out = reinterpret_cast<double*>(out);
+    double* tmp = nullptr;
+    const bool out_host_g = out && opts->out_mem == TTN_MEM_HOST;
+    if (out_host_g) {
+      TTN_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)base.npts * NC));
+      d_out = tmp;
+    }
+    CoordSource src = base;
+    src.reduce_mode = opts->reduce_sum;
+    src.weights = opts->reduce_sum == TTN_REDUCE_WEIGHTED ? opts->weights : nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st.s);
+    int n_partial = 0;
+    double flops = 0.0;
+    rc = launch_grid_share(p, st, src, d_out, do_sum_g ? st.d_partial : nullptr, &n_partial, st.s, &opts->n_launches, &flops);
+    if (rc == TTN_OK && do_sum_g) {
+      rc = launch_sum_partials(p, st.d_partial, n_partial, NC, p->d_sum, st.s);
+      opts->n_launches += 1;
+    }
+    cudaEventRecord(e1, st.s);
+    if (rc == TTN_OK && out_host_g)
+      cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)base.npts * NC, cudaMemcpyDeviceToHost, st.s);
+    const cudaError_t e = cudaStreamSynchronize(st.s);
+    if (rc == TTN_OK && e != cudaSuccess) rc = fail(TTN_ERR_CUDA, std::string("grid kernel: ") + cudaGetErrorString(e));
+    if (rc == TTN_OK) {
+      cudaEventElapsedTime(&opts->kernel_ms, e0, e1);
+      opts->flops_executed = flops;
+      if (do_sum_g) {
+        double hs[2];
+        cudaMemcpy(hs, p->d_sum, sizeof(hs), cudaMemcpyDeviceToHost);
+        opts->sum_out[0] = hs[0];
+        opts->sum_out[1] = hs[1];
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (tmp) cudaFree(tmp);
+    opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return rc;
+  }
+  if (opts->kernel == TTN_KERNEL_GRID)
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GRID needs ttn_evaluate_grid on the FULL dyadic grid (count = 2^L, step = 2^-L, first = 0) of a chain with one binary site index per vertex and width <= 32");
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
@@ -422,6 +478,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       if (ev[2 * ci] && ev[2 * ci + 1] && cudaEventElapsedTime(&ms, ev[2 * ci], ev[2 * ci + 1]) == cudaSuccess) total += ms;
     }
     opts->kernel_ms = total;
+    opts->flops_executed = p->info.flops_per_point * (double)npts;
     int herr = 0;
     cudaMemcpy(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost);
     if (herr & 2)

@@ -166,6 +166,8 @@ struct ttn_plan {
   bool cmma_ok = false;
   ttn::ChainGemmDev cgemm{};
   bool cgemm_ok = false;
+  bool gshare_ok = false;            // prefix-shared full-grid evaluation (k_grid_share.cu)
+  std::vector<int> gs_coord, gs_digit, gs_L;
   ttn::TreeGemmDev tgemm{};
   bool tgemm_ok = false;
   std::vector<int64_t> tg_frag_off;
@@ -191,6 +193,10 @@ int build_chain(ttn_plan* p, const ttn_desc* d);
 int build_chain_mma(ttn_plan* p, const ttn_desc* d);
 int build_chain_gemm(ttn_plan* p, const ttn_desc* d);
 int build_tree_gemm(ttn_plan* p, const ttn_desc* d);
+int build_grid_share(ttn_plan* p, const ttn_desc* d);
+bool grid_share_applicable(const ttn_plan* p, const CoordSource& src);
+int launch_grid_share(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                      int* n_partial, cudaStream_t s, int* n_launches, double* flops_executed);
 int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                      int* n_partial, cudaStream_t s, int* n_launches);
 int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,

@@ -104,7 +104,7 @@ class Plan:
                       want_values=False, out_ptr=None):
         steps = np.ascontiguousarray(steps, dtype=np.float64)
         counts = np.ascontiguousarray(counts, dtype=np.int64)
-        total = int(np.prod(counts))
+        total = int(np.prod(counts.astype(object)))
         if npts is None:
             npts = total - first
         g = _capi.ttn_grid()

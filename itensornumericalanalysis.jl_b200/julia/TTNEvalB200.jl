@@ -63,9 +63,10 @@ mutable struct TTNOpts
   weights::Ptr{Float64}
   weights_mem::Int32
   reserved_::Int32
+  flops_executed::Float64
 end
 TTNOpts(; reduce_sum=false) =
-  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, reduce_sum ? 1 : 0, 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, C_NULL, TTN_MEM_HOST, 0)
+  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, reduce_sum ? 1 : 0, 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, C_NULL, TTN_MEM_HOST, 0, 0.0)
 
 "Flat arrays of one packed network; keeps everything the C side points at alive."
 struct PackedNetwork

@@ -147,7 +147,8 @@ def test_sum_reduction_and_chunking_are_deterministic():
 def test_grid_mode_matches_points_and_integrate_identity():
     """grid_points(s, N, d) evaluated on the device (no coordinate bytes read) == explicit points;
     the sum over all 2^L grid points == integrate(fitn; take_sum=true) (src/integration.jl:6-17),
-    i.e. the network contracted with all-ones vectors on every site index."""
+    i.e. the network contracted with all-ones vectors on every site index.  Both grid paths:
+    per-point kernels on generated coordinates, and the prefix-shared expansion (TTN_KERNEL_GRID)."""
     L = 16
     s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=2)
     f = t.rand_itn(s, link_space=8, rng=5, normalise=True)
@@ -155,18 +156,53 @@ def test_grid_mode_matches_points_and_integrate_identity():
     xs, ys = s.grid_points(n, 1), s.grid_points(n, 2)
     assert len(xs) == n and len(ys) == n
     plan = f.plan()
-    vals, o = plan.evaluate_grid([xs[1], ys[1]], [n, n], want_values=True, reduce_sum=True)
     pts = np.array([[x, y] for x in xs for y in ys])
-    explicit, _ = plan.evaluate_host(pts)
-    assert (vals == explicit).all()
-    # integrate identity via the dense oracle: sum of all entries of the dense tensor
     dense, _ = orc.dense_tensor(f)
+    for k in ("dmma", "chain", "generic"):
+        vals, o = plan.evaluate_grid([xs[1], ys[1]], [n, n], want_values=True, reduce_sum=True, kernel=k)
+        explicit, _ = plan.evaluate_host(pts, kernel=k)
+        assert (vals == explicit).all(), k
+        assert abs(o.sum_out[0] - dense.sum()) <= 1e-11 * np.abs(dense).sum()
+        # sharded grid (what each rank of a multi-GPU run does) gives the same values
+        half = n * n // 2
+        a, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=0, npts=half, want_values=True, kernel=k)
+        b, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=half, npts=n * n - half, want_values=True, kernel=k)
+        assert (np.concatenate([a, b]) == vals).all()
+    # prefix-shared expansion: the planner's choice for a full dyadic grid
+    ref = orc.evaluate(plan.packed, pts, orc.ORACLE_LD, nthreads=orc.max_threads())
+    shared, o = plan.evaluate_grid([xs[1], ys[1]], [n, n], want_values=True, reduce_sum=True)
+    assert o.kernel_used == _capi.TTN_KERNEL_GRID
+    assert orc.error_metric(shared, ref).max() < TOL
     assert abs(o.sum_out[0] - dense.sum()) <= 1e-11 * np.abs(dense).sum()
-    # sharded grid (what each rank of a multi-GPU run does) gives the same values
-    half = n * n // 2
-    a, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=0, npts=half, want_values=True)
-    b, _ = plan.evaluate_grid([xs[1], ys[1]], [n, n], first=half, npts=n * n - half, want_values=True)
-    assert (np.concatenate([a, b]) == vals).all()
+    assert o.flops_executed < 0.5 * plan.info()["flops_per_point"] * n * n   # it really shares prefixes
+    _, o2 = plan.evaluate_grid([xs[1], ys[1]], [n, n], reduce_sum="abs2")
+    assert abs(o2.sum_out[0] - np.sum(ref ** 2)) <= 1e-12 * np.sum(ref ** 2)
+
+
+@pytest.mark.parametrize("which", ["comb2x6_chi16", "mps2d_chi32", "sin_qtt20", "cplx_alt"])
+def test_prefix_shared_grid_other_layouts(which):
+    """TTN_KERNEL_GRID on per-tooth digits, chi = 32, a 1-D complex-valued QTT and a ComplexIndexMap
+    with alternating Real/Imag vertices: every grid value against the 80-bit oracle."""
+    allc = {c[0]: (c, False) for c in cases.real_cases()}
+    allc.update({c[0]: (c, True) for c in cases.complex_cases()})
+    (name, f, dims, L), cplx = allc[which]
+    plan = f.plan(dims)
+    packed = plan.packed
+    assert plan.info()["kernels_available"] & (1 << _capi.TTN_KERNEL_GRID), which
+    Lc = [0] * packed.n_coords
+    for sidx, c in enumerate(packed.site_coord):
+        Lc[c] = max(Lc[c], int(packed.site_digit[sidx]))
+    if sum(Lc) > 20:
+        pytest.skip("grid too large for the oracle")
+    counts = [2 ** l for l in Lc]
+    steps = [2.0 ** -l for l in Lc]
+    vals, o = plan.evaluate_grid(steps, counts, want_values=True, reduce_sum=True)
+    assert o.kernel_used == _capi.TTN_KERNEL_GRID
+    grids = np.meshgrid(*[np.arange(cn) * st for cn, st in zip(counts, steps)], indexing="ij")
+    coords = np.stack([g.reshape(-1) for g in grids], axis=1)
+    ref = orc.evaluate(packed, coords, orc.ORACLE_LD, nthreads=orc.max_threads())
+    assert orc.error_metric(vals, ref).max() < TOL
+    assert abs(complex(o.sum_out[0], o.sum_out[1]) - ref.sum()) <= 1e-11 * np.abs(ref).sum()
 
 
 def test_device_pointer_path_with_torch():
