@@ -156,6 +156,44 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_grid(args, plan, rank, world, local_rank, torch):
+    """BASELINE config 4 as literally stated: the 2-D chi=32 MPS on the full 16384^2 grid with the summed-grid
+    quadrature.  No coordinate bytes exist (the grid is generated on the device); a step = the whole grid + sum."""
+    import ctypes as C
+    from itna_b200 import _capi
+    assert args.config == 4 and world == 1, "--grid is a single-GPU, config-4 line"
+    n = 2 ** 14
+    dfma, dmma = C.c_double(), C.c_double()
+    _capi.check(_capi.lib().ttn_measure_fp64_peak(local_rank, C.byref(dfma), C.byref(dmma)))
+    out = torch.empty(n * n, dtype=torch.float64, device=f"cuda:{local_rank}")
+    for _ in range(args.warmup):
+        plan.evaluate_grid([2.0 ** -14] * 2, [n, n], reduce_sum=True, out_ptr=out.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms = 0.0
+    for _ in range(args.steps):
+        _, o = plan.evaluate_grid([2.0 ** -14] * 2, [n, n], reduce_sum=True, out_ptr=out.data_ptr())
+        kms += o.kernel_ms
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    kms /= args.steps
+    peak = max(dfma.value, dmma.value)
+    ach = o.flops_executed / (kms * 1e-3) / 1e12
+    print(json.dumps({
+        "metric": "points_per_sec_fp64", "value": n * n / dt, "unit": "points/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: 2-D interleaved MPS 28 sites, chi=32, FULL 16384^2 grid + summed quadrature "
+                               "(values written to HBM and summed)", "kernel": _capi.KERNEL_NAMES[o.kernel_used],
+                   "grid_sum": o.sum_out[0]},
+        "kernel_ms_events": kms, "gpu_launches": o.n_launches * args.steps,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "traffic": None,
+                     "algorithmic": f"{o.flops_executed:.4g} flop EXECUTED per grid (prefix sharing; the per-point flop "
+                                    f"rule would count {plan.info()['flops_per_point'] * n * n:.4g})"},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +203,9 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="2 (default, BASELINE configs[1]), 4, 5 or 1")
     ap.add_argument("--points", type=float, default=0, help="override points per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", action="store_true",
+                    help="config 4 only: evaluate the FULL 16384^2 grid with the summed quadrature (ttn_evaluate_grid, "
+                         "prefix-shared kernel) instead of random points")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -189,6 +230,8 @@ def main():
     if args.points:
         npts = int(args.points)
     plan = f.plan(device=local_rank)
+    if args.grid:
+        return bench_grid(args, plan, rank, world, local_rank, torch)
     info = plan.info()
     nc_out = 2 if info["is_complex"] else 1
     flops_pp = info["flops_per_point"]
