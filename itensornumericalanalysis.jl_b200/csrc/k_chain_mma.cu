@@ -42,346 +42,6 @@ __device__ __forceinline__ uint32_t row_chunk(uint32_t state_base, int row, int 
   return state_base + (uint32_t)row * (CHI * 8) + (uint32_t)((chunk ^ ((row / RP) & SW)) << 4);
 }
 
-// One batch: NBAT (<= GB) 8-row groups of the same class, starting at group gi.
-template <int CHI, int NBAT>
-__device__ __forceinline__ void process_batch(uint32_t state_base, const uint16_t* list, int gi, int g, int tq,
-                                              uint32_t stage_base, int c, int sites, int nsl) {
-  constexpr int NB = CHI / 8, KB = CHI / 4;
-  int rows[NBAT];
-  double a[NBAT][KB];
-#pragma unroll
-  for (int b = 0; b < NBAT; ++b) {
-    rows[b] = (int)list[((gi + b) << 3) + g];
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
-      a[b][2 * nb] = v.x;
-      a[b][2 * nb + 1] = v.y;
-    }
-  }
-  int crem = c;
-  for (int s = 0; s < sites; ++s) {
-    const int d = crem % nsl;
-    crem /= nsl;
-    const uint32_t bb = stage_base + (uint32_t)(s * nsl + d) * (CHI * CHI * 8);
-    double acc[NBAT][KB];
-#pragma unroll
-    for (int b = 0; b < NBAT; ++b)
-#pragma unroll
-      for (int j = 0; j < KB; ++j) acc[b][j] = 0.0;
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-      for (int nbp = 0; nbp < NB; ++nbp) {
-        const double bf = lds64(bb + (uint32_t)((kb * NB + nbp) * 32) * 8u);
-#pragma unroll
-        for (int b = 0; b < NBAT; ++b) dmma884(acc[b][2 * nbp], acc[b][2 * nbp + 1], a[b][kb], bf);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < NBAT; ++b)
-#pragma unroll
-      for (int j = 0; j < KB; ++j) a[b][j] = acc[b][j];
-  }
-#pragma unroll
-  for (int b = 0; b < NBAT; ++b) {
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb)
-      sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), a[b][2 * nb], a[b][2 * nb + 1]);
-  }
-}
-
-// CTA = NH independent "halves" of NTH consumer threads (each with its own tile stream, state,
-// lists, B-fragment ring and named barrier, so that one half computes while the other sits in a
-// barrier or builds its lists) + NH producer warps.
-template <int CHI, int P, int NTH, int NH, int GB>
-__global__ void __launch_bounds__(NTH * NH + 32 * NH, 1)
-    chain_mma_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
-                     double* __restrict__ partial, int do_sum, int n_stage, int resident,
-                     uint32_t stage_stride, uint32_t half_bytes) {
-  constexpr int NT = NTH * NH;
-  constexpr int NWH = NTH / 32;    // consumer warps per half
-  constexpr int PPT = P / NTH;     // points owned per thread
-  constexpr int CPR = CHI / 2;
-  constexpr int LIST_CAP = P + 8 * kMaxClasses;
-  static_assert(P % NTH == 0 && NWH <= 32 && GB <= 4, "tile shape");
-
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t full_bar[NH][kMmaMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[NH][kMmaMaxStages];
-  __shared__ double red[2][NT / 32];
-
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int h = 0; h < NH; ++h)
-      for (int s = 0; s < n_stage; ++s) {
-        mbar_init(smem_u32(&full_bar[h][s]), 1);
-        mbar_init(smem_u32(&empty_bar[h][s]), NWH);
-      }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  // scratch rows (targets of the class padding) start out as zeros
-  for (int h = 0; h < NH; ++h)
-    for (int i = tid; i < 8 * CHI; i += NT + 32 * NH)
-      reinterpret_cast<double*>(smem + (size_t)h * half_bytes + (size_t)P * CHI * 8)[i] = 0.0;
-  __syncthreads();
-
-  const int64_t n_tiles = (src.npts + P - 1) / P;
-  const int n_rounds = ch.n_rounds, spr = ch.spr, nsl = ch.nsl, n_steps = ch.n_steps;
-  const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
-  const int h = (tid < NT) ? tid / NTH : (tid - NT) / 32;
-  unsigned char* half = smem + (size_t)h * half_bytes;
-  unsigned char* state_p = half;                                              // (P + 8) rows
-  uint16_t* list = reinterpret_cast<uint16_t*>(half + (size_t)(P + 8) * CHI * 8);
-  int* cnt = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(list) + ((LIST_CAP * 2 + 15) / 16) * 16);
-  unsigned char* ring = reinterpret_cast<unsigned char*>(cnt) + NWH * kMaxClasses * 4;
-  ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ring) + 127) & ~(uintptr_t)127);
-  const uint32_t ring_base = smem_u32(ring);
-  const int64_t tile0 = (int64_t)blockIdx.x * NH + h, tile_step = (int64_t)gridDim.x * NH;
-
-  if (tid >= NT) {
-    // ===== producer warps: one elected lane per half streams the rounds' B fragments =====
-    if (((tid - NT) & 31) == 0 && n_rounds > 0) {
-      const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(ch.frags);
-      if (resident) {
-        for (int r = 0; r < n_rounds; ++r) {
-          const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
-          mbar_expect_tx(smem_u32(&full_bar[h][r]), bytes);
-          bulk_g2s(ring_base + (uint32_t)r * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
-                   smem_u32(&full_bar[h][r]));
-        }
-      } else {
-        uint32_t slot = 0, phase = 0;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-          for (int r = 0; r < n_rounds; ++r) {
-            const uint32_t bytes = (uint32_t)min(spr, n_steps - r * spr) * site_bytes;
-            mbar_wait(smem_u32(&empty_bar[h][slot]), phase ^ 1u);
-            mbar_expect_tx(smem_u32(&full_bar[h][slot]), bytes);
-            bulk_g2s(ring_base + slot * stage_stride, gsrc + (size_t)r * spr * site_bytes, bytes,
-                     smem_u32(&full_bar[h][slot]));
-            if (++slot == (uint32_t)n_stage) {
-              slot = 0;
-              phase ^= 1u;
-            }
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers =====
-  const int ltid = tid - h * NTH;            // thread index inside the half
-  const int lane = tid & 31, warp = ltid >> 5;
-  const int g = lane >> 2, tq = lane & 3;
-  const int bar_id = 1 + h;
-  const uint32_t state_base = smem_u32(state_p);
-  const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
-  const int bits = ch.bits, per_word = ch.per_word;
-  double sum_re = 0.0, sum_im = 0.0;
-  uint32_t slot = 0, phase = 0;
-
-  for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-    // ---- K1 per owned point: digits -> packed slice stream (position 0 = leaf ... n-1 = root)
-    uint64_t w0[PPT], w1[PPT], cw[PPT];
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      const int64_t p = tile * P + k * NTH + ltid;
-      w0[k] = w1[k] = 0;
-      if (p < src.npts) {
-        for (int c = 0; c < dg.n_coords; ++c) {
-          double x = load_coord(src, p, c);
-          if (!coord_in_domain(x)) {
-            atomicOr(err, 1);
-            x = 0.0;
-          }
-          for (int e_i = dg.coord_ptr[c]; e_i < dg.coord_ptr[c + 1]; ++e_i) {
-            const DigitEntry e = dg.entries[e_i];
-            const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
-            const uint64_t b = (uint64_t)(v * e.stride) << e.shift;
-            w0[k] += (e.word == 0) ? b : 0ull;
-            w1[k] += (e.word == 1) ? b : 0ull;
-          }
-        }
-      }
-      cw[k] = w0[k];
-    }
-    int in_word = 0;
-    auto advance = [&]() { // move every owned point's stream to the next chain position
-      const bool wrap = (++in_word == per_word);
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) cw[k] = wrap ? w1[k] : (cw[k] >> bits);
-      if (wrap) in_word = 0;
-    };
-
-    // ---- leaf: row(point) = L[d_0]
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      const int row = k * NTH + ltid;
-      const double* L = ch.leaf + (size_t)(cw[k] & MASK) * CHI;
-#pragma unroll
-      for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
-    }
-    advance();
-
-    // ---- rounds of `spr` middle sites
-    for (int r = 0; r < n_rounds; ++r) {
-      const int sites = min(spr, n_steps - r * spr);
-      int ncls = 1;
-      for (int k = 0; k < sites; ++k) ncls *= nsl;
-      // class of every owned point
-      int cls[PPT];
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) cls[k] = 0;
-      {
-        int mul = 1;
-        for (int s = 0; s < sites; ++s) {
-#pragma unroll
-          for (int k = 0; k < PPT; ++k) cls[k] += (int)(cw[k] & MASK) * mul;
-          mul *= nsl;
-          advance();
-        }
-      }
-      // per-warp histogram + ranks (k-major order inside the warp)
-      int rank[PPT];
-      {
-        int mycnt = 0; // lane c keeps the warp's count of class c
-        for (int c = 0; c < ncls; ++c) {
-          int run = 0;
-#pragma unroll
-          for (int k = 0; k < PPT; ++k) {
-            const uint32_t m = __ballot_sync(0xffffffffu, cls[k] == c);
-            if (cls[k] == c) rank[k] = run + __popc(m & ((1u << lane) - 1u));
-            run += __popc(m);
-          }
-          if (lane == c) mycnt = run;
-        }
-        if (lane < ncls) cnt[warp * kMaxClasses + lane] = mycnt;
-      }
-      named_bar_sync(bar_id, NTH);
-      // exclusive offsets: lane c ends up with (start row of class c) and (start + this warp's offset)
-      int mystart = 0, mybase = 0, total_rows = 0;
-      {
-        int run_start = 0;
-        for (int c = 0; c < ncls; ++c) {
-          const int v = (lane < NWH) ? cnt[lane * kMaxClasses + c] : 0;
-          int incl = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
-          }
-          const int tot = __shfl_sync(0xffffffffu, incl, 31);
-          const int excl_w = __shfl_sync(0xffffffffu, incl - v, warp);
-          if (lane == c) {
-            mystart = run_start;
-            mybase = run_start + excl_w;
-          }
-          if (warp == 0 && (tot & 7) && lane >= (tot & 7) && lane < 8)
-            list[run_start + (tot & ~7) + lane] = (uint16_t)P; // padding -> scratch row
-          run_start += (tot + 7) & ~7;
-        }
-        total_rows = run_start;
-        if (lane >= ncls) mystart = total_rows;
-      }
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int base = __shfl_sync(0xffffffffu, mybase, cls[k]);
-        list[base + rank[k]] = (uint16_t)(k * NTH + ltid);
-      }
-      named_bar_sync(bar_id, NTH);
-
-      // B fragments of this round
-      const uint32_t s_use = resident ? (uint32_t)r : slot;
-      mbar_wait(smem_u32(&full_bar[h][s_use]), resident ? 0u : phase);
-      const uint32_t stage_base = ring_base + s_use * stage_stride + (uint32_t)lane * 8u;
-
-      const int n_groups = total_rows >> 3;
-      const int gpw = (n_groups + NWH - 1) / NWH;
-      int gi = warp * gpw;
-      const int gend = min(n_groups, gi + gpw);
-      while (gi < gend) {
-        const int row0 = gi << 3;
-        const uint32_t m = __ballot_sync(0xffffffffu, lane < ncls && mystart <= row0);
-        const int c = 31 - __clz(m);
-        const int cend = __shfl_sync(0xffffffffu, mystart, c + 1) >> 3;
-        const int nbat = min(GB, min(gend, cend) - gi);
-        if (nbat >= 4 && GB >= 4) process_batch<CHI, (GB >= 4 ? 4 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else if (nbat == 3 && GB >= 3) process_batch<CHI, (GB >= 3 ? 3 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else if (nbat == 2 && GB >= 2) process_batch<CHI, (GB >= 2 ? 2 : 1)>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        else process_batch<CHI, 1>(state_base, list, gi, g, tq, stage_base, c, sites, nsl);
-        gi += (nbat >= 1 ? (nbat > GB ? GB : nbat) : 1);
-      }
-      if (!resident) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[h][slot]));
-        if (++slot == (uint32_t)n_stage) {
-          slot = 0;
-          phase ^= 1u;
-        }
-      }
-      named_bar_sync(bar_id, NTH); // rows change hands between rounds
-    }
-
-    // ---- root: out = row . R[d_{n-1}]  (one or two output components)
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-      const int row = k * NTH + ltid;
-      const int64_t p = tile * P + row;
-      double o0 = 0.0, o1 = 0.0;
-      if (ch.n_vertices > 1) {
-        const double* R0 = ch.root + (size_t)(cw[k] & MASK) * CHI;
-        const double* R1 = R0 + (size_t)nsl * CHI;
-#pragma unroll
-        for (int j = 0; j < CPR; ++j) {
-          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
-          o0 = fma(v.x, __ldg(R0 + 2 * j), o0);
-          o0 = fma(v.y, __ldg(R0 + 2 * j + 1), o0);
-          if (ch.nout == 2) {
-            o1 = fma(v.x, __ldg(R1 + 2 * j), o1);
-            o1 = fma(v.y, __ldg(R1 + 2 * j + 1), o1);
-          }
-        }
-      } else {
-        o0 = lds64(row_chunk<CHI>(state_base, row, 0));
-        if (ch.nout == 2) o1 = lds64(row_chunk<CHI>(state_base, row, CPR / 2));
-      }
-      if (p < src.npts) {
-        if (out) {
-          if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
-          else out[p] = o0;
-        }
-        accumulate_point(src, p, o0, o1, sum_re, sum_im);
-      }
-    }
-    // the next tile's leaf writes touch only rows owned by the writing thread, and the list /
-    // histogram buffers are next written after a barrier: no extra sync needed here.
-  }
-
-  if (do_sum) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
-      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
-    }
-    if (lane == 0) {
-      red[0][tid >> 5] = sum_re;
-      red[1][tid >> 5] = sum_im;
-    }
-    named_bar_sync(1 + NH, NT);
-    if (tid == 0) {
-      double x = 0.0, y = 0.0;
-      for (int w = 0; w < NT / 32; ++w) {
-        x += red[0][w];
-        y += red[1][w];
-      }
-      partial[2 * blockIdx.x] = x;
-      partial[2 * blockIdx.x + 1] = y;
-    }
-  }
-}
-
 template <int CHI, int NBAT>
 __device__ __forceinline__ void site_mma(double (&dst)[NBAT][CHI / 4], const double (&srcA)[NBAT][CHI / 4],
                                          uint32_t bb) {
@@ -461,8 +121,8 @@ struct __align__(16) Digit2 {
 //   * B fragments are prefetched by MMA thread 0 into the ring slot the end-of-round barrier has
 //     just freed (no producer warp, no "empty" barriers).
 // Handshakes are mbarriers: tile_ready/tile_free (slice streams), list_full/list_empty, ring full.
-constexpr int kFeMaxSites = 160;
-constexpr int kFeMaxThr = 640;
+constexpr int kFeMaxSites = 160; // static shared-memory copies of the digit tables (within the 12 KB the
+constexpr int kFeMaxThr = 640;   // launchers reserve); larger networks take the chain / generic kernels
 
 __device__ __forceinline__ int greedy_digit_smem(double& x, const double* thr, int base) {
   int v = base - 1;
@@ -1549,41 +1209,8 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       c.run_scale[cidx] = std::ldexp(1.0, L);
     }
   }
-  p->cmma_ok = true;
-  return TTN_OK;
-}
-
-template <int CHI, int P, int NTH, int NH, int GB>
-static int launch_mma_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial,
-                           int* n_partial, cudaStream_t s) {
-  const ChainMmaDev& c = p->cmma;
-  constexpr int NWH = NTH / 32;
-  constexpr int LIST_CAP = P + 8 * kMaxClasses;
-  const size_t fixed = (size_t)(P + 8) * CHI * 8 + ((LIST_CAP * 2 + 15) / 16) * 16 + NWH * kMaxClasses * 4 + 128;
-  const size_t smem_max = 227 * 1024 - 2048; // static shared: barriers + reduction scratch
-  const size_t per_half_max = (smem_max / NH) & ~(size_t)127;
-  const size_t stage = (size_t)c.spr * c.nsl * CHI * CHI * 8;
-  if (fixed + stage > per_half_max) {
-    set_error("chain DMMA kernel: one round of site matrices does not fit in shared memory");
-    return TTN_ERR_UNSUPPORTED;
-  }
-  int n_stage = (int)std::min<size_t>((per_half_max - fixed) / stage, (size_t)kMmaMaxStages);
-  int resident = 0;
-  if (c.n_rounds <= n_stage) {
-    n_stage = std::max(c.n_rounds, 1);
-    resident = 1;
-  }
-  const size_t half_bytes = (fixed + (size_t)n_stage * stage + 127) & ~(size_t)127;
-  const size_t smem = half_bytes * NH;
-  auto kern = chain_mma_kernel<CHI, P, NTH, NH, GB>;
-  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  const int64_t n_tiles = (src.npts + P - 1) / P;
-  const int grid = (int)std::min<int64_t>((n_tiles + NH - 1) / NH, p->sm_count);
-  const int do_sum = d_partial != nullptr;
-  kern<<<grid, NTH * NH + 32 * NH, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum, n_stage,
-                                               resident, (uint32_t)stage, (uint32_t)half_bytes);
-  TTN_CUDA(cudaGetLastError());
-  *n_partial = do_sum ? grid : 0;
+  // both kernels keep the digit and threshold tables in static shared memory
+  p->cmma_ok = p->digits.n_sites <= kFeMaxSites && d->n_sites <= kFeMaxSites && d->thr_ptr[d->n_sites] <= kFeMaxThr;
   return TTN_OK;
 }
 
@@ -1658,47 +1285,30 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     set_error("DMMA chain kernel requested but the network is not a supported chain");
     return TTN_ERR_UNSUPPORTED;
   }
-  static const int variant = getenv("TTN_MMA_VARIANT") ? atoi(getenv("TTN_MMA_VARIANT")) : 0;
-  // v3 (warp-specialised) needs the digit tables to fit its static shared-memory copies
-  bool v3_ok = p->digits.n_sites <= kFeMaxSites && p->info.n_sites <= kFeMaxSites && p->fe_thr_len <= kFeMaxThr;
-  if (variant == 1 || variant == 2) v3_ok = false;
-  if (v3_ok && variant != 3 && (p->cmma.chi == 8 || p->cmma.chi == 16)) {
-    // v5 (warp-autonomous).  Fast instances: binary digits with 2 sites per round, or two binary
-    // digits per vertex (4 slices) with 1 site per round; everything else takes the generic one.
-    const ChainMmaDev& c = p->cmma;
-    const bool full_rounds = c.n_steps % std::max(c.spr, 1) == 0;
-    const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2 && full_rounds;
-    const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
-    if (c.chi == 8) {
-      if (f22) return launch_mma5_inst<8, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+  const ChainMmaDev& c = p->cmma;
+  // fast instances: binary digits with 2 sites per round, or two binary digits per vertex (4 slices)
+  // with 1 site per round; everything else takes the runtime-generic instance
+  const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2;
+  const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
+  // the warp-autonomous kernel's 2-sites-per-round instance has no partial last round
+  const bool f22w = f22 && c.n_steps % 2 == 0;
+  if (p->digits.n_sites > kFeMaxSites || p->info.n_sites > kFeMaxSites || p->fe_thr_len > kFeMaxThr) {
+    set_error("DMMA chain kernel: digit tables exceed the kernel's shared-memory copies (160 sites / 640 thresholds)");
+    return TTN_ERR_UNSUPPORTED;
+  }
+  switch (c.chi) {
+    case 8: // warp-autonomous kernel (v5)
+      if (f22w) return launch_mma5_inst<8, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
       if (f41) return launch_mma5_inst<8, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
       return launch_mma5_inst<8, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
-    }
-    if (f22) return launch_mma5_inst<16, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
-    if (f41) return launch_mma5_inst<16, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
-    return launch_mma5_inst<16, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
-  }
-  if (v3_ok) {
-    const ChainMmaDev& c = p->cmma;
-    const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2;
-    const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
-    switch (c.chi) {
-      case 16:
-        if (f22) return launch_mma3_inst<16, 1024, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
-        return launch_mma3_inst<16, 1024, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
-      case 32:
-        if (f22) return launch_mma3_inst<32, 512, 8, 3, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
-        if (f41) return launch_mma3_inst<32, 512, 8, 3, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
-        return launch_mma3_inst<32, 512, 8, 2, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
-    }
-  }
-  switch (p->cmma.chi) {
-    case 8: return launch_mma_inst<8, 1024, 128, 2, 4>(p, src, d_out, d_partial, n_partial, s);
     case 16:
-      if (variant == 2) return launch_mma_inst<16, 1024, 256, 1, 4>(p, src, d_out, d_partial, n_partial, s);
-      return launch_mma_inst<16, 512, 128, 2, 4>(p, src, d_out, d_partial, n_partial, s);
-    case 32:
-      return launch_mma_inst<32, 448, 224, 1, 4>(p, src, d_out, d_partial, n_partial, s);
+      if (f22w) return launch_mma5_inst<16, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+      if (f41) return launch_mma5_inst<16, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+      return launch_mma5_inst<16, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
+    case 32: // CTA-sorted, warp-specialised kernel (v3): 128 rows per warp would not fit at this width
+      if (f22) return launch_mma3_inst<32, 512, 8, 3, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
+      if (f41) return launch_mma3_inst<32, 512, 8, 3, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+      return launch_mma3_inst<32, 512, 8, 2, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
   }
   set_error("DMMA chain kernel: unsupported width");
   return TTN_ERR_UNSUPPORTED;
