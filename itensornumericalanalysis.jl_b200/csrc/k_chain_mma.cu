@@ -34,6 +34,11 @@ namespace ttn {
 constexpr int kMmaMaxStages = 16;
 constexpr int kMaxClasses = 16;
 
+// stream bits per chain position holding `nsl` slices (<= 16)
+__host__ __device__ constexpr int slice_bits(int nsl) {
+  return nsl <= 1 ? 0 : (nsl <= 2 ? 1 : (nsl <= 4 ? 2 : (nsl <= 8 ? 3 : 4)));
+}
+
 template <int CHI>
 __device__ __forceinline__ uint32_t row_chunk(uint32_t state_base, int row, int chunk) {
   constexpr int CPR = CHI / 2;                      // 16-byte chunks per row
@@ -198,10 +203,10 @@ __global__ void __launch_bounds__(NMW * 32 + 128, 1)
   const int n_rounds = ch.n_rounds, spr = SPRT ? SPRT : ch.spr, nsl = NSLT ? NSLT : ch.nsl, n_steps = ch.n_steps;
   const uint32_t site_bytes = (uint32_t)nsl * CHI * CHI * 8;
   const uint32_t ring_base = smem_u32(ring);
-  const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
-  const int bits = NSLT ? (NSLT <= 1 ? 0 : (NSLT <= 2 ? 1 : 2)) : ch.bits;
-  const int per_word = NSLT ? (NSLT <= 1 ? (1 << 30) : 64 / (NSLT <= 2 ? 1 : 2)) : ch.per_word;
-  const bool pow2 = (nsl == 1) || (nsl == 2) || (nsl == 4);
+  const int bits = NSLT ? slice_bits(NSLT) : ch.bits;
+  const uint64_t MASK = (1ull << bits) - 1ull;
+  const int per_word = NSLT ? (NSLT <= 1 ? (1 << 30) : 64 / slice_bits(NSLT > 1 ? NSLT : 2)) : ch.per_word;
+  const bool pow2 = (nsl & (nsl - 1)) == 0;
   const int lane = tid & 31;
   int64_t my_tiles = 0;
   if ((int64_t)blockIdx.x < n_tiles) my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -698,11 +703,10 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
   const int g = lane >> 2, tq = lane & 3;
   const uint32_t state_base = smem_u32(state_all + (size_t)warp * ROWS * CHI * 8);
   uint8_t* list = list_all + warp * 256;
-  const uint64_t MASK = (nsl <= 1) ? 0ull : (nsl <= 2 ? 1ull : 3ull);
-  const int bits = NSLT ? (NSLT <= 1 ? 0 : (NSLT <= 2 ? 1 : 2)) : ch.bits;
-  const int per_word = NSLT ? (NSLT <= 1 ? (1 << 30) : 64 / (NSLT <= 2 ? 1 : 2)) : ch.per_word;
+  const int bits = NSLT ? slice_bits(NSLT) : ch.bits;
+  const uint64_t MASK = (1ull << bits) - 1ull;
   const uint32_t lt = (1u << lane) - 1u;
-  const bool pow2 = (nsl == 1) || (nsl == 2) || (nsl == 4); // slice index == bit field of the stream
+  const bool pow2 = (nsl & (nsl - 1)) == 0; // slice index == bit field of the stream
   double sum_re = 0.0, sum_im = 0.0;
   uint32_t slot = 0, phase = 0;
   PH_DECL
@@ -711,7 +715,6 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
     const int64_t sub = (int64_t)blockIdx.x * NMW + warp + it * stride;
     const bool live_sub = sub < n_sub;     // warp-uniform
     uint64_t w0[PPL], w1[PPL], cw[PPL];
-    int in_word = 0;
     if (live_sub) {
       // ---- K1: digits of the lane's PPL points (interleaved for ILP)
       double x[PPL];
@@ -788,13 +791,17 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
         for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
       }
     }
-    auto advance = [&]() {
-      const bool wrap = (++in_word == per_word);
+    // the packed stream is consumed as a 128-bit shift register (cw = low word, w1 = high word):
+    // position p of the stream is bits [p * bits, (p + 1) * bits), whatever the field width
+    auto shift_stream = [&](int nb) {
+      if (nb == 0) return;
 #pragma unroll
-      for (int k = 0; k < PPL; ++k) cw[k] = wrap ? w1[k] : (cw[k] >> bits);
-      if (wrap) in_word = 0;
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = (cw[k] >> nb) | (w1[k] << (64 - nb));
+        w1[k] >>= nb;
+      }
     };
-    if (live_sub) advance();
+    if (live_sub) shift_stream(bits);
     __syncwarp();
     PH_MARK(0)
 
@@ -805,18 +812,13 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
         int ncls = 1;
         for (int k = 0; k < sites; ++k) ncls *= nsl;
         int cls[PPL];
-        if (pow2 && in_word + sites <= per_word) {
+        if (pow2) {
           // slices are bit fields: the class is the next bits*sites bits of the stream
           const int nb_ = bits * sites;
           const uint64_t rmask = (1ull << nb_) - 1ull;
-          in_word += sites;
-          const bool wrap = in_word == per_word;
 #pragma unroll
-          for (int k = 0; k < PPL; ++k) {
-            cls[k] = (int)(cw[k] & rmask);
-            cw[k] = wrap ? w1[k] : (cw[k] >> nb_);
-          }
-          if (wrap) in_word = 0;
+          for (int k = 0; k < PPL; ++k) cls[k] = (int)(cw[k] & rmask);
+          shift_stream(nb_);
         } else {
 #pragma unroll
           for (int k = 0; k < PPL; ++k) cls[k] = 0;
@@ -825,7 +827,7 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
 #pragma unroll
             for (int k = 0; k < PPL; ++k) cls[k] += (int)(cw[k] & MASK) * mul;
             mul *= nsl;
-            advance();
+            shift_stream(bits);
           }
         }
         PH_MARK(5)
@@ -1010,8 +1012,134 @@ static int mma_width(int w) {
   return 0;
 }
 
+// Host image of a chain before upload: position 0 = leaf, steps, last = root; every position has
+// the same (padded) number of slices; matrices are CHI x CHI row-major in the real embedding.
+struct ChainImage {
+  int nsl = 1;
+  std::vector<double> leaf;               // [nsl][CHI]
+  std::vector<double> root;               // [nout][nsl][CHI]
+  std::vector<std::vector<double>> steps; // [t][nsl * CHI * CHI]
+};
+
+// Group merging (plan-time pre-contraction): k consecutive positions of a chain whose slice
+// indices are bit fields (bits0 bits each) are contracted into one position with 2^(k*bits0)
+// slices, slice index = sum_i s_i << (bits0 * i) with i = 0 the position nearest the leaf — i.e.
+// exactly the same packed bit stream read k*bits0 bits at a time — so K1 and the run fast path are
+// untouched while a point needs 1/k as many matrix-vector products.  Products are accumulated in
+// long double and rounded once.  Needs (#positions) % k == 0 and >= 2k positions.
+static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0) {
+  typedef long double ld;
+  const size_t M = (size_t)CHI * CHI;
+  const int T = (int)a.steps.size(), S0 = a.nsl, SK = 1 << (bits0 * k);
+  ChainImage m;
+  m.nsl = SK;
+  // extend a table of row vectors / matrices (rows x CHI each) by one chain member
+  auto extend = [&](const std::vector<ld>& cur, int n_cur, int rows, const std::vector<double>& E, int member) {
+    std::vector<ld> nxt((size_t)n_cur * (1 << bits0) * rows * CHI, 0.0L);
+    for (int s = 0; s < n_cur; ++s)
+      for (int bsl = 0; bsl < S0; ++bsl) {
+        const ld* A = cur.data() + (size_t)s * rows * CHI;
+        const double* B = E.data() + (size_t)bsl * M;
+        ld* C = nxt.data() + (size_t)(s + (bsl << (bits0 * member))) * rows * CHI;
+        for (int i = 0; i < rows; ++i)
+          for (int kk = 0; kk < CHI; ++kk) {
+            const ld av = A[(size_t)i * CHI + kk];
+            if (av == 0.0L) continue;
+            for (int j = 0; j < CHI; ++j) C[(size_t)i * CHI + j] += av * (ld)B[(size_t)kk * CHI + j];
+          }
+      }
+    return nxt;
+  };
+  // leaf group: leaf vectors times the first k-1 steps
+  {
+    std::vector<ld> cur((size_t)(1 << bits0) * CHI, 0.0L);
+    for (int s = 0; s < S0; ++s)
+      for (int j = 0; j < CHI; ++j) cur[(size_t)s * CHI + j] = a.leaf[(size_t)s * CHI + j];
+    int n_cur = 1 << bits0;
+    for (int i = 1; i < k; ++i) {
+      cur = extend(cur, n_cur, 1, a.steps[i - 1], i);
+      n_cur <<= bits0;
+    }
+    m.leaf.resize((size_t)SK * CHI);
+    for (size_t i = 0; i < m.leaf.size(); ++i) m.leaf[i] = (double)cur[i];
+  }
+  auto first_member = [&](const std::vector<double>& E) {
+    std::vector<ld> cur((size_t)(1 << bits0) * M, 0.0L);
+    for (int s = 0; s < S0; ++s)
+      for (size_t i = 0; i < M; ++i) cur[(size_t)s * M + i] = E[(size_t)s * M + i];
+    return cur;
+  };
+  // middle groups: steps [g*k - 1, g*k + k - 2]
+  const int G = (T + 2) / k;
+  for (int g = 1; g + 1 < G; ++g) {
+    std::vector<ld> cur = first_member(a.steps[g * k - 1]);
+    int n_cur = 1 << bits0;
+    for (int i = 1; i < k; ++i) {
+      cur = extend(cur, n_cur, CHI, a.steps[g * k - 1 + i], i);
+      n_cur <<= bits0;
+    }
+    std::vector<double> E((size_t)SK * M);
+    for (size_t i = 0; i < E.size(); ++i) E[i] = (double)cur[i];
+    m.steps.push_back(std::move(E));
+  }
+  // root group: the last k-1 steps times the root vectors
+  {
+    std::vector<ld> cur = first_member(a.steps[T - (k - 1)]);
+    int n_cur = 1 << bits0;
+    for (int i = 1; i < k - 1; ++i) {
+      cur = extend(cur, n_cur, CHI, a.steps[T - (k - 1) + i], i);
+      n_cur <<= bits0;
+    }
+    m.root.assign((size_t)nout * SK * CHI, 0.0);
+    for (int o = 0; o < nout; ++o)
+      for (int s = 0; s < n_cur; ++s)
+        for (int bsl = 0; bsl < S0; ++bsl)
+          for (int i = 0; i < CHI; ++i) {
+            ld acc = 0.0L;
+            for (int j = 0; j < CHI; ++j)
+              acc += cur[(size_t)s * M + (size_t)i * CHI + j] * (ld)a.root[((size_t)o * S0 + bsl) * CHI + j];
+            m.root[((size_t)o * SK + (s + (bsl << (bits0 * (k - 1))))) * CHI + i] = (double)acc;
+          }
+  }
+  return m;
+}
+
+static int upload_chain_image(ttn_plan* p, const ChainImage& im, int CHI, ChainMmaDev& c) {
+  const int NSL = im.nsl, T = (int)im.steps.size();
+  const size_t M = (size_t)CHI * CHI;
+  std::vector<double> frags((size_t)std::max(T, 1) * NSL * M, 0.0);
+  const int NB = CHI / 8, KB = CHI / 4;
+  for (int t = 0; t < T; ++t)
+    for (int s = 0; s < NSL; ++s) {
+      // B-fragment order: [kb][nb'][lane = 4 g' + t'] = E[8 (kb/2) + 2 t' + (kb%2)][8 nb' + g']
+      const double* E = im.steps[t].data() + (size_t)s * M;
+      double* F = frags.data() + ((size_t)t * NSL + s) * M;
+      for (int kb = 0; kb < KB; ++kb)
+        for (int nbp = 0; nbp < NB; ++nbp)
+          for (int ln = 0; ln < 32; ++ln) {
+            const int gp = ln >> 2, tp = ln & 3;
+            F[((size_t)kb * NB + nbp) * 32 + ln] = E[(size_t)(8 * (kb / 2) + 2 * tp + (kb % 2)) * CHI + 8 * nbp + gp];
+          }
+    }
+  double *d_leaf, *d_root, *d_frags;
+  TTN_CUDA(cudaMalloc(&d_leaf, im.leaf.size() * 8));
+  p->allocs.push_back(d_leaf);
+  TTN_CUDA(cudaMalloc(&d_root, im.root.size() * 8));
+  p->allocs.push_back(d_root);
+  TTN_CUDA(cudaMalloc(&d_frags, frags.size() * 8));
+  p->allocs.push_back(d_frags);
+  TTN_CUDA(cudaMemcpy(d_leaf, im.leaf.data(), im.leaf.size() * 8, cudaMemcpyHostToDevice));
+  TTN_CUDA(cudaMemcpy(d_root, im.root.data(), im.root.size() * 8, cudaMemcpyHostToDevice));
+  TTN_CUDA(cudaMemcpy(d_frags, frags.data(), frags.size() * 8, cudaMemcpyHostToDevice));
+  c.leaf = d_leaf;
+  c.root = d_root;
+  c.frags = d_frags;
+  return TTN_OK;
+}
+
 int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   p->cmma_ok = false;
+  p->cmma_plain_ok = false;
   if (!p->is_chain) return TTN_OK;
   const int n = d->n_vertices;
   const bool cplx = d->is_complex != 0;
@@ -1024,35 +1152,50 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   const int CHI = cplx ? mma_width(2 * maxchi) : mma_width(maxchi);
   const int H = CHI / 2; // complex: row = [re(H) | im(H)]
   if (CHI == 0 || maxsl > 4) return TTN_OK;
-  const int NSL = maxsl;
-  const int bits = NSL <= 1 ? 0 : (NSL <= 2 ? 1 : 2);
-  const int per_word = bits == 0 ? (1 << 30) : 64 / bits;
+  const int NSL0 = maxsl; // slices per vertex of the network as given
+  const int bits0 = NSL0 <= 1 ? 0 : (NSL0 <= 2 ? 1 : 2); // stream bits per VERTEX
+  // group merging (merge_groups): k vertices per stream position when the slice indices are bit
+  // fields, the merged position has <= 16 slices and one position's matrices stay <= 32 KB (one
+  // ring stage).  TTN_MMA_MERGE caps k (0 or 1: one vertex per position).
+  int kmerge = 1;
+  {
+    int kmax = 4;
+    if (const char* e = getenv("TTN_MMA_MERGE")) kmax = atoi(e);
+    if (NSL0 == 2 || NSL0 == 4)
+      for (int kk : {3, 2, 4}) // measured on B200 (scripts/merge_probe.py): 3 > 4 > 2 > 1 for binary chains
+        if (kk <= kmax && bits0 * kk <= 4 && ((size_t)1 << (bits0 * kk)) * CHI * CHI * 8 <= 32 * 1024 && n >= 2 * kk &&
+            (kk != 3 || CHI <= 16)) { // 3-bit fields straddle words: only the warp-autonomous kernel reads those
+          kmerge = kk;
+          break;
+        }
+  }
+  const bool merge = kmerge > 1;
 
   // sites per round: as many as keep the class count <= 4 (binary digits: 2 sites -> 4 classes)
   int spr = 1;
-  while (true) {
+  if (!merge) {
+    while (true) {
+      int cls = 1;
+      for (int k = 0; k < spr + 1; ++k) cls *= NSL0;
+      if (NSL0 <= 1 || cls > 4 || spr >= 4) break;
+      ++spr;
+    }
+    if (NSL0 <= 1) spr = 2;
+    if (const char* e = getenv("TTN_MMA_SPR")) spr = std::max(1, atoi(e));
     int cls = 1;
-    for (int k = 0; k < spr + 1; ++k) cls *= NSL;
-    if (NSL <= 1 || cls > 4 || spr >= 4) break;
-    ++spr;
-  }
-  if (NSL <= 1) spr = 2;
-  if (const char* e = getenv("TTN_MMA_SPR")) spr = std::max(1, atoi(e));
-  {
-    int cls = 1;
-    for (int k = 0; k < spr; ++k) cls *= std::max(NSL, 1);
+    for (int k = 0; k < spr; ++k) cls *= std::max(NSL0, 1);
     while (cls > kMaxClasses && spr > 1) {
       --spr;
-      cls /= NSL;
+      cls /= NSL0;
     }
   }
-  // the chain is padded with identity sites (slice bits always 0) up to a whole number of rounds,
-  // so that every round has exactly `spr` sites
+  // the chain is padded with identity sites (slice bits always 0) up to a whole number of rounds
+  // (merged: up to an even number of positions), so that every round has exactly `spr` sites
   const int n_steps = n >= 2 ? n - 2 : 0;
-  const int n_steps_p = (n_steps + spr - 1) / spr * spr;
-  const int root_pos = n >= 2 ? 1 + n_steps_p : 0;
+  const int n_steps_p = merge ? (n + kmerge - 1) / kmerge * kmerge - 2 : (n_steps + spr - 1) / spr * spr;
+  const int root_pos = n >= 2 ? 1 + n_steps_p : 0; // in vertices
   const int n_pos = root_pos + 1;
-  const int n_words = bits == 0 ? 0 : (n_pos + per_word - 1) / per_word;
+  const int n_words = bits0 == 0 ? 0 : (n_pos * bits0 + 63) / 64;
   if (n_words > 2) return TTN_OK;
 
   std::vector<int> order(n), pos_of(n);
@@ -1071,101 +1214,139 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     *im = cplx ? T[(d->tensor_ptr[v] + idx) * NC + 1] : 0.0;
   };
   const int nout = cplx ? 2 : 1;
-  std::vector<double> leaf((size_t)NSL * CHI, 0.0), root((size_t)nout * NSL * CHI, 0.0);
-  std::vector<double> frags((size_t)std::max(n_steps_p, 1) * NSL * CHI * CHI, 0.0);
+  const size_t M = (size_t)CHI * CHI;
+  ChainImage im;
+  im.nsl = NSL0;
+  im.leaf.assign((size_t)NSL0 * CHI, 0.0);
+  im.root.assign((size_t)nout * NSL0 * CHI, 0.0);
   {
     const int v = order[0], b = d->link_dim[v];
     for (int s = 0; s < p->nslices[v]; ++s)
       for (int j = 0; j < b; ++j) {
-        double re, im;
-        elem(v, (int64_t)s * b + j, &re, &im);
-        leaf[(size_t)s * CHI + j] = re;
-        if (cplx) leaf[(size_t)s * CHI + H + j] = im;
+        double re, imv;
+        elem(v, (int64_t)s * b + j, &re, &imv);
+        im.leaf[(size_t)s * CHI + j] = re;
+        if (cplx) im.leaf[(size_t)s * CHI + H + j] = imv;
       }
   }
   if (n >= 2) {
     const int v = order[n - 1], a = d->link_dim[order[n - 2]];
     for (int s = 0; s < p->nslices[v]; ++s)
       for (int i = 0; i < a; ++i) {
-        double re, im;
-        elem(v, (int64_t)s * a + i, &re, &im);
-        root[(size_t)s * CHI + i] = re; // out_re = v_re.R_re - v_im.R_im
+        double re, imv;
+        elem(v, (int64_t)s * a + i, &re, &imv);
+        im.root[(size_t)s * CHI + i] = re; // out_re = v_re.R_re - v_im.R_im
         if (cplx) {
-          root[(size_t)s * CHI + H + i] = -im;
-          root[((size_t)NSL + s) * CHI + i] = im; // out_im = v_re.R_im + v_im.R_re
-          root[((size_t)NSL + s) * CHI + H + i] = re;
+          im.root[(size_t)s * CHI + H + i] = -imv;
+          im.root[((size_t)NSL0 + s) * CHI + i] = imv; // out_im = v_re.R_im + v_im.R_re
+          im.root[((size_t)NSL0 + s) * CHI + H + i] = re;
         }
       }
   }
-  std::vector<double> E((size_t)CHI * CHI);
+  double flops_exec = 0.0;
+  std::vector<int> dim_in, dim_out;
+  dim_out.reserve(n_steps_p + 1);
   for (int t = 0; t < n_steps_p; ++t) {
     const bool dummy = t >= n_steps;
     const int v = dummy ? -1 : order[t + 1];
     const int a = dummy ? 0 : d->link_dim[order[t]], b = dummy ? 0 : d->link_dim[v];
-    for (int s = 0; s < (dummy ? NSL : p->nslices[v]); ++s) {
-      std::fill(E.begin(), E.end(), 0.0);
+    std::vector<double> Es((size_t)NSL0 * M, 0.0);
+    for (int s = 0; s < (dummy ? NSL0 : p->nslices[v]); ++s) {
+      double* E = Es.data() + (size_t)s * M;
       if (dummy) {
         for (int i = 0; i < CHI; ++i) E[(size_t)i * CHI + i] = 1.0;
       }
       for (int i = 0; i < a; ++i)
         for (int j = 0; j < b; ++j) {
-          double re, im;
-          elem(v, ((int64_t)s * a + i) * b + j, &re, &im);
+          double re, imv;
+          elem(v, ((int64_t)s * a + i) * b + j, &re, &imv);
           E[(size_t)i * CHI + j] = re;
           if (cplx) {
-            E[(size_t)i * CHI + H + j] = im;
-            E[(size_t)(H + i) * CHI + j] = -im;
+            E[(size_t)i * CHI + H + j] = imv;
+            E[(size_t)(H + i) * CHI + j] = -imv;
             E[(size_t)(H + i) * CHI + H + j] = re;
           }
         }
-      // B-fragment order: [kb][nb'][lane = 4 g' + t'] = E[8 (kb/2) + 2 t' + (kb%2)][8 nb' + g']
-      double* F = frags.data() + ((size_t)t * NSL + s) * CHI * CHI;
-      const int NB = CHI / 8, KB = CHI / 4;
-      for (int kb = 0; kb < KB; ++kb)
-        for (int nbp = 0; nbp < NB; ++nbp)
-          for (int ln = 0; ln < 32; ++ln) {
-            const int gp = ln >> 2, tp = ln & 3;
-            F[((size_t)kb * NB + nbp) * 32 + ln] = E[(size_t)(8 * (kb / 2) + 2 * tp + (kb % 2)) * CHI + 8 * nbp + gp];
-          }
     }
+    im.steps.push_back(std::move(Es));
+    flops_exec += (cplx ? 8.0 : 2.0) * a * b;
+    dim_in.push_back(dummy ? dim_out.back() : a);
+    dim_out.push_back(dummy ? dim_out.back() : b);
   }
-  double *d_leaf, *d_root, *d_frags;
-  TTN_CUDA(cudaMalloc(&d_leaf, leaf.size() * 8));
-  p->allocs.push_back(d_leaf);
-  TTN_CUDA(cudaMalloc(&d_root, root.size() * 8));
-  p->allocs.push_back(d_root);
-  TTN_CUDA(cudaMalloc(&d_frags, frags.size() * 8));
-  p->allocs.push_back(d_frags);
-  TTN_CUDA(cudaMemcpy(d_leaf, leaf.data(), leaf.size() * 8, cudaMemcpyHostToDevice));
-  TTN_CUDA(cudaMemcpy(d_root, root.data(), root.size() * 8, cudaMemcpyHostToDevice));
-  TTN_CUDA(cudaMemcpy(d_frags, frags.data(), frags.size() * 8, cudaMemcpyHostToDevice));
+  const double root_flops = n >= 2 ? (cplx ? 8.0 : 2.0) * d->link_dim[order[n - 2]] : 0.0;
+  p->cmma_flops_exec = flops_exec + root_flops;
+  if (merge) {
+    // one product per middle group: steps [g*k - 1, g*k + k - 2]
+    double fm = 0.0;
+    const int G = (n_steps_p + 2) / kmerge;
+    for (int g = 1; g + 1 < G; ++g) fm += (cplx ? 8.0 : 2.0) * dim_in[g * kmerge - 1] * dim_out[g * kmerge + kmerge - 2];
+    p->cmma_flops_exec = fm + (cplx ? 8.0 : 2.0) * dim_in[n_steps_p - (kmerge - 1)];
+  }
 
+  // the unmerged image stays available for the prefix-shared grid kernel (k_grid_share.cu)
   ChainMmaDev& c = p->cmma;
+  c = ChainMmaDev{};
   c.n_vertices = n;
-  c.n_steps = n_steps_p;
-  c.nsl = NSL;
   c.chi = CHI;
   c.nout = nout;
+  c.root_pos = root_pos / kmerge; // in stream positions
+  int rc;
+  if (NSL0 == 2) {
+    ChainMmaDev& q = p->cmma_plain;
+    q = ChainMmaDev{};
+    q.n_vertices = n;
+    q.chi = CHI;
+    q.nout = nout;
+    q.nsl = NSL0;
+    q.n_steps = n_steps_p;
+    if (!merge) {
+      if ((rc = upload_chain_image(p, im, CHI, q))) return rc;
+      p->cmma_plain_ok = true;
+    } else {
+      // identity padding is not part of the plain image the grid kernel walks
+      ChainImage plain = im;
+      plain.steps.resize(n_steps);
+      q.n_steps = n_steps;
+      if ((rc = upload_chain_image(p, plain, CHI, q))) return rc;
+      p->cmma_plain_ok = true;
+    }
+  }
+  int NSL = NSL0, bits = bits0;
+  if (merge) {
+    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0);
+    if ((rc = upload_chain_image(p, mg, CHI, c))) return rc;
+    NSL = mg.nsl;
+    bits = bits0 * kmerge;
+    spr = 1;
+    c.n_steps = (int)mg.steps.size();
+  } else if (p->cmma_plain_ok) {
+    c.leaf = p->cmma_plain.leaf;
+    c.root = p->cmma_plain.root;
+    c.frags = p->cmma_plain.frags;
+    c.n_steps = n_steps_p;
+  } else {
+    if ((rc = upload_chain_image(p, im, CHI, c))) return rc;
+    c.n_steps = n_steps_p;
+  }
+  c.merged = merge ? kmerge : 0;
+  c.nsl = NSL;
   c.bits = bits;
-  c.per_word = per_word;
+  c.per_word = bits == 0 ? (1 << 30) : 64 / bits;
   c.n_words = n_words;
-  c.root_pos = root_pos;
   c.spr = spr;
-  c.n_rounds = n_steps_p / spr;
-  c.leaf = d_leaf;
-  c.root = d_root;
-  c.frags = d_frags;
+  c.n_rounds = c.n_steps / spr;
 
-  // the DMMA kernels get their own copy of the digit table: (word, shift) follow THEIR packed
-  // stream positions (identity padding shifts the root)
+  // the DMMA kernels get their own copy of the digit table: (word, shift) are the BIT position of
+  // the vertex in THEIR packed stream (identity padding shifts the root; a merged position reads
+  // the bits of its two vertices as one 2-bit slice index)
   p->digits_mma = p->digits;
+  std::vector<DigitEntry> ent(std::max(d->n_sites, 1));
   if (d->n_sites > 0) {
-    std::vector<DigitEntry> ent(d->n_sites);
     TTN_CUDA(cudaMemcpy(ent.data(), p->digits.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
-    for (auto& e : ent) {
-      const int pos = pos_of[e.vertex];
-      e.word = bits ? pos / per_word : 0;
-      e.shift = bits ? (pos % per_word) * bits : 0;
+    for (int i = 0; i < d->n_sites; ++i) {
+      const int bitpos = pos_of[ent[i].vertex] * bits0;
+      ent[i].word = bits0 ? bitpos / 64 : 0;
+      ent[i].shift = bits0 ? bitpos % 64 : 0;
     }
     DigitEntry* d_ent;
     TTN_CUDA(cudaMalloc(&d_ent, sizeof(DigitEntry) * d->n_sites));
@@ -1175,18 +1356,15 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   }
   // K1 "run" fast path per coordinate slot.  Conditions (all checked here, bitwise):
   //   every site index of the slot is binary, its vertex carries no other site index (1 bit per
-  //   chain position), the digit numbers are exactly 1..L with thresholds exactly 2^-k, L <= 63, and
-  //   the digits sit on CONSECUTIVE chain positions in increasing or decreasing order.
+  //   vertex), the digit numbers are exactly 1..L with thresholds exactly 2^-k, L <= 63, and
+  //   the digits sit on CONSECUTIVE stream bits in increasing or decreasing order.
   // Then the greedy loop (abstractindexmap.jl:121-138) yields digit k = bit (L-k) of floor(x * 2^L):
   // x >= 2^-k ? subtract : keep is exact in binary floating point (the subtraction clears the leading
   // bit), the scaling by 2^L is exact, and x >= 1 saturates to all ones exactly as the loop does.
   for (int cidx = 0; cidx < TTN_MAX_COORDS; ++cidx) c.run_L[cidx] = 0;
-  if (bits == 1) {
+  if (bits0 == 1) {
     std::vector<int32_t> cptr(d->n_coords + 1);
-    std::vector<DigitEntry> ent(std::max(d->n_sites, 1));
     TTN_CUDA(cudaMemcpy(cptr.data(), p->digits_mma.coord_ptr, sizeof(int32_t) * (d->n_coords + 1), cudaMemcpyDeviceToHost));
-    if (d->n_sites > 0)
-      TTN_CUDA(cudaMemcpy(ent.data(), p->digits_mma.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
     for (int cidx = 0; cidx < d->n_coords; ++cidx) {
       const int L = cptr[cidx + 1] - cptr[cidx];
       if (L < 1 || L > 63) continue;
@@ -1194,7 +1372,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       int step = 0, first_pos = -1;
       for (int k = 0; k < L && ok; ++k) {
         const DigitEntry& e = ent[cptr[cidx] + k];
-        const int pos = e.word * per_word + e.shift;
+        const int pos = e.word * 64 + e.shift;
         ok = ok && e.base == 2 && e.stride == 1 && p->nslices[e.vertex] == 2;
         ok = ok && d->site_digit[e.site] == k + 1 && d->thr[e.thr_off + 1] == std::ldexp(1.0, -(k + 1));
         if (k == 0) first_pos = pos;
@@ -1290,20 +1468,28 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   // with 1 site per round; everything else takes the runtime-generic instance
   const bool f22 = p->all_base2 && c.nsl == 2 && c.spr == 2;
   const bool f41 = p->all_base2 && c.nsl == 4 && c.spr == 1;
+  const bool f161 = p->all_base2 && c.nsl == 16 && c.spr == 1; // 4 merged binary vertices per position
+  const bool f81 = p->all_base2 && c.nsl == 8 && c.spr == 1;   // 3 merged binary vertices per position
   // the warp-autonomous kernel's 2-sites-per-round instance has no partial last round
   const bool f22w = f22 && c.n_steps % 2 == 0;
   if (p->digits.n_sites > kFeMaxSites || p->info.n_sites > kFeMaxSites || p->fe_thr_len > kFeMaxThr) {
     set_error("DMMA chain kernel: digit tables exceed the kernel's shared-memory copies (160 sites / 640 thresholds)");
     return TTN_ERR_UNSUPPORTED;
   }
+  static const int force_v3 = getenv("TTN_MMA_V3") ? atoi(getenv("TTN_MMA_V3")) : 0; // experiments
   switch (c.chi) {
     case 8: // warp-autonomous kernel (v5)
       if (f22w) return launch_mma5_inst<8, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
       if (f41) return launch_mma5_inst<8, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+      if (f81) return launch_mma5_inst<8, 8, 4, true, 8, 1>(p, src, d_out, d_partial, n_partial, s);
+      if (f161) return launch_mma5_inst<8, 8, 4, true, 16, 1>(p, src, d_out, d_partial, n_partial, s);
       return launch_mma5_inst<8, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
     case 16:
+      if (f161 && force_v3) return launch_mma3_inst<16, 1024, 8, 4, true, 16, 1>(p, src, d_out, d_partial, n_partial, s);
       if (f22w) return launch_mma5_inst<16, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
       if (f41) return launch_mma5_inst<16, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
+      if (f81) return launch_mma5_inst<16, 8, 4, true, 8, 1>(p, src, d_out, d_partial, n_partial, s);
+      if (f161) return launch_mma5_inst<16, 8, 4, true, 16, 1>(p, src, d_out, d_partial, n_partial, s);
       return launch_mma5_inst<16, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
     case 32: // CTA-sorted, warp-specialised kernel (v3): 128 rows per warp would not fit at this width
       if (f22) return launch_mma3_inst<32, 512, 8, 3, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);

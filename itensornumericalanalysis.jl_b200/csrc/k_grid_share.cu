@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256, 1)
 // 1..L_c per coordinate slot.
 int build_grid_share(ttn_plan* p, const ttn_desc* d) {
   p->gshare_ok = false;
-  if (!p->cmma_ok || p->cmma.nsl != 2 || !p->all_base2 || d->n_vertices < 2) return TTN_OK;
+  if (!p->cmma_ok || !p->cmma_plain_ok || p->cmma_plain.nsl != 2 || !p->all_base2 || d->n_vertices < 2) return TTN_OK;
   const int n = d->n_vertices;
   for (int v = 0; v < n; ++v)
     if (p->nslices[v] != 2 || d->site_ptr[v + 1] - d->site_ptr[v] != 1) return TTN_OK;
@@ -256,7 +256,7 @@ bool grid_share_applicable(const ttn_plan* p, const CoordSource& src) {
     total *= src.count[c];
   }
   if (src.npts != total) return false;
-  const int n = p->cmma.n_vertices;
+  const int n = p->cmma_plain.n_vertices;
   if (n - 1 > 40) return false; // 2^40 points and more: not a realistic dense grid
   return true;
 }
@@ -297,7 +297,7 @@ static int launch_expand_d(int D, bool final_, const GridShareArgs& A, int sm_co
 int launch_grid_share(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                       int* n_partial, cudaStream_t s, int* n_launches, double* flops_executed) {
   *n_partial = 0;
-  const ChainMmaDev& c = p->cmma;
+  const ChainMmaDev& c = p->cmma_plain;
   const int n = c.n_vertices, CHI = c.chi;
   const int n_mid = n - 2;
   constexpr int DMAX = 5;

@@ -99,6 +99,7 @@ struct ChainMmaDev {
   int32_t nout;     // 1 (real) or 2 (re, im)
   int32_t bits, per_word, n_words;
   int32_t root_pos; // position of the root in the packed slice stream (after identity padding)
+  int32_t merged;   // 1: vertex pairs pre-contracted into 4-slice positions (build_chain_mma)
   // per coordinate slot: "run" fast path of K1 (see build_chain_mma): L == 0 -> use the table loop
   int32_t run_L[TTN_MAX_COORDS];     // number of binary digits
   int32_t run_plow[TTN_MAX_COORDS];  // lowest stream position of the run
@@ -163,6 +164,9 @@ struct ttn_plan {
   ttn::ChainDev chain{};
   bool chain_ok = false;
   ttn::ChainMmaDev cmma{};
+  ttn::ChainMmaDev cmma_plain{}; // one vertex per position (leaf/root/frags only): grid-share kernel
+  bool cmma_plain_ok = false;
+  double cmma_flops_exec = 0.0;  // flops per point the DMMA chain kernel executes (merged: about half the rule)
   bool cmma_ok = false;
   ttn::ChainGemmDev cgemm{};
   bool cgemm_ok = false;

@@ -233,7 +233,13 @@ def test_linearity_at_scale():
     rng = np.random.default_rng(3)
     pts = rng.random((1_000_000, 2))
     a, b, c = t.evaluate(f1, pts), t.evaluate(f2, pts), t.evaluate(f1 + f2, pts)
-    assert orc.error_metric(c, a + b).max() < TOL
+    # a and b each carry ~1e-13 relative error, so the comparison is relative to |a| + |b| (where
+    # a ~ -b the sum a + b itself loses digits to cancellation), floored like SURVEY §8(d)'s metric
+    scale = np.maximum(np.abs(a) + np.abs(b), 1e-3 * np.sqrt(np.mean(np.abs(a + b) ** 2)))
+    lin = np.abs(c - (a + b)) / scale
+    # three FP64 evaluations of a 60-site chain: at the maximum over 10^6 points none of them stays
+    # below 1e-12 (see the audit below), so the bar is the same as there
+    assert np.quantile(lin, 0.9999) < TOL and lin.max() < 1e-11
     # Audited sample against the 80-bit oracle.  Over 10^4+ points of a 60-site random chain NO
     # FP64 evaluation stays below 1e-12 at the maximum: the CPU restatements of the reference's own
     # arithmetic reach 3.5e-12 (plain FP64) and 4.4e-12 (two-way BP + exp(sum log)) over 3e5
@@ -389,3 +395,47 @@ def test_evaluate_at_index_settings(which):
     with pytest.raises(_capi.TTNError) as e:
         plan.evaluate_indices_host(bad)
     assert e.value.code == _capi.TTN_ERR_INVALID
+
+
+@pytest.mark.parametrize("kmax", ["1", "2", "3", "4"])
+def test_merged_chain_images(kmax, monkeypatch):
+    """Plan-time group merging of the DMMA chain kernel (k vertices pre-contracted per stream
+    position, k <= TTN_MMA_MERGE): every chain length 2..14 (identity padding, leaf/root groups of
+    every size), real and complex, one and two digits per vertex (complex maps), ragged link dimensions — values
+    against the 80-bit oracle, digits untouched, and the same point gives the same bits wherever
+    it sits in the batch."""
+    monkeypatch.setenv("TTN_MMA_MERGE", kmax)
+    rng = np.random.default_rng(int(kmax))
+    nets = []
+    for L in range(2, 15):
+        s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=1 + (L % 2 if L >= 4 else 0))
+        nets.append((f"mps{L}_chi{8 + 8 * (L % 2)}", t.rand_itn(s, link_space=8 + 8 * (L % 2), rng=L, normalise=True)))
+    s = t.continuous_siteinds(t.named_grid((9, 1)), map_dimension=1)
+    nets.append(("mps9_cplx_chi8", t.rand_itn(s, link_space=8, rng=1, eltype=complex, normalise=True)))
+    nets.append(("mps9_ragged", t.rand_itn(s, link_space=8, rng=2, normalise=True) + t.cosh_itn(s, k=0.7, a=0.2, c=0.5)))
+    s = t.continuous_siteinds(t.named_grid((21, 1)), map_dimension=1)
+    nets.append(("mps21_chi32", t.rand_itn(s, link_space=32, rng=3, normalise=True)))
+    # default complex map: Real + Imag digit on every vertex (4 slices per vertex, two vertices -> 16)
+    sc = t.complex_continuous_siteinds(t.named_grid((7, 1)))
+    nets.append(("cplx_map7", t.rand_itn(sc, link_space=6, rng=5, eltype=complex, normalise=True)))
+    sc = t.complex_continuous_siteinds(t.named_grid((8, 1)), map_dimension=2)
+    nets.append(("cplx_map8_2d", t.rand_itn(sc, link_space=4, rng=6, eltype=complex, normalise=True)))
+    for name, f in nets:
+        f._plans.clear()
+        dims = f.indexmap.dimensions()
+        plan = f.plan(dims)
+        if isinstance(f.indexmap, t.ComplexIndexMap):
+            pts = cases.complex_points(8, len(dims), rng, 300)
+        else:
+            pts = cases.edge_points(8, len(dims), rng, 300)
+        coords = coords_of(plan.packed, pts)
+        assert (plan.digits_host(coords) == orc.digits(plan.packed, coords)).all()
+        ref = orc.evaluate(plan.packed, coords, orc.ORACLE_LD)
+        got, o = plan.evaluate_host(coords, kernel="dmma")
+        assert o.kernel_used == _capi.TTN_KERNEL_DMMA
+        err = orc.error_metric(got, ref).max()
+        assert err < TOL, (name, kmax, err)
+        perm = rng.permutation(len(coords))
+        got2, _ = plan.evaluate_host(coords[perm], kernel="dmma")
+        assert (got2 == got[perm]).all(), name
+        f._plans.clear()
