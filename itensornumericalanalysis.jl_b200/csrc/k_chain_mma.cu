@@ -1004,6 +1004,344 @@ __global__ void __launch_bounds__(NMW * 32 + 32, 1)
   }
 }
 
+// =====================================================================================
+// v6: team-sorted, B-stationary kernel for MERGED binary chains (one stream position per round,
+// NCLS = 4, 8 or 16 slices per position).  A CTA holds NTEAM independent teams of 4 warps; a team
+// owns a tile of 512 points.
+//  * every warp is "home" to 128 points of the tile: K1, leaf rows, class counts, root;
+//  * per round the team counting-sorts its 512 points by class: per-warp match.any counts, one
+//    word of 4 byte counters per class in shared memory, ONE team barrier per round (the counts of
+//    round r+1 are published before the barrier of round r);
+//  * warp w then owns classes w, w+4, ...: the class's site matrix sits in REGISTERS as DMMA B
+//    fragments (read from L2 one class ahead) while the warp streams the class's rows through
+//    gather -> DMMA -> scatter.  No B traffic through shared memory, class padding amortised over
+//    512 points, and the teams drift apart so one team's sort hides under the other's DMMAs.
+template <int CHI, int NBAT>
+__device__ __forceinline__ void batch6(uint32_t state_base, const int (&rows)[4], int tq, int zrow,
+                                       const double (&bf)[(CHI / 4) * (CHI / 8)]) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+  double a[NBAT][KB], d[NBAT][KB];
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
+      a[b][2 * nb] = v.x;
+      a[b][2 * nb + 1] = v.y;
+      d[b][2 * nb] = 0.0;
+      d[b][2 * nb + 1] = 0.0;
+    }
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+    for (int nbp = 0; nbp < NB; ++nbp)
+#pragma unroll
+      for (int b = 0; b < NBAT; ++b) dmma884(d[b][2 * nbp], d[b][2 * nbp + 1], a[b][kb], bf[kb * NB + nbp]);
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+    if (rows[b] != zrow) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), d[b][2 * nb], d[b][2 * nb + 1]);
+    }
+}
+
+template <int CHI, int NCLS>
+struct Team6 {
+  static constexpr int TW = 4, PW = 128, TP = TW * PW;
+  static constexpr int LIST_CAP = TP + 8 * NCLS;
+  static constexpr size_t STATE_BYTES = (size_t)(TP + 8) * CHI * 8;
+  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 2 * 16 * 4 + 127) / 128 * 128;
+};
+
+template <int CHI, int NCLS, int NTEAM>
+__global__ void __launch_bounds__(NTEAM * 128, 1)
+    chain_mma6_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
+                      double* __restrict__ partial, int do_sum) {
+  using T6 = Team6<CHI, NCLS>;
+  constexpr int TW = T6::TW, PW = T6::PW, PPL = PW / 32, TP = T6::TP;
+  constexpr int CPW = NCLS / TW;           // classes owned by a warp
+  constexpr int BITS = slice_bits(NCLS);
+  constexpr int NB = CHI / 8, KB = CHI / 4, CPR = CHI / 2;
+  constexpr int NBF = KB * NB;             // B-fragment doubles per lane per class
+  constexpr int NW = (NCLS + 3) / 4;       // words of 4 byte counters
+  constexpr int LIST_CAP = T6::LIST_CAP;
+  constexpr int ZROW = TP;                 // the team's all-zero row (class padding target)
+  constexpr int NT = NTEAM * TW * 32;
+  static_assert(NCLS % TW == 0 && NCLS <= 16 && (NCLS & (NCLS - 1)) == 0, "class count");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[2][NTEAM * TW];
+  __shared__ Digit2 s_d2[kFeMaxSites];
+  __shared__ int s_cptr[TTN_MAX_COORDS + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int team = tid / (TW * 32), warp = (tid >> 5) % TW;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
+  for (int i = tid; i < dg.n_sites; i += NT) {
+    const DigitEntry e = dg.entries[i];
+    Digit2 d2;
+    d2.thr1 = dg.thr[e.thr_off + 1];
+    d2.sh = (uint32_t)e.shift;
+    d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+    s_d2[i] = d2;
+  }
+  unsigned char* tbase = smem + (size_t)team * T6::BYTES;
+  const uint32_t state_base = smem_u32(tbase);
+  uint16_t* lists = reinterpret_cast<uint16_t*>(tbase + T6::STATE_BYTES);     // [2][LIST_CAP]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);           // [2][16]: 4 byte counters (one per warp)
+  for (int i = tid % (TW * 32); i < 8 * CHI; i += TW * 32)
+    reinterpret_cast<double*>(tbase + (size_t)TP * CHI * 8)[i] = 0.0;
+  __syncthreads();
+
+  const int bar_id = 1 + team;
+  const int64_t n_tiles = (src.npts + TP - 1) / TP;
+  const int64_t tstride = (int64_t)gridDim.x * NTEAM;
+  const int R = ch.n_rounds;
+  const uint64_t MASK = (uint64_t)(NCLS - 1);
+  const uint32_t lt = (1u << lane) - 1u;
+  double sum_re = 0.0, sum_im = 0.0;
+
+  // B fragments of class c of round r (fragment order, see build_chain_mma): 32 consecutive doubles per (kb, nb)
+  double bcur[NBF], bnxt[NBF];
+  auto load_b = [&](double (&b)[NBF], int r, int c) {
+    const double* F = ch.frags + ((size_t)r * NCLS + c) * (CHI * CHI) + lane;
+#pragma unroll
+    for (int i = 0; i < NBF; ++i) b[i] = __ldg(F + i * 32);
+  };
+  if (R > 0) load_b(bcur, 0, warp);
+
+  for (int64_t tile = (int64_t)blockIdx.x * NTEAM + team; tile < n_tiles; tile += tstride) {
+    const int64_t p0 = tile * TP + warp * PW; // first home point of this warp
+    uint64_t w1[PPL], cw[PPL];
+    {
+      // ---- K1: digits of the lane's PPL home points (interleaved for ILP)
+      uint64_t w0[PPL];
+      double x[PPL];
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
+      for (int c = 0; c < dg.n_coords; ++c) {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int64_t p = p0 + k * 32 + lane;
+          x[k] = 0.0;
+          if (p < src.npts) {
+            x[k] = load_coord(src, p, c);
+            if (!coord_in_domain(x[k])) {
+              atomicOr(err, 1);
+              x[k] = 0.0;
+            }
+          }
+        }
+        if (ch.run_L[c] > 0 && !src.digits) {
+          const int L = ch.run_L[c], plow = ch.run_plow[c];
+          const double scale = ch.run_scale[c];
+          const bool rev = ch.run_rev[c] != 0;
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+            if (rev) q = __brevll(q) >> (64 - L);
+            if (plow < 64) {
+              w0[k] += q << plow;
+              if (plow + L > 64) w1[k] += q >> (64 - plow);
+            } else {
+              w1[k] += q << (plow - 64);
+            }
+          }
+        } else {
+          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+            const Digit2 e = s_d2[e_i];
+            const uint32_t stride = e.wv & 0xffu;
+            const bool hi = ((e.wv >> 8) & 0xffu) != 0;
+#pragma unroll
+            for (int k = 0; k < PPL; ++k) {
+              const bool ge = src.digits ? (given_digit(src, p0 + k * 32 + lane, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                         : (x[k] >= e.thr1);
+              x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
+              const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+              if (hi) w1[k] += bb;
+              else w0[k] += bb;
+            }
+          }
+        }
+      }
+      // ---- leaf rows
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = w0[k];
+        const int row = warp * PW + k * 32 + lane;
+        const double* L = ch.leaf + (size_t)(cw[k] & MASK) * CHI;
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
+      }
+    }
+    auto shift_stream = [&]() {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = (cw[k] >> BITS) | (w1[k] << (64 - BITS));
+        w1[k] >>= BITS;
+      }
+    };
+    shift_stream();
+
+    // classes of the next stream position: per-warp counting (match.any + packed redux.add), the
+    // warp's per-class totals go to byte `warp` of cnt[buf][class]; info[k] = class | position
+    // of the point among the warp's points of that class << 8
+    uint32_t info[PPL];
+    auto count_and_publish = [&](int buf) {
+      int cls[PPL];
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) cls[k] = (int)(cw[k] & MASK);
+      shift_stream();
+      uint32_t bw[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) bw[w] = 0;
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const uint32_t m = __match_any_sync(0xffffffffu, cls[k]);
+        const uint32_t rank = __popc(m & lt);
+        const bool leader = (m & lt) == 0u;
+        const uint32_t contrib = leader ? ((uint32_t)__popc(m) << (8 * (cls[k] & 3))) : 0u;
+        const int cwd = cls[k] >> 2, csh = 8 * (cls[k] & 3);
+        uint32_t before = bw[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) before = (cwd == w) ? bw[w] : before;
+        info[k] = (uint32_t)cls[k] | ((((before >> csh) & 255u) + rank) << 8);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) bw[w] += __reduce_add_sync(0xffffffffu, (cwd == w) ? contrib : 0u);
+      }
+      if (lane < NCLS) {
+        uint32_t word = bw[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) word = ((lane >> 2) == w) ? bw[w] : word;
+        reinterpret_cast<uint8_t*>(cnt + buf * 16)[lane * 4 + warp] = (uint8_t)((word >> (8 * (lane & 3))) & 255u);
+      }
+    };
+    if (R > 0) count_and_publish(0);
+    named_bar_sync(bar_id, TW * 32); // leaf rows + counts of round 0
+
+    for (int r = 0; r < R; ++r) {
+      const int buf = r & 1;
+      uint16_t* list = lists + buf * LIST_CAP;
+      // ---- list of round r: lane c holds class c's total, padded start and this warp's offset
+      const uint32_t packed = (lane < NCLS) ? cnt[buf * 16 + lane] : 0u;
+      const int b0 = packed & 255u, b1 = (packed >> 8) & 255u, b2 = (packed >> 16) & 255u, b3 = packed >> 24;
+      const int total = b0 + b1 + b2 + b3;
+      const int woff = (warp > 0 ? b0 : 0) + (warp > 1 ? b1 : 0) + (warp > 2 ? b2 : 0);
+      const int padded = (total + 7) & ~7;
+      int incl = padded;
+#pragma unroll
+      for (int o = 1; o < NCLS; o <<= 1) {
+        const int nn = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nn;
+      }
+      const int mystart = incl - padded;
+      const int mybase = mystart + woff;
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int st = __shfl_sync(0xffffffffu, mybase, (int)(info[k] & 255u));
+        list[st + (int)(info[k] >> 8)] = (uint16_t)(warp * PW + k * 32 + lane);
+      }
+      for (int c0 = 4 * warp; c0 < NCLS; c0 += 4 * TW) { // class padding -> zero row
+        const int pc = c0 + (lane >> 3), pi = lane & 7;
+        const int cn = __shfl_sync(0xffffffffu, total, pc & 15), cs = __shfl_sync(0xffffffffu, mystart, pc & 15);
+        if (pc < NCLS && (cn & 7) && pi >= (cn & 7)) list[cs + (cn & ~7) + pi] = (uint16_t)ZROW;
+      }
+      if (r + 1 < R) count_and_publish(buf ^ 1);
+      named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 published
+
+      // ---- owned classes: B in registers, rows streamed through gather -> DMMA -> scatter
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) {
+        const int c = warp + j * TW;
+        {
+          // prefetch the next class in the flattened (round, class) sequence; the sequence of the
+          // next tile starts again at (0, warp)
+          const int rn = (j + 1 < CPW) ? r : ((r + 1 < R) ? r + 1 : 0);
+          const int cn_ = (j + 1 < CPW) ? c + TW : warp;
+          load_b(bnxt, rn, cn_);
+        }
+        const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
+        const int ng = (n_c + 7) >> 3;
+        const uint16_t* Lc = list + st;
+        int rows_nx[4];
+        if (ng > 0) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) rows_nx[b] = (int)Lc[(min(b, ng - 1) << 3) + g];
+        }
+        for (int gi = 0; gi < ng; gi += 4) {
+          const int nbat = min(4, ng - gi);
+          int rows[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) rows[b] = rows_nx[b];
+          if (gi + 4 < ng) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) rows_nx[b] = (int)Lc[(min(gi + 4 + b, ng - 1) << 3) + g];
+          }
+          if (nbat == 4) batch6<CHI, 4>(state_base, rows, tq, ZROW, bcur);
+          else if (nbat == 3) batch6<CHI, 3>(state_base, rows, tq, ZROW, bcur);
+          else if (nbat == 2) batch6<CHI, 2>(state_base, rows, tq, ZROW, bcur);
+          else batch6<CHI, 1>(state_base, rows, tq, ZROW, bcur);
+        }
+#pragma unroll
+        for (int i = 0; i < NBF; ++i) bcur[i] = bnxt[i];
+      }
+    }
+    if (R > 0) named_bar_sync(bar_id, TW * 32); // rows of the last round complete
+
+    // ---- root: out = row . R[d_{n-1}] for the home rows
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+      const int row = warp * PW + k * 32 + lane;
+      const int64_t p = p0 + k * 32 + lane;
+      const double* R0 = ch.root + (size_t)(cw[k] & MASK) * CHI;
+      const double* R1 = R0 + (size_t)NCLS * CHI;
+      double o0 = 0.0, o1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) {
+        const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+        o0 = fma(v.x, __ldg(R0 + 2 * j), o0);
+        o0 = fma(v.y, __ldg(R0 + 2 * j + 1), o0);
+        if (ch.nout == 2) {
+          o1 = fma(v.x, __ldg(R1 + 2 * j), o1);
+          o1 = fma(v.y, __ldg(R1 + 2 * j + 1), o1);
+        }
+      }
+      if (p < src.npts) {
+        if (out) {
+          if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+          else out[p] = o0;
+        }
+        accumulate_point(src, p, o0, o1, sum_re, sum_im);
+      }
+    }
+    // the next tile's leaf rows overwrite home rows only: no barrier needed here, the first barrier
+    // of the next tile orders them before any other warp's gather
+  }
+
+  if (do_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
+      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
+    }
+    if (lane == 0) {
+      red[0][tid >> 5] = sum_re;
+      red[1][tid >> 5] = sum_im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double xx = 0.0, yy = 0.0;
+      for (int w = 0; w < NTEAM * TW; ++w) {
+        xx += red[0][w];
+        yy += red[1][w];
+      }
+      partial[2 * blockIdx.x] = xx;
+      partial[2 * blockIdx.x + 1] = yy;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ host side
 
 static int mma_width(int w) {
@@ -1159,11 +1497,16 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // ring stage).  TTN_MMA_MERGE caps k (0 or 1: one vertex per position).
   int kmerge = 1;
   {
-    int kmax = 4;
-    if (const char* e = getenv("TTN_MMA_MERGE")) kmax = atoi(e);
+    // measured on B200 (scripts/merge_probe.py): 4 > 3 > 2 > 1 for binary chains; TTN_MMA_MERGE=k
+    // asks for exactly k (falling back to smaller groups when k does not apply)
+    std::vector<int> cand = {4, 3, 2};
+    if (const char* e = getenv("TTN_MMA_MERGE")) {
+      cand.clear();
+      for (int kk = std::min(atoi(e), 4); kk >= 2; --kk) cand.push_back(kk);
+    }
     if (NSL0 == 2 || NSL0 == 4)
-      for (int kk : {3, 2, 4}) // measured on B200 (scripts/merge_probe.py): 3 > 4 > 2 > 1 for binary chains
-        if (kk <= kmax && bits0 * kk <= 4 && ((size_t)1 << (bits0 * kk)) * CHI * CHI * 8 <= 32 * 1024 && n >= 2 * kk &&
+      for (int kk : cand)
+        if (bits0 * kk <= 4 && ((size_t)1 << (bits0 * kk)) * CHI * CHI * 8 <= 32 * 1024 && n >= 2 * kk &&
             (kk != 3 || CHI <= 16)) { // 3-bit fields straddle words: only the warp-autonomous kernel reads those
           kmerge = kk;
           break;
@@ -1454,6 +1797,23 @@ static int launch_mma5_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
   return TTN_OK;
 }
 
+template <int CHI, int NCLS, int NTEAM>
+static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                            cudaStream_t s) {
+  using T6 = Team6<CHI, NCLS>;
+  const ChainMmaDev& c = p->cmma;
+  const size_t smem = (size_t)NTEAM * T6::BYTES;
+  auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (src.npts + T6::TP - 1) / T6::TP;
+  const int grid = (int)std::min<int64_t>((n_tiles + NTEAM - 1) / NTEAM, p->sm_count);
+  const int do_sum = d_partial != nullptr;
+  kern<<<grid, NTEAM * 128, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum);
+  TTN_CUDA(cudaGetLastError());
+  *n_partial = do_sum ? grid : 0;
+  return TTN_OK;
+}
+
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
                      int* n_partial, cudaStream_t s) {
   (void)st;
@@ -1477,6 +1837,23 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     return TTN_ERR_UNSUPPORTED;
   }
   static const int force_v3 = getenv("TTN_MMA_V3") ? atoi(getenv("TTN_MMA_V3")) : 0; // experiments
+  // merged binary chains of width <= 16: team-sorted, B-stationary kernel (v6), 3 teams per CTA
+  // (TTN_MMA_V6=0 falls back to the warp-autonomous kernel, =2 runs two teams: experiments)
+  static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
+  if (v6 && c.merged && p->all_base2 && c.spr == 1 && (c.chi == 16 || c.chi == 8) &&
+      (c.nsl == 4 || c.nsl == 8 || c.nsl == 16)) {
+#define TTN_V6_CASE(W, N)                                                                                   \
+  if (c.chi == W && c.nsl == N)                                                                             \
+    return v6 == 2 ? launch_mma6_inst<W, N, 2>(p, src, d_out, d_partial, n_partial, s)                      \
+                   : launch_mma6_inst<W, N, 3>(p, src, d_out, d_partial, n_partial, s);
+    TTN_V6_CASE(16, 4)
+    TTN_V6_CASE(16, 8)
+    TTN_V6_CASE(16, 16)
+    TTN_V6_CASE(8, 4)
+    TTN_V6_CASE(8, 8)
+    TTN_V6_CASE(8, 16)
+#undef TTN_V6_CASE
+  }
   switch (c.chi) {
     case 8: // warp-autonomous kernel (v5)
       if (f22w) return launch_mma5_inst<8, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
