@@ -1050,7 +1050,7 @@ struct Team6 {
   static constexpr int TW = 4, PW = 128, TP = TW * PW;
   static constexpr int LIST_CAP = TP + 8 * NCLS;
   static constexpr size_t STATE_BYTES = (size_t)(TP + 8) * CHI * 8;
-  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 2 * 16 * 4 + 127) / 128 * 128;
+  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 3 * 32 * 4 + 127) / 128 * 128;
 };
 
 template <int CHI, int NCLS, int NTEAM>
@@ -1063,10 +1063,10 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   constexpr int BITS = slice_bits(NCLS);
   constexpr int NB = CHI / 8, KB = CHI / 4, CPR = CHI / 2;
   constexpr int NBF = KB * NB;             // B-fragment doubles per lane per class
-  constexpr int NW = (NCLS + 3) / 4;       // words of 4 byte counters
   constexpr int LIST_CAP = T6::LIST_CAP;
   constexpr int ZROW = TP;                 // the team's all-zero row (class padding target)
   constexpr int NT = NTEAM * TW * 32;
+  constexpr int PAR_BIT = (CHI >= 16) ? 2 : 0;  // row bit that selects the bank half of a 64-byte piece
   static_assert(NCLS % TW == 0 && NCLS <= 16 && (NCLS & (NCLS - 1)) == 0, "class count");
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1089,7 +1089,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   unsigned char* tbase = smem + (size_t)team * T6::BYTES;
   const uint32_t state_base = smem_u32(tbase);
   uint16_t* lists = reinterpret_cast<uint16_t*>(tbase + T6::STATE_BYTES);     // [2][LIST_CAP]
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);           // [2][16]: 4 byte counters (one per warp)
+  uint32_t* hist = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);          // [3][2][16] (class, parity) counters
+  for (int i = tid % (TW * 32); i < 96; i += TW * 32) hist[i] = 0u;
   for (int i = tid % (TW * 32); i < 8 * CHI; i += TW * 32)
     reinterpret_cast<double*>(tbase + (size_t)TP * CHI * 8)[i] = 0.0;
   __syncthreads();
@@ -1101,6 +1102,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   const uint64_t MASK = (uint64_t)(NCLS - 1);
   const uint32_t lt = (1u << lane) - 1u;
   double sum_re = 0.0, sum_im = 0.0;
+  int qh = 0; // global round counter of the team (rotates the counter sets)
 
   // B fragments of class c of round r (fragment order, see build_chain_mma): 32 consecutive doubles per (kb, nb)
   double bcur[NBF], bnxt[NBF];
@@ -1184,50 +1186,34 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     };
     shift_stream();
 
-    // classes of the next stream position: per-warp counting (match.any + packed redux.add), the
-    // warp's per-class totals go to byte `warp` of cnt[buf][class]; info[k] = class | position
-    // of the point among the warp's points of that class << 8
+    // classes of the next stream position: one shared-memory atomic per point on the team's
+    // (class, parity) counters gives the point its position among the team's points of that class
+    // and parity; info[k] = class | position << 8.  `parity` is the row bit that decides which half
+    // of the bank line a 64-byte piece of the row occupies (row_chunk swizzle): it is a lane
+    // constant for home rows.  Counter sets rotate over 3 buffers (qh = global round counter).
     uint32_t info[PPL];
-    auto count_and_publish = [&](int buf) {
-      int cls[PPL];
-#pragma unroll
-      for (int k = 0; k < PPL; ++k) cls[k] = (int)(cw[k] & MASK);
-      shift_stream();
-      uint32_t bw[NW];
-#pragma unroll
-      for (int w = 0; w < NW; ++w) bw[w] = 0;
+    const int par = (lane >> PAR_BIT) & 1;
+    auto count_round = [&](int hb) {
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {
-        const uint32_t m = __match_any_sync(0xffffffffu, cls[k]);
-        const uint32_t rank = __popc(m & lt);
-        const bool leader = (m & lt) == 0u;
-        const uint32_t contrib = leader ? ((uint32_t)__popc(m) << (8 * (cls[k] & 3))) : 0u;
-        const int cwd = cls[k] >> 2, csh = 8 * (cls[k] & 3);
-        uint32_t before = bw[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) before = (cwd == w) ? bw[w] : before;
-        info[k] = (uint32_t)cls[k] | ((((before >> csh) & 255u) + rank) << 8);
-#pragma unroll
-        for (int w = 0; w < NW; ++w) bw[w] += __reduce_add_sync(0xffffffffu, (cwd == w) ? contrib : 0u);
+        const int cls = (int)(cw[k] & MASK);
+        const uint32_t pos = atomicAdd(hist + hb * 32 + par * NCLS + cls, 1u);
+        info[k] = (uint32_t)cls | (pos << 8);
       }
-      if (lane < NCLS) {
-        uint32_t word = bw[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) word = ((lane >> 2) == w) ? bw[w] : word;
-        reinterpret_cast<uint8_t*>(cnt + buf * 16)[lane * 4 + warp] = (uint8_t)((word >> (8 * (lane & 3))) & 255u);
-      }
+      shift_stream();
     };
-    if (R > 0) count_and_publish(0);
+    if (R > 0) count_round(qh % 3);
     named_bar_sync(bar_id, TW * 32); // leaf rows + counts of round 0
 
-    for (int r = 0; r < R; ++r) {
-      const int buf = r & 1;
+    for (int r = 0; r < R; ++r, ++qh) {
+      const int buf = r & 1, hb = qh % 3;
       uint16_t* list = lists + buf * LIST_CAP;
-      // ---- list of round r: lane c holds class c's total, padded start and this warp's offset
-      const uint32_t packed = (lane < NCLS) ? cnt[buf * 16 + lane] : 0u;
-      const int b0 = packed & 255u, b1 = (packed >> 8) & 255u, b2 = (packed >> 16) & 255u, b3 = packed >> 24;
-      const int total = b0 + b1 + b2 + b3;
-      const int woff = (warp > 0 ? b0 : 0) + (warp > 1 ? b1 : 0) + (warp > 2 ? b2 : 0);
+      // ---- list of round r.  Lane c holds class c's counts.  Inside a class the rows of opposite
+      // parity are zipped into (even, odd) slot pairs — the two rows a quarter-warp gathers at once
+      // then never collide — and the surplus of the larger parity follows.
+      const int n0 = (lane < NCLS) ? (int)hist[hb * 32 + lane] : 0;
+      const int n1 = (lane < NCLS) ? (int)hist[hb * 32 + NCLS + lane] : 0;
+      const int total = n0 + n1, mzip = min(n0, n1);
       const int padded = (total + 7) & ~7;
       int incl = padded;
 #pragma unroll
@@ -1236,19 +1222,20 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         if (lane >= o) incl += nn;
       }
       const int mystart = incl - padded;
-      const int mybase = mystart + woff;
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {
-        const int st = __shfl_sync(0xffffffffu, mybase, (int)(info[k] & 255u));
-        list[st + (int)(info[k] >> 8)] = (uint16_t)(warp * PW + k * 32 + lane);
+        const int c = (int)(info[k] & 255u), pos = (int)(info[k] >> 8);
+        const int st = __shfl_sync(0xffffffffu, mystart, c), mm = __shfl_sync(0xffffffffu, mzip, c);
+        list[st + (pos < mm ? 2 * pos + par : mm + pos)] = (uint16_t)(warp * PW + k * 32 + lane);
       }
       for (int c0 = 4 * warp; c0 < NCLS; c0 += 4 * TW) { // class padding -> zero row
         const int pc = c0 + (lane >> 3), pi = lane & 7;
         const int cn = __shfl_sync(0xffffffffu, total, pc & 15), cs = __shfl_sync(0xffffffffu, mystart, pc & 15);
         if (pc < NCLS && (cn & 7) && pi >= (cn & 7)) list[cs + (cn & ~7) + pi] = (uint16_t)ZROW;
       }
-      if (r + 1 < R) count_and_publish(buf ^ 1);
-      named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 published
+      if (r + 1 < R) count_round((qh + 1) % 3);
+      if (warp == 0) hist[((qh + 2) % 3) * 32 + lane] = 0u; // last read before the previous barrier
+      named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 final
 
       // ---- owned classes: B in registers, rows streamed through gather -> DMMA -> scatter
 #pragma unroll

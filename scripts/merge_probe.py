@@ -8,7 +8,7 @@ import itna_b200 as t
 from itna_b200 import _capi
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 20_000_000
-MERGES = ("1", "2", "3", "4")
+MERGES = tuple(os.environ.get("PROBE_MERGES", "1,2,3,4").split(","))
 
 def run(name, f, ncol, npts=npts):
     res = {}
