@@ -1086,9 +1086,23 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
     s_d2[i] = d2;
   }
+  // leaf / root vectors of the CTA in shared memory (after the team regions), 16-byte chunks
+  // XOR-swizzled by the slice number: lanes reading chunk j of different slices spread over banks
+  double* s_leaf = reinterpret_cast<double*>(smem + (size_t)NTEAM * T6::BYTES);  // [NCLS][CHI]
+  double* s_root = s_leaf + NCLS * CHI;                                           // [nout][NCLS][CHI]
+  for (int i = tid; i < NCLS * CPR; i += NT) {
+    const int sl = i / CPR, j = i % CPR, pj = j ^ (sl & (CPR - 1) & 7);
+    s_leaf[sl * CHI + 2 * pj] = ch.leaf[sl * CHI + 2 * j];
+    s_leaf[sl * CHI + 2 * pj + 1] = ch.leaf[sl * CHI + 2 * j + 1];
+    for (int o = 0; o < ch.nout; ++o) {
+      s_root[(o * NCLS + sl) * CHI + 2 * pj] = ch.root[(o * NCLS + sl) * CHI + 2 * j];
+      s_root[(o * NCLS + sl) * CHI + 2 * pj + 1] = ch.root[(o * NCLS + sl) * CHI + 2 * j + 1];
+    }
+  }
   unsigned char* tbase = smem + (size_t)team * T6::BYTES;
   const uint32_t state_base = smem_u32(tbase);
   uint16_t* lists = reinterpret_cast<uint16_t*>(tbase + T6::STATE_BYTES);     // [2][LIST_CAP]
+  const uint32_t s_leaf_u32 = smem_u32(s_leaf), s_root_u32 = smem_u32(s_root);
   uint32_t* hist = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);          // [3][2][16] (class, parity) counters
   for (int i = tid % (TW * 32); i < 96; i += TW * 32) hist[i] = 0u;
   for (int i = tid % (TW * 32); i < 8 * CHI; i += TW * 32)
@@ -1172,9 +1186,13 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       for (int k = 0; k < PPL; ++k) {
         cw[k] = w0[k];
         const int row = warp * PW + k * 32 + lane;
-        const double* L = ch.leaf + (size_t)(cw[k] & MASK) * CHI;
+        const int sl = (int)(cw[k] & MASK);
+        const uint32_t L = s_leaf_u32 + (uint32_t)sl * (CHI * 8);
 #pragma unroll
-        for (int j = 0; j < CPR; ++j) sts128(row_chunk<CHI>(state_base, row, j), __ldg(L + 2 * j), __ldg(L + 2 * j + 1));
+        for (int j = 0; j < CPR; ++j) {
+          const double2 v = lds128(L + (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4));
+          sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+        }
       }
     }
     auto shift_stream = [&]() {
@@ -1281,17 +1299,20 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     for (int k = 0; k < PPL; ++k) {
       const int row = warp * PW + k * 32 + lane;
       const int64_t p = p0 + k * 32 + lane;
-      const double* R0 = ch.root + (size_t)(cw[k] & MASK) * CHI;
-      const double* R1 = R0 + (size_t)NCLS * CHI;
+      const int sl = (int)(cw[k] & MASK);
+      const uint32_t R0 = s_root_u32 + (uint32_t)sl * (CHI * 8), R1 = R0 + (uint32_t)(NCLS * CHI * 8);
       double o0 = 0.0, o1 = 0.0;
 #pragma unroll
       for (int j = 0; j < CPR; ++j) {
         const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
-        o0 = fma(v.x, __ldg(R0 + 2 * j), o0);
-        o0 = fma(v.y, __ldg(R0 + 2 * j + 1), o0);
+        const uint32_t off = (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4);
+        const double2 q0 = lds128(R0 + off);
+        o0 = fma(v.x, q0.x, o0);
+        o0 = fma(v.y, q0.y, o0);
         if (ch.nout == 2) {
-          o1 = fma(v.x, __ldg(R1 + 2 * j), o1);
-          o1 = fma(v.y, __ldg(R1 + 2 * j + 1), o1);
+          const double2 q1 = lds128(R1 + off);
+          o1 = fma(v.x, q1.x, o1);
+          o1 = fma(v.y, q1.y, o1);
         }
       }
       if (p < src.npts) {
@@ -1789,7 +1810,7 @@ static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
                             cudaStream_t s) {
   using T6 = Team6<CHI, NCLS>;
   const ChainMmaDev& c = p->cmma;
-  const size_t smem = (size_t)NTEAM * T6::BYTES;
+  const size_t smem = (size_t)NTEAM * T6::BYTES + (size_t)3 * NCLS * CHI * 8; // teams + leaf + root (re, im)
   auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (src.npts + T6::TP - 1) / T6::TP;
