@@ -34,9 +34,9 @@ namespace ttn {
 constexpr int kMmaMaxStages = 16;
 constexpr int kMaxClasses = 16;
 
-// stream bits per chain position holding `nsl` slices (<= 16)
+// stream bits per chain position holding `nsl` slices (<= 32)
 __host__ __device__ constexpr int slice_bits(int nsl) {
-  return nsl <= 1 ? 0 : (nsl <= 2 ? 1 : (nsl <= 4 ? 2 : (nsl <= 8 ? 3 : 4)));
+  return nsl <= 1 ? 0 : (nsl <= 2 ? 1 : (nsl <= 4 ? 2 : (nsl <= 8 ? 3 : (nsl <= 16 ? 4 : 5))));
 }
 
 template <int CHI>
@@ -1050,7 +1050,7 @@ struct Team6 {
   static constexpr int TW = 4, PW = 128, TP = TW * PW;
   static constexpr int LIST_CAP = TP + 8 * NCLS;
   static constexpr size_t STATE_BYTES = (size_t)(TP + 8) * CHI * 8;
-  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 3 * 32 * 4 + 127) / 128 * 128;
+  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 3 * 2 * NCLS * 4 + 127) / 128 * 128;
 };
 
 template <int CHI, int NCLS, int NTEAM>
@@ -1067,7 +1067,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   constexpr int ZROW = TP;                 // the team's all-zero row (class padding target)
   constexpr int NT = NTEAM * TW * 32;
   constexpr int PAR_BIT = (CHI >= 16) ? 2 : 0;  // row bit that selects the bank half of a 64-byte piece
-  static_assert(NCLS % TW == 0 && NCLS <= 16 && (NCLS & (NCLS - 1)) == 0, "class count");
+  constexpr int HS = 2 * NCLS;             // counters per set: (parity, class)
+  static_assert(NCLS % TW == 0 && NCLS <= 32 && (NCLS & (NCLS - 1)) == 0, "class count");
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NTEAM * TW];
@@ -1104,7 +1105,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   uint16_t* lists = reinterpret_cast<uint16_t*>(tbase + T6::STATE_BYTES);     // [2][LIST_CAP]
   const uint32_t s_leaf_u32 = smem_u32(s_leaf), s_root_u32 = smem_u32(s_root);
   uint32_t* hist = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);          // [3][2][16] (class, parity) counters
-  for (int i = tid % (TW * 32); i < 96; i += TW * 32) hist[i] = 0u;
+  for (int i = tid % (TW * 32); i < 3 * HS; i += TW * 32) hist[i] = 0u;
   for (int i = tid % (TW * 32); i < 8 * CHI; i += TW * 32)
     reinterpret_cast<double*>(tbase + (size_t)TP * CHI * 8)[i] = 0.0;
   __syncthreads();
@@ -1215,7 +1216,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {
         const int cls = (int)(cw[k] & MASK);
-        const uint32_t pos = atomicAdd(hist + hb * 32 + par * NCLS + cls, 1u);
+        const uint32_t pos = atomicAdd(hist + hb * HS + par * NCLS + cls, 1u);
         info[k] = (uint32_t)cls | (pos << 8);
       }
       shift_stream();
@@ -1229,8 +1230,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       // ---- list of round r.  Lane c holds class c's counts.  Inside a class the rows of opposite
       // parity are zipped into (even, odd) slot pairs — the two rows a quarter-warp gathers at once
       // then never collide — and the surplus of the larger parity follows.
-      const int n0 = (lane < NCLS) ? (int)hist[hb * 32 + lane] : 0;
-      const int n1 = (lane < NCLS) ? (int)hist[hb * 32 + NCLS + lane] : 0;
+      const int n0 = (lane < NCLS) ? (int)hist[hb * HS + lane] : 0;
+      const int n1 = (lane < NCLS) ? (int)hist[hb * HS + NCLS + lane] : 0;
       const int total = n0 + n1, mzip = min(n0, n1);
       const int padded = (total + 7) & ~7;
       int incl = padded;
@@ -1248,11 +1249,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       }
       for (int c0 = 4 * warp; c0 < NCLS; c0 += 4 * TW) { // class padding -> zero row
         const int pc = c0 + (lane >> 3), pi = lane & 7;
-        const int cn = __shfl_sync(0xffffffffu, total, pc & 15), cs = __shfl_sync(0xffffffffu, mystart, pc & 15);
+        const int cn = __shfl_sync(0xffffffffu, total, pc & 31), cs = __shfl_sync(0xffffffffu, mystart, pc & 31);
         if (pc < NCLS && (cn & 7) && pi >= (cn & 7)) list[cs + (cn & ~7) + pi] = (uint16_t)ZROW;
       }
       if (r + 1 < R) count_round((qh + 1) % 3);
-      if (warp == 0) hist[((qh + 2) % 3) * 32 + lane] = 0u; // last read before the previous barrier
+      if (warp == 0)
+        for (int i = lane; i < HS; i += 32) hist[((qh + 2) % 3) * HS + i] = 0u; // last read before the previous barrier
       named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 final
 
       // ---- owned classes: B in registers, rows streamed through gather -> DMMA -> scatter
@@ -1510,15 +1512,20 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     std::vector<int> cand = {4, 3, 2};
     if (const char* e = getenv("TTN_MMA_MERGE")) {
       cand.clear();
-      for (int kk = std::min(atoi(e), 4); kk >= 2; --kk) cand.push_back(kk);
+      for (int kk = std::min(atoi(e), 5); kk >= 2; --kk) cand.push_back(kk);
     }
+    // the team-sorted kernel (v6) reads site matrices straight from L2 into registers: no ring-stage
+    // limit and up to 32 slices per position; the ring kernels take <= 16 slices and <= 32 KB per position
+    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && CHI <= 16 && p->all_base2;
     if (NSL0 == 2 || NSL0 == 4)
-      for (int kk : cand)
-        if (bits0 * kk <= 4 && ((size_t)1 << (bits0 * kk)) * CHI * CHI * 8 <= 32 * 1024 && n >= 2 * kk &&
-            (kk != 3 || CHI <= 16)) { // 3-bit fields straddle words: only the warp-autonomous kernel reads those
-          kmerge = kk;
+      for (int kk : cand) {
+        const int sb = bits0 * kk;
+        const bool fits = v6_on ? sb <= 5 : (sb <= 4 && ((size_t)1 << sb) * CHI * CHI * 8 <= 32 * 1024);
+        if (fits && n >= 2 * kk && (kk != 3 || CHI <= 16) && (sb != 5 || v6_on)) {
+          kmerge = kk; // 3- and 5-bit fields straddle words: only the kernels with the 128-bit stream read those
           break;
         }
+      }
   }
   const bool merge = kmerge > 1;
 
@@ -1849,7 +1856,7 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   // (TTN_MMA_V6=0 falls back to the warp-autonomous kernel, =2 runs two teams: experiments)
   static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
   if (v6 && c.merged && p->all_base2 && c.spr == 1 && (c.chi == 16 || c.chi == 8) &&
-      (c.nsl == 4 || c.nsl == 8 || c.nsl == 16)) {
+      (c.nsl == 4 || c.nsl == 8 || c.nsl == 16 || c.nsl == 32)) {
 #define TTN_V6_CASE(W, N)                                                                                   \
   if (c.chi == W && c.nsl == N)                                                                             \
     return v6 == 2 ? launch_mma6_inst<W, N, 2>(p, src, d_out, d_partial, n_partial, s)                      \
@@ -1857,9 +1864,11 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     TTN_V6_CASE(16, 4)
     TTN_V6_CASE(16, 8)
     TTN_V6_CASE(16, 16)
+    TTN_V6_CASE(16, 32)
     TTN_V6_CASE(8, 4)
     TTN_V6_CASE(8, 8)
     TTN_V6_CASE(8, 16)
+    TTN_V6_CASE(8, 32)
 #undef TTN_V6_CASE
   }
   switch (c.chi) {

@@ -376,7 +376,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   int64_t chunk = npts;
   int n_chunks = 1;
   if (coords_host || out_host || weights_host) {
-    chunk = opts->chunk_points > 0 ? opts->chunk_points : (int64_t)1 << 22;
+    chunk = opts->chunk_points > 0 ? opts->chunk_points : (int64_t)1 << 21; // measured best on PCIe 5 x16 (scripts/e2e_probe.py)
     chunk = std::min(chunk, npts);
     n_chunks = (int)((npts + chunk - 1) / chunk);
     if (n_chunks > kMaxChunks) {

@@ -397,7 +397,7 @@ def test_evaluate_at_index_settings(which):
     assert e.value.code == _capi.TTN_ERR_INVALID
 
 
-@pytest.mark.parametrize("kmax", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("kmax", ["1", "2", "3", "4", "5"])
 def test_merged_chain_images(kmax, monkeypatch):
     """Plan-time group merging of the DMMA chain kernel (k vertices pre-contracted per stream
     position, k <= TTN_MMA_MERGE): every chain length 2..14 (identity padding, leaf/root groups of
