@@ -1045,20 +1045,21 @@ __device__ __forceinline__ void batch6(uint32_t state_base, const int (&rows)[4]
     }
 }
 
-template <int CHI, int NCLS>
+template <int CHI, int NCLS, int PW_>
 struct Team6 {
-  static constexpr int TW = 4, PW = 128, TP = TW * PW;
+  static constexpr int TW = 4, PW = PW_, TP = TW * PW;
   static constexpr int LIST_CAP = TP + 8 * NCLS;
   static constexpr size_t STATE_BYTES = (size_t)(TP + 8) * CHI * 8;
   static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 3 * 2 * NCLS * 4 + 127) / 128 * 128;
 };
 
-template <int CHI, int NCLS, int NTEAM>
+template <int CHI, int NCLS, int NTEAM, int PW_>
 __global__ void __launch_bounds__(NTEAM * 128, 1)
     chain_mma6_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                       double* __restrict__ partial, int do_sum) {
-  using T6 = Team6<CHI, NCLS>;
+  using T6 = Team6<CHI, NCLS, PW_>;
   constexpr int TW = T6::TW, PW = T6::PW, PPL = PW / 32, TP = T6::TP;
+  constexpr int GB = (CHI >= 32) ? 2 : 4;   // 8-row groups per batch (register budget)
   constexpr int CPW = NCLS / TW;           // classes owned by a warp
   constexpr int BITS = slice_bits(NCLS);
   constexpr int NB = CHI / 8, KB = CHI / 4, CPR = CHI / 2;
@@ -1271,22 +1272,22 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
         const int ng = (n_c + 7) >> 3;
         const uint16_t* Lc = list + st;
-        int rows_nx[4];
+        int rows_nx[4] = {0, 0, 0, 0};
         if (ng > 0) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) rows_nx[b] = (int)Lc[(min(b, ng - 1) << 3) + g];
+          for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(b, ng - 1) << 3) + g];
         }
-        for (int gi = 0; gi < ng; gi += 4) {
-          const int nbat = min(4, ng - gi);
-          int rows[4];
+        for (int gi = 0; gi < ng; gi += GB) {
+          const int nbat = min(GB, ng - gi);
+          int rows[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int b = 0; b < 4; ++b) rows[b] = rows_nx[b];
-          if (gi + 4 < ng) {
+          for (int b = 0; b < GB; ++b) rows[b] = rows_nx[b];
+          if (gi + GB < ng) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) rows_nx[b] = (int)Lc[(min(gi + 4 + b, ng - 1) << 3) + g];
+            for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(gi + GB + b, ng - 1) << 3) + g];
           }
-          if (nbat == 4) batch6<CHI, 4>(state_base, rows, tq, ZROW, bcur);
-          else if (nbat == 3) batch6<CHI, 3>(state_base, rows, tq, ZROW, bcur);
+          if (GB >= 4 && nbat == 4) batch6<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, ZROW, bcur);
+          else if (GB >= 4 && nbat == 3) batch6<CHI, (GB >= 4 ? 3 : 1)>(state_base, rows, tq, ZROW, bcur);
           else if (nbat == 2) batch6<CHI, 2>(state_base, rows, tq, ZROW, bcur);
           else batch6<CHI, 1>(state_base, rows, tq, ZROW, bcur);
         }
@@ -1516,12 +1517,12 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     }
     // the team-sorted kernel (v6) reads site matrices straight from L2 into registers: no ring-stage
     // limit and up to 32 slices per position; the ring kernels take <= 16 slices and <= 32 KB per position
-    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && CHI <= 16 && p->all_base2;
+    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && p->all_base2;
     if (NSL0 == 2 || NSL0 == 4)
       for (int kk : cand) {
         const int sb = bits0 * kk;
-        const bool fits = v6_on ? sb <= 5 : (sb <= 4 && ((size_t)1 << sb) * CHI * CHI * 8 <= 32 * 1024);
-        if (fits && n >= 2 * kk && (kk != 3 || CHI <= 16) && (sb != 5 || v6_on)) {
+        const bool fits = v6_on ? sb <= (CHI <= 16 ? 5 : 4) : (sb <= 4 && ((size_t)1 << sb) * CHI * CHI * 8 <= 32 * 1024);
+        if (fits && n >= 2 * kk && (kk != 3 || CHI <= 16 || v6_on)) {
           kmerge = kk; // 3- and 5-bit fields straddle words: only the kernels with the 128-bit stream read those
           break;
         }
@@ -1812,13 +1813,13 @@ static int launch_mma5_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
   return TTN_OK;
 }
 
-template <int CHI, int NCLS, int NTEAM>
+template <int CHI, int NCLS, int NTEAM, int PW_>
 static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                             cudaStream_t s) {
-  using T6 = Team6<CHI, NCLS>;
+  using T6 = Team6<CHI, NCLS, PW_>;
   const ChainMmaDev& c = p->cmma;
   const size_t smem = (size_t)NTEAM * T6::BYTES + (size_t)3 * NCLS * CHI * 8; // teams + leaf + root (re, im)
-  auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM>;
+  auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM, PW_>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (src.npts + T6::TP - 1) / T6::TP;
   const int grid = (int)std::min<int64_t>((n_tiles + NTEAM - 1) / NTEAM, p->sm_count);
@@ -1855,12 +1856,11 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   // merged binary chains of width <= 16: team-sorted, B-stationary kernel (v6), 3 teams per CTA
   // (TTN_MMA_V6=0 falls back to the warp-autonomous kernel, =2 runs two teams: experiments)
   static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
-  if (v6 && c.merged && p->all_base2 && c.spr == 1 && (c.chi == 16 || c.chi == 8) &&
-      (c.nsl == 4 || c.nsl == 8 || c.nsl == 16 || c.nsl == 32)) {
+  if (v6 && c.merged && p->all_base2 && c.spr == 1) {
 #define TTN_V6_CASE(W, N)                                                                                   \
   if (c.chi == W && c.nsl == N)                                                                             \
-    return v6 == 2 ? launch_mma6_inst<W, N, 2>(p, src, d_out, d_partial, n_partial, s)                      \
-                   : launch_mma6_inst<W, N, 3>(p, src, d_out, d_partial, n_partial, s);
+    return v6 == 2 ? launch_mma6_inst<W, N, 2, 128>(p, src, d_out, d_partial, n_partial, s)                 \
+                   : launch_mma6_inst<W, N, 3, 128>(p, src, d_out, d_partial, n_partial, s);
     TTN_V6_CASE(16, 4)
     TTN_V6_CASE(16, 8)
     TTN_V6_CASE(16, 16)
@@ -1870,6 +1870,10 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     TTN_V6_CASE(8, 16)
     TTN_V6_CASE(8, 32)
 #undef TTN_V6_CASE
+    // width 32: rows are 256 bytes and a class's B fragments take 64 registers -> 2 teams of 384 points
+    if (c.chi == 32 && c.nsl == 4) return launch_mma6_inst<32, 4, 2, 96>(p, src, d_out, d_partial, n_partial, s);
+    if (c.chi == 32 && c.nsl == 8) return launch_mma6_inst<32, 8, 2, 96>(p, src, d_out, d_partial, n_partial, s);
+    if (c.chi == 32 && c.nsl == 16) return launch_mma6_inst<32, 16, 2, 96>(p, src, d_out, d_partial, n_partial, s);
   }
   switch (c.chi) {
     case 8: // warp-autonomous kernel (v5)

@@ -43,3 +43,5 @@ s = t.continuous_siteinds(t.named_grid((41, 1)), map_dimension=1)
 run("mps41 chi32 (v3 kernel)", t.rand_itn(s, link_space=32, rng=0, normalise=True), 1, npts // 2)
 s = t.continuous_siteinds(t.named_grid((30, 1)), map_dimension=1)
 run("mps30 chi16 complex", t.rand_itn(s, link_space=16, rng=0, eltype=complex, normalise=True), 1, npts // 2)
+s = t.continuous_siteinds(t.named_grid((28, 1)), map_dimension=2)
+run("cfg4 mps28 chi32 2-D", t.rand_itn(s, link_space=32, rng=0, normalise=True), 2, npts // 2)
