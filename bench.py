@@ -159,6 +159,29 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank, torch):
+    """Multi-rank runs: pin this process to the CPUs of the NUMA node its GPU hangs off, so that the
+    pinned staging buffers (first touch) and the copy-engine traffic stay on the local socket.
+    Best effort: returns the node number, or None when sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def bench_grid(args, plan, rank, world, local_rank, torch):
     """BASELINE config 4 as literally stated: the 2-D chi=32 MPS on the full 16384^2 grid with the summed-grid
     quadrature.  No coordinate bytes exist (the grid is generated on the device); a step = the whole grid + sum."""
@@ -229,6 +252,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    numa = bind_to_gpu_numa_node(local_rank, torch) if world > 1 else None
     f, ncol, npts, desc = build_workload(args.config)
     if args.points:
         npts = int(args.points)
@@ -320,7 +344,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": desc, "points_per_gpu": npts, "kernel": _capi.KERNEL_NAMES[o_dev.kernel_used],
                        "flops_per_point": flops_pp, "l2": "inputs_larger_than_l2 (1.6 GB coords + 0.8 GB values per step)",
-                       "device_eq_host_bitwise": same},
+                       "device_eq_host_bitwise": same, "rank0_numa_node": numa},
             "kernel_ms_events": kernel_ms,
             "e2e": {"value": e2e, "unit": "points/s", "h2d_bytes_per_step": int(npts * ncol * 8) * world,
                     "d2h_bytes_per_step": int(npts * nc_out * 8) * world, "ms_per_step": dt_e2e / args.steps * 1e3,

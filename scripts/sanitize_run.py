@@ -8,8 +8,8 @@ from itna_b200 import _capi
 rng = np.random.default_rng(0)
 nets = []
 s = t.continuous_siteinds(t.named_grid((12, 1)), map_dimension=2)
-nets.append(("mps chi16 (v5)", t.rand_itn(s, link_space=16, rng=1, normalise=True), 2, 3000))
-nets.append(("mps chi32 (v3)", t.rand_itn(s, link_space=32, rng=2, normalise=True), 2, 1500))
+nets.append(("mps chi16 (v6 / v5)", t.rand_itn(s, link_space=16, rng=1, normalise=True), 2, 3000))
+nets.append(("mps chi32 (v6 / v3)", t.rand_itn(s, link_space=32, rng=2, normalise=True), 2, 1500))
 nets.append(("mps chi48 (gemm)", t.rand_itn(s, link_space=48, rng=3, normalise=True), 2, 700))
 s3 = t.continuous_siteinds(t.named_grid((9, 1)), base=3)
 nets.append(("mps base3 chi8 (generic digits)", t.rand_itn(s3, link_space=8, rng=4, normalise=True), 1, 2000))
@@ -18,18 +18,25 @@ ws = g.vertices()[1:]
 sb = t.continuous_siteinds(g, [ws[i::3] for i in range(3)])
 nets.append(("bintree chi20 (tree)", t.rand_itn(sb, link_space=20, rng=5, normalise=True), 3, 700))
 skip = os.environ.get('SAN_SKIP', '')
-for name, f, ncol, n in nets:
-    if skip and skip in name:
-        continue
-    only = os.environ.get('SAN_ONLY', '')
-    if only and only not in name:
-        continue
-    plan = f.plan()
-    pts = rng.random((n, ncol))
-    avail = plan.info()["kernels_available"]
-    for kname, kid in _capi.KERNEL_IDS.items():
-        if kid and avail & (1 << kid):
-            out, o = plan.evaluate_host(pts, kernel=kname, reduce_sum=True)
-            print(name, kname, "ok", float(np.abs(out).max()))
-    plan.digits_host(pts)
+only = os.environ.get('SAN_ONLY', '')
+# default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
+# per position and exercises the warp-autonomous (v5) and warp-specialised (v3) kernels
+for merge in (os.environ.get('SAN_MERGES', 'default,1').split(',')):
+    if merge == 'default':
+        os.environ.pop('TTN_MMA_MERGE', None)
+    else:
+        os.environ['TTN_MMA_MERGE'] = merge
+    for name, f, ncol, n in nets:
+        if (skip and skip in name) or (only and only not in name):
+            continue
+        f._plans.clear()
+        plan = f.plan()
+        pts = rng.random((n, ncol))
+        avail = plan.info()["kernels_available"]
+        for kname, kid in _capi.KERNEL_IDS.items():
+            if kid and kname != 'grid' and avail & (1 << kid) and (merge == 'default' or kname == 'dmma'):
+                out, o = plan.evaluate_host(pts, kernel=kname, reduce_sum=True)
+                print(f"merge={merge}", name, kname, "ok", float(np.abs(out).max()))
+        plan.digits_host(pts)
+        f._plans.clear()
 print("done")
