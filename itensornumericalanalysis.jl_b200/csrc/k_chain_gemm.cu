@@ -25,6 +25,8 @@ namespace ttn {
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3;
 constexpr int GA_STRIDE = GBK + 4; // doubles per A row in shared memory (160 B: conflict-free fragment loads)
+constexpr int kGemmMaxCls = 16;     // slices per stream position (pair-merged vertices: 4 x 4)
+constexpr int kGemmOff = kGemmMaxCls + 1; // per-site stride of the class / tile offset arrays
 
 __global__ void gemm_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, int pc, const int32_t* __restrict__ pos_of_vertex,
                                    int n_pos, uint8_t* __restrict__ slices, int* err) {
@@ -43,7 +45,8 @@ __global__ void gemm_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, i
     for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
       const DigitEntry e = dg.entries[k];
       const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
-      slices[(size_t)pos_of_vertex[e.vertex] * pc + i] += (uint8_t)(v * e.stride);
+      const int pv = pos_of_vertex[e.vertex]; // stream position | (bit shift inside the position) << 16
+      slices[(size_t)(pv & 0xffff) * pc + i] += (uint8_t)((v * e.stride) << (pv >> 16));
     }
   }
 }
@@ -55,8 +58,8 @@ __global__ void __launch_bounds__(1024)
   const int site = blockIdx.x; // middle site index t (position t + 1)
   const uint8_t* sl = slices + (size_t)(site + 1) * pc;
   uint32_t* list = lists + (size_t)site * pc;
-  __shared__ int cnt[8], cursor[8];
-  if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+  __shared__ int cnt[kGemmMaxCls], cursor[kGemmMaxCls];
+  if (threadIdx.x < kGemmMaxCls) cnt[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < pc; i += blockDim.x) atomicAdd(&cnt[sl[i]], 1);
   __syncthreads();
@@ -64,13 +67,13 @@ __global__ void __launch_bounds__(1024)
     int run = 0, trun = 0;
     for (int c = 0; c < nsl; ++c) {
       cursor[c] = run;
-      cls_off[site * 8 + c] = run;
-      tile_off[site * 8 + c] = trun;
+      cls_off[site * kGemmOff + c] = run;
+      tile_off[site * kGemmOff + c] = trun;
       run += cnt[c];
       trun += (cnt[c] + GBM - 1) / GBM * n_nblk;
     }
-    cls_off[site * 8 + nsl] = run;
-    tile_off[site * 8 + nsl] = trun;
+    cls_off[site * kGemmOff + nsl] = run;
+    tile_off[site * kGemmOff + nsl] = trun;
   }
   __syncthreads();
   // order inside a class is irrelevant for the result of a row (each row is an independent product)
@@ -291,7 +294,18 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
     *re = T[(d->tensor_ptr[v] + idx) * NC];
     *im = cplx ? T[(d->tensor_ptr[v] + idx) * NC + 1] : 0.0;
   };
-  const int n_steps = n - 2, nout = cplx ? 2 : 1;
+  const int nout = cplx ? 2 : 1;
+  const size_t M = (size_t)W * W;
+  // Pair merging (same idea as build_chain_mma's group merging): when the slice indices are bit
+  // fields and two vertices together have <= 16 slices, chain positions (2m, 2m+1) are contracted
+  // into one stream position at plan time, M[s_0 + NSL0 s_1] = E_0[s_0] E_1[s_1]: half as many
+  // GEMMs per point.  An odd chain gets an identity vertex in front of the root.
+  const int bits0 = NSL == 2 ? 1 : (NSL == 4 ? 2 : -1);
+  bool merge = bits0 > 0 && n >= 4;
+  if (const char* e = getenv("TTN_MMA_MERGE")) merge = merge && atoi(e) >= 2;
+  const int n_pad = merge ? (n + 1) / 2 * 2 : n;             // chain positions incl. identity padding
+  const int n_steps0 = n_pad - 2;                            // unmerged middle positions
+  if (n >= 2) pos_of[order[n - 1]] = n_pad - 1;
   std::vector<double> leaf((size_t)NSL * W, 0.0), root((size_t)nout * NSL * W, 0.0);
   {
     const int v = order[0], b = d->link_dim[v];
@@ -317,37 +331,112 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
         }
       }
   }
-  const size_t per_site = (size_t)NSL * W * W;
-  double* d_frags;
-  TTN_CUDA(cudaMalloc(&d_frags, per_site * n_steps * 8));
-  p->allocs.push_back(d_frags);
-  {
-    std::vector<double> E((size_t)W * W), F(per_site);
-    const int NBW = W / 8;
-    for (int tI = 0; tI < n_steps; ++tI) {
-      const int v = order[tI + 1], a = d->link_dim[order[tI]], b = d->link_dim[v];
-      std::fill(F.begin(), F.end(), 0.0);
-      for (int s = 0; s < p->nslices[v]; ++s) {
-        std::fill(E.begin(), E.end(), 0.0);
-        for (int i = 0; i < a; ++i)
-          for (int j = 0; j < b; ++j) {
-            double re, im;
-            elem(v, ((int64_t)s * a + i) * b + j, &re, &im);
-            E[(size_t)i * W + j] = re;
-            if (cplx) {
-              E[(size_t)i * W + H + j] = im;
-              E[(size_t)(H + i) * W + j] = -im;
-              E[(size_t)(H + i) * W + H + j] = re;
-            }
-          }
-        double* Fs = F.data() + (size_t)s * W * W;
-        for (int kb = 0; kb < W / 4; ++kb)
-          for (int nb = 0; nb < NBW; ++nb)
-            for (int ln = 0; ln < 32; ++ln)
-              Fs[((size_t)kb * NBW + nb) * 32 + ln] = E[(size_t)(4 * kb + (ln & 3)) * W + 8 * nb + (ln >> 2)];
-      }
-      TTN_CUDA(cudaMemcpy(d_frags + per_site * tI, F.data(), per_site * 8, cudaMemcpyHostToDevice));
+  // row-major site matrices of middle position t (slice s): W x W, zero padded
+  auto site_matrix = [&](int tI, int s, double* E) {
+    std::fill(E, E + M, 0.0);
+    if (tI >= n - 2) { // identity padding
+      if (s == 0)
+        for (int i = 0; i < W; ++i) E[(size_t)i * W + i] = 1.0;
+      return;
     }
+    const int v = order[tI + 1], a = d->link_dim[order[tI]], b = d->link_dim[v];
+    if (s >= p->nslices[v]) return;
+    for (int i = 0; i < a; ++i)
+      for (int j = 0; j < b; ++j) {
+        double re, im;
+        elem(v, ((int64_t)s * a + i) * b + j, &re, &im);
+        E[(size_t)i * W + j] = re;
+        if (cplx) {
+          E[(size_t)i * W + H + j] = im;
+          E[(size_t)(H + i) * W + j] = -im;
+          E[(size_t)(H + i) * W + H + j] = re;
+        }
+      }
+  };
+  auto to_frags = [&](const double* E, double* Fs) {
+    const int NBW = W / 8;
+    for (int kb = 0; kb < W / 4; ++kb)
+      for (int nb = 0; nb < NBW; ++nb)
+        for (int ln = 0; ln < 32; ++ln)
+          Fs[((size_t)kb * NBW + nb) * 32 + ln] = E[(size_t)(4 * kb + (ln & 3)) * W + 8 * nb + (ln >> 2)];
+  };
+  auto matmul = [&](const double* A, const double* B, double* C) { // C = A B, rows of A that are zero are skipped
+    std::fill(C, C + M, 0.0);
+    for (int i = 0; i < W; ++i)
+      for (int k = 0; k < W; ++k) {
+        const double a = A[(size_t)i * W + k];
+        if (a == 0.0) continue;
+        const double* Bk = B + (size_t)k * W;
+        double* Ci = C + (size_t)i * W;
+        for (int j = 0; j < W; ++j) Ci[j] += a * Bk[j];
+      }
+  };
+  const int NSLm = merge ? NSL * NSL : NSL;
+  const int n_steps = merge ? (n_pad - 4) / 2 : n_steps0;
+  const size_t per_site = (size_t)NSLm * M;
+  double* d_frags;
+  TTN_CUDA(cudaMalloc(&d_frags, std::max<size_t>(per_site * n_steps, 1) * 8));
+  p->allocs.push_back(d_frags);
+  double flops_exec = 0.0;
+  const double fmul = cplx ? 8.0 : 2.0;
+  auto dim_in = [&](int tI) { return tI < n - 2 ? d->link_dim[order[tI]] : d->link_dim[order[n - 2]]; };
+  auto dim_out = [&](int tI) { return tI < n - 2 ? d->link_dim[order[tI + 1]] : d->link_dim[order[n - 2]]; };
+  {
+    std::vector<double> F(per_site), Ea(M), Eb(M), Ec(M);
+    if (!merge) {
+      for (int tI = 0; tI < n_steps; ++tI) {
+        std::fill(F.begin(), F.end(), 0.0);
+        for (int s = 0; s < NSL; ++s) {
+          site_matrix(tI, s, Ea.data());
+          to_frags(Ea.data(), F.data() + (size_t)s * M);
+        }
+        flops_exec += fmul * dim_in(tI) * dim_out(tI);
+        TTN_CUDA(cudaMemcpy(d_frags + per_site * tI, F.data(), per_site * 8, cudaMemcpyHostToDevice));
+      }
+    } else {
+      // leaf' [s0 + NSL s1] = leaf[s0] E_0[s1];  root' [s0 + NSL s1] = E_last[s0] root[s1]
+      std::vector<double> leaf2((size_t)NSLm * W, 0.0), root2((size_t)nout * NSLm * W, 0.0);
+      for (int s1 = 0; s1 < NSL; ++s1) {
+        site_matrix(0, s1, Ea.data());
+        for (int s0 = 0; s0 < NSL; ++s0)
+          for (int i = 0; i < W; ++i) {
+            const double a = leaf[(size_t)s0 * W + i];
+            if (a == 0.0) continue;
+            for (int j = 0; j < W; ++j) leaf2[(size_t)(s0 + NSL * s1) * W + j] += a * Ea[(size_t)i * W + j];
+          }
+      }
+      for (int s0 = 0; s0 < NSL; ++s0) {
+        site_matrix(n_steps0 - 1, s0, Ea.data());
+        for (int o = 0; o < nout; ++o)
+          for (int s1 = 0; s1 < NSL; ++s1)
+            for (int i = 0; i < W; ++i) {
+              double acc = 0.0;
+              for (int j = 0; j < W; ++j) acc += Ea[(size_t)i * W + j] * root[((size_t)o * NSL + s1) * W + j];
+              root2[((size_t)o * NSLm + (s0 + NSL * s1)) * W + i] = acc;
+            }
+      }
+      leaf.swap(leaf2);
+      root.swap(root2);
+      for (int m = 0; m < n_steps; ++m) { // middle positions (2m+1, 2m+2) of the unmerged chain
+        const int ta = 2 * m + 1, tb = 2 * m + 2;
+        for (int s1 = 0; s1 < NSL; ++s1) {
+          site_matrix(tb, s1, Eb.data());
+          for (int s0 = 0; s0 < NSL; ++s0) {
+            site_matrix(ta, s0, Ea.data());
+            matmul(Ea.data(), Eb.data(), Ec.data());
+            to_frags(Ec.data(), F.data() + (size_t)(s0 + NSL * s1) * M);
+          }
+        }
+        flops_exec += fmul * dim_in(ta) * dim_out(tb);
+        TTN_CUDA(cudaMemcpy(d_frags + per_site * m, F.data(), per_site * 8, cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  p->cgemm_flops_exec = flops_exec + fmul * (merge ? dim_in(n_steps0 - 1) : d->link_dim[order[n - 2]]);
+  // stream position and bit shift of every vertex
+  for (int v = 0; v < n; ++v) {
+    const int pos = pos_of[v];
+    pos_of[v] = merge ? ((pos / 2) | ((bits0 * (pos & 1)) << 16)) : pos;
   }
   double *d_leaf, *d_root;
   int32_t* d_pos;
@@ -363,7 +452,9 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
   ChainGemmDev& c = p->cgemm;
   c.n_vertices = n;
   c.n_steps = n_steps;
-  c.nsl = NSL;
+  c.n_pos = merge ? n_pad / 2 : n;
+  c.merged = merge ? 2 : 0;
+  c.nsl = NSLm;
   c.W = W;
   c.nout = nout;
   c.leaf = d_leaf;
@@ -395,16 +486,16 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
     return TTN_ERR_UNSUPPORTED;
   }
   const ChainGemmDev& c = p->cgemm;
-  const int W = c.W, n_pos = c.n_vertices;
+  const int W = c.W, n_pos = c.n_pos;
   // points per chunk: (PC/128 + nsl) * (W/128) tiles per site should fill a whole number of waves
   const int nnb = W / GBN;
   const int waves = nnb == 2 ? 7 : 4;
-  const int PC = (waves * p->sm_count / nnb - 8) * GBM;
+  const int PC = (waves * p->sm_count / nnb - std::max(c.nsl, 8)) * GBM; // every class may end in a partial tile
   // workspace: two state buffers, slices, lists, offsets
   const size_t state_b = (size_t)PC * W * 8;
   const size_t slices_b = ((size_t)n_pos * PC + 255) / 256 * 256;
   const size_t lists_b = (size_t)std::max(c.n_steps, 1) * PC * 4;
-  const size_t offs_b = (size_t)std::max(c.n_steps, 1) * 8 * 4 * 2 + 256;
+  const size_t offs_b = (size_t)std::max(c.n_steps, 1) * kGemmOff * 4 * 2 + 256;
   const size_t need = 2 * state_b + slices_b + lists_b + offs_b;
   if (st.gemm_bytes < need) {
     if (st.d_gemm) cudaFree(st.d_gemm);
@@ -419,7 +510,7 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
   uint8_t* slices = base + 2 * state_b;
   uint32_t* lists = reinterpret_cast<uint32_t*>(base + 2 * state_b + slices_b);
   int* cls_off = reinterpret_cast<int*>(base + 2 * state_b + slices_b + lists_b);
-  int* tile_off = cls_off + (size_t)std::max(c.n_steps, 1) * 8 + 8;
+  int* tile_off = cls_off + (size_t)std::max(c.n_steps, 1) * kGemmOff + 8;
   const int do_sum = d_partial != nullptr;
   const int64_t n_chunks = (src.npts + PC - 1) / PC;
   const int root_blocks = PC * 32 / 256;
@@ -447,8 +538,8 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
     for (int t = 0; t < c.n_steps; ++t) {
       const double* fr = c.frags + (size_t)t * c.nsl * W * W;
       int rc;
-      if (W == 128) rc = launch_site<128>(Sin, Sout, lists + (size_t)t * pc, cls_off + t * 8, tile_off + t * 8, fr, c.nsl, pc, s);
-      else rc = launch_site<256>(Sin, Sout, lists + (size_t)t * pc, cls_off + t * 8, tile_off + t * 8, fr, c.nsl, pc, s);
+      if (W == 128) rc = launch_site<128>(Sin, Sout, lists + (size_t)t * pc, cls_off + t * kGemmOff, tile_off + t * kGemmOff, fr, c.nsl, pc, s);
+      else rc = launch_site<256>(Sin, Sout, lists + (size_t)t * pc, cls_off + t * kGemmOff, tile_off + t * kGemmOff, fr, c.nsl, pc, s);
       if (rc) return rc;
       std::swap(Sin, Sout);
       *n_launches += 1;

@@ -478,7 +478,10 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       if (ev[2 * ci] && ev[2 * ci + 1] && cudaEventElapsedTime(&ms, ev[2 * ci], ev[2 * ci + 1]) == cudaSuccess) total += ms;
     }
     opts->kernel_ms = total;
-    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged) ? p->cmma_flops_exec : p->info.flops_per_point) * (double)npts;
+    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? p->cmma_flops_exec
+                            : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
+                                                                             : p->info.flops_per_point) *
+                           (double)npts;
     int herr = 0;
     cudaMemcpy(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost);
     if (herr & 2)

@@ -113,10 +113,12 @@ struct ChainMmaDev {
 // wide chains as per-site grouped GEMMs (k_chain_gemm.cu)
 struct ChainGemmDev {
   int32_t n_vertices, n_steps, nsl, W, nout;
+  int32_t n_pos;                 // stream positions (= vertices, or vertex pairs when merged)
+  int32_t merged;                // 2: vertex pairs pre-contracted at plan time (build_chain_gemm)
   const double* leaf;            // [nsl][W]
   const double* root;            // [nout][nsl][W]
   const double* frags;           // [n_steps][nsl][W*W], B-fragment order
-  const int32_t* pos_of_vertex;  // chain position of every vertex
+  const int32_t* pos_of_vertex;  // stream position of every vertex | (bit shift inside the position) << 16
 };
 
 // trees with <= 2 children per vertex as per-vertex (Khatri-Rao) GEMMs (k_tree_gemm.cu)
@@ -166,6 +168,7 @@ struct ttn_plan {
   ttn::ChainMmaDev cmma{};
   ttn::ChainMmaDev cmma_plain{}; // one vertex per position (leaf/root/frags only): grid-share kernel
   bool cmma_plain_ok = false;
+  double cgemm_flops_exec = 0.0; // flops per point the GEMM chain kernel executes
   double cmma_flops_exec = 0.0;  // flops per point the DMMA chain kernel executes (merged: about half the rule)
   bool cmma_ok = false;
   ttn::ChainGemmDev cgemm{};

@@ -420,10 +420,17 @@ def test_merged_chain_images(kmax, monkeypatch):
     nets.append(("cplx_map7", t.rand_itn(sc, link_space=6, rng=5, eltype=complex, normalise=True)))
     sc = t.complex_continuous_siteinds(t.named_grid((8, 1)), map_dimension=2)
     nets.append(("cplx_map8_2d", t.rand_itn(sc, link_space=4, rng=6, eltype=complex, normalise=True)))
+    # GEMM-regime chains (width > 32): pair merging in build_chain_gemm, odd lengths get an identity vertex
+    for L in (4, 5, 7):
+        s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=1)
+        nets.append((f"gemm_mps{L}_chi40", t.rand_itn(s, link_space=40, rng=10 + L, normalise=True)))
+    sc = t.complex_continuous_siteinds(t.named_grid((5, 1)))
+    nets.append(("gemm_cplx_map5_chi20", t.rand_itn(sc, link_space=20, rng=16, eltype=complex, normalise=True)))
     for name, f in nets:
         f._plans.clear()
         dims = f.indexmap.dimensions()
         plan = f.plan(dims)
+        kern = "gemm" if name.startswith("gemm") else "dmma"
         if isinstance(f.indexmap, t.ComplexIndexMap):
             pts = cases.complex_points(8, len(dims), rng, 300)
         else:
@@ -431,11 +438,11 @@ def test_merged_chain_images(kmax, monkeypatch):
         coords = coords_of(plan.packed, pts)
         assert (plan.digits_host(coords) == orc.digits(plan.packed, coords)).all()
         ref = orc.evaluate(plan.packed, coords, orc.ORACLE_LD)
-        got, o = plan.evaluate_host(coords, kernel="dmma")
-        assert o.kernel_used == _capi.TTN_KERNEL_DMMA
+        got, o = plan.evaluate_host(coords, kernel=kern)
+        assert o.kernel_used == _capi.KERNEL_IDS[kern]
         err = orc.error_metric(got, ref).max()
         assert err < TOL, (name, kmax, err)
         perm = rng.permutation(len(coords))
-        got2, _ = plan.evaluate_host(coords[perm], kernel="dmma")
+        got2, _ = plan.evaluate_host(coords[perm], kernel=kern)
         assert (got2 == got[perm]).all(), name
         f._plans.clear()
