@@ -1092,7 +1092,10 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   // XOR-swizzled by the slice number: lanes reading chunk j of different slices spread over banks
   double* s_leaf = reinterpret_cast<double*>(smem + (size_t)NTEAM * T6::BYTES);  // [NCLS][CHI]
   double* s_root = s_leaf + NCLS * CHI;                                           // [nout][NCLS][CHI]
-  for (int i = tid; i < NCLS * CPR; i += NT) {
+  // deep leaf / root groups (build_chain_mma): tables of 2^leaf_bits / 2^root_bits vectors stay in
+  // global memory and a point gathers one row of each
+  const bool deep = ch.leaf_bits != BITS || ch.root_bits != BITS;
+  for (int i = tid; i < (deep ? 0 : NCLS * CPR); i += NT) {
     const int sl = i / CPR, j = i % CPR, pj = j ^ (sl & (CPR - 1) & 7);
     s_leaf[sl * CHI + 2 * pj] = ch.leaf[sl * CHI + 2 * j];
     s_leaf[sl * CHI + 2 * pj + 1] = ch.leaf[sl * CHI + 2 * j + 1];
@@ -1116,6 +1119,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   const int64_t tstride = (int64_t)gridDim.x * NTEAM;
   const int R = ch.n_rounds;
   const uint64_t MASK = (uint64_t)(NCLS - 1);
+  const uint64_t LMASK = (1ull << ch.leaf_bits) - 1ull, RMASK = (1ull << ch.root_bits) - 1ull;
   const uint32_t lt = (1u << lane) - 1u;
   double sum_re = 0.0, sum_im = 0.0;
   int qh = 0; // global round counter of the team (rotates the counter sets)
@@ -1129,71 +1133,85 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   };
   if (R > 0) load_b(bcur, 0, warp);
 
+  // ---- K1: packed slice streams of the lane's PPL home points of one tile (interleaved for ILP)
+  auto compute_words = [&](int64_t tile_, uint64_t (&w0)[PPL], uint64_t (&w1)[PPL]) {
+    const int64_t p0 = tile_ * TP + warp * PW;
+    double x[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
+    for (int c = 0; c < dg.n_coords; ++c) {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int64_t p = p0 + k * 32 + lane;
+        x[k] = 0.0;
+        if (p < src.npts) {
+          x[k] = load_coord(src, p, c);
+          if (!coord_in_domain(x[k])) {
+            atomicOr(err, 1);
+            x[k] = 0.0;
+          }
+        }
+      }
+      if (ch.run_L[c] > 0 && !src.digits) {
+        const int L = ch.run_L[c], plow = ch.run_plow[c];
+        const double scale = ch.run_scale[c];
+        const bool rev = ch.run_rev[c] != 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+          if (rev) q = __brevll(q) >> (64 - L);
+          if (plow < 64) {
+            w0[k] += q << plow;
+            if (plow + L > 64) w1[k] += q >> (64 - plow);
+          } else {
+            w1[k] += q << (plow - 64);
+          }
+        }
+      } else {
+        for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+          const Digit2 e = s_d2[e_i];
+          const uint32_t stride = e.wv & 0xffu;
+          const bool hi = ((e.wv >> 8) & 0xffu) != 0;
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            const bool ge = src.digits ? (given_digit(src, p0 + k * 32 + lane, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                       : (x[k] >= e.thr1);
+            x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
+            const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+            if (hi) w1[k] += bb;
+            else w0[k] += bb;
+          }
+        }
+      }
+    }
+  };
+
   for (int64_t tile = (int64_t)blockIdx.x * NTEAM + team; tile < n_tiles; tile += tstride) {
     const int64_t p0 = tile * TP + warp * PW; // first home point of this warp
     uint64_t w1[PPL], cw[PPL];
     {
-      // ---- K1: digits of the lane's PPL home points (interleaved for ILP)
       uint64_t w0[PPL];
-      double x[PPL];
-#pragma unroll
-      for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
-      for (int c = 0; c < dg.n_coords; ++c) {
-#pragma unroll
-        for (int k = 0; k < PPL; ++k) {
-          const int64_t p = p0 + k * 32 + lane;
-          x[k] = 0.0;
-          if (p < src.npts) {
-            x[k] = load_coord(src, p, c);
-            if (!coord_in_domain(x[k])) {
-              atomicOr(err, 1);
-              x[k] = 0.0;
-            }
-          }
-        }
-        if (ch.run_L[c] > 0 && !src.digits) {
-          const int L = ch.run_L[c], plow = ch.run_plow[c];
-          const double scale = ch.run_scale[c];
-          const bool rev = ch.run_rev[c] != 0;
-#pragma unroll
-          for (int k = 0; k < PPL; ++k) {
-            unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
-            if (rev) q = __brevll(q) >> (64 - L);
-            if (plow < 64) {
-              w0[k] += q << plow;
-              if (plow + L > 64) w1[k] += q >> (64 - plow);
-            } else {
-              w1[k] += q << (plow - 64);
-            }
-          }
-        } else {
-          for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
-            const Digit2 e = s_d2[e_i];
-            const uint32_t stride = e.wv & 0xffu;
-            const bool hi = ((e.wv >> 8) & 0xffu) != 0;
-#pragma unroll
-            for (int k = 0; k < PPL; ++k) {
-              const bool ge = src.digits ? (given_digit(src, p0 + k * 32 + lane, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
-                                         : (x[k] >= e.thr1);
-              x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
-              const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
-              if (hi) w1[k] += bb;
-              else w0[k] += bb;
-            }
-          }
-        }
-      }
+      compute_words(tile, w0, w1);
       // ---- leaf rows
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {
         cw[k] = w0[k];
         const int row = warp * PW + k * 32 + lane;
-        const int sl = (int)(cw[k] & MASK);
-        const uint32_t L = s_leaf_u32 + (uint32_t)sl * (CHI * 8);
+        if (deep) {
+          const double2* L = reinterpret_cast<const double2*>(ch.leaf + (size_t)(cw[k] & LMASK) * CHI);
 #pragma unroll
-        for (int j = 0; j < CPR; ++j) {
-          const double2 v = lds128(L + (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4));
-          sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+          for (int j = 0; j < CPR; ++j) {
+            const double2 v = __ldg(L + j);
+            sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+          }
+        } else {
+          const int sl = (int)(cw[k] & MASK);
+          const uint32_t L = s_leaf_u32 + (uint32_t)sl * (CHI * 8);
+#pragma unroll
+          for (int j = 0; j < CPR; ++j) {
+            const double2 v = lds128(L + (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4));
+            sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+          }
         }
       }
     }
@@ -1204,7 +1222,14 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         w1[k] >>= BITS;
       }
     };
-    shift_stream();
+    {
+      const int lb = ch.leaf_bits; // 1..21
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = (cw[k] >> lb) | (w1[k] << (64 - lb));
+        w1[k] >>= lb;
+      }
+    }
 
     // classes of the next stream position: one shared-memory atomic per point on the team's
     // (class, parity) counters gives the point its position among the team's points of that class
@@ -1302,20 +1327,37 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     for (int k = 0; k < PPL; ++k) {
       const int row = warp * PW + k * 32 + lane;
       const int64_t p = p0 + k * 32 + lane;
-      const int sl = (int)(cw[k] & MASK);
-      const uint32_t R0 = s_root_u32 + (uint32_t)sl * (CHI * 8), R1 = R0 + (uint32_t)(NCLS * CHI * 8);
       double o0 = 0.0, o1 = 0.0;
+      if (deep) {
+        const double2* R0 = reinterpret_cast<const double2*>(ch.root + (size_t)(cw[k] & RMASK) * CHI);
+        const double2* R1 = R0 + ((size_t)1 << ch.root_bits) * CPR;
 #pragma unroll
-      for (int j = 0; j < CPR; ++j) {
-        const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
-        const uint32_t off = (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4);
-        const double2 q0 = lds128(R0 + off);
-        o0 = fma(v.x, q0.x, o0);
-        o0 = fma(v.y, q0.y, o0);
-        if (ch.nout == 2) {
-          const double2 q1 = lds128(R1 + off);
-          o1 = fma(v.x, q1.x, o1);
-          o1 = fma(v.y, q1.y, o1);
+        for (int j = 0; j < CPR; ++j) {
+          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+          const double2 q0 = __ldg(R0 + j);
+          o0 = fma(v.x, q0.x, o0);
+          o0 = fma(v.y, q0.y, o0);
+          if (ch.nout == 2) {
+            const double2 q1 = __ldg(R1 + j);
+            o1 = fma(v.x, q1.x, o1);
+            o1 = fma(v.y, q1.y, o1);
+          }
+        }
+      } else {
+        const int sl = (int)(cw[k] & MASK);
+        const uint32_t R0 = s_root_u32 + (uint32_t)sl * (CHI * 8), R1 = R0 + (uint32_t)(NCLS * CHI * 8);
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+          const uint32_t off = (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4);
+          const double2 q0 = lds128(R0 + off);
+          o0 = fma(v.x, q0.x, o0);
+          o0 = fma(v.y, q0.y, o0);
+          if (ch.nout == 2) {
+            const double2 q1 = lds128(R1 + off);
+            o1 = fma(v.x, q1.x, o1);
+            o1 = fma(v.y, q1.y, o1);
+          }
         }
       }
       if (p < src.npts) {
@@ -1376,21 +1418,53 @@ struct ChainImage {
 // exactly the same packed bit stream read k*bits0 bits at a time — so K1 and the run fast path are
 // untouched while a point needs 1/k as many matrix-vector products.  Products are accumulated in
 // long double and rounded once.  Needs (#positions) % k == 0 and >= 2k positions.
-static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0) {
+static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0, int kL, int kR) {
+  // positions: leaf group = leaf + steps[0, kL-1), middle groups of k steps, root group =
+  // steps[T-(kR-1), T) + root.  kL and kR may be much larger than k ("deep" leaf / root tables of
+  // 2^(bits0 kL) vectors, kept in global memory): those are built with vector products only, one
+  // member at a time (rounded to double per member, dot products accumulated in long double).
   typedef long double ld;
   const size_t M = (size_t)CHI * CHI;
   const int T = (int)a.steps.size(), S0 = a.nsl, SK = 1 << (bits0 * k);
   ChainImage m;
   m.nsl = SK;
-  // extend a table of row vectors / matrices (rows x CHI each) by one chain member
-  auto extend = [&](const std::vector<ld>& cur, int n_cur, int rows, const std::vector<double>& E, int member) {
-    std::vector<ld> nxt((size_t)n_cur * (1 << bits0) * rows * CHI, 0.0L);
-    for (int s = 0; s < n_cur; ++s)
+  // ---- leaf table: T_i[s + (b << bits0 i)] = T_{i-1}[s] . E_{i-1}[b]
+  {
+    std::vector<double> cur((size_t)S0 * CHI);
+    for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.leaf[i];
+    size_t n_cur = (size_t)1 << bits0;
+    for (int i = 1; i < kL; ++i) {
+      std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
+      const std::vector<double>& E = a.steps[i - 1];
       for (int bsl = 0; bsl < S0; ++bsl) {
-        const ld* A = cur.data() + (size_t)s * rows * CHI;
         const double* B = E.data() + (size_t)bsl * M;
-        ld* C = nxt.data() + (size_t)(s + (bsl << (bits0 * member))) * rows * CHI;
-        for (int i = 0; i < rows; ++i)
+        for (size_t sidx = 0; sidx < n_cur; ++sidx) {
+          const double* A = cur.data() + sidx * CHI;
+          double* C = nxt.data() + (sidx + ((size_t)bsl << (bits0 * i))) * CHI;
+          ld acc[32];
+          for (int j = 0; j < CHI; ++j) acc[j] = 0.0L;
+          for (int kk = 0; kk < CHI; ++kk) {
+            const ld av = A[kk];
+            if (av == 0.0L) continue;
+            for (int j = 0; j < CHI; ++j) acc[j] += av * (ld)B[(size_t)kk * CHI + j];
+          }
+          for (int j = 0; j < CHI; ++j) C[j] = (double)acc[j];
+        }
+      }
+      cur.swap(nxt);
+      n_cur <<= bits0;
+    }
+    m.leaf.swap(cur);
+  }
+  // ---- middle groups: matrix products in long double, rounded once
+  auto extend = [&](const std::vector<ld>& cur, int n_cur, const std::vector<double>& E, int member) {
+    std::vector<ld> nxt((size_t)n_cur * (1 << bits0) * M, 0.0L);
+    for (int sidx = 0; sidx < n_cur; ++sidx)
+      for (int bsl = 0; bsl < S0; ++bsl) {
+        const ld* A = cur.data() + (size_t)sidx * M;
+        const double* B = E.data() + (size_t)bsl * M;
+        ld* C = nxt.data() + (size_t)(sidx + (bsl << (bits0 * member))) * M;
+        for (int i = 0; i < CHI; ++i)
           for (int kk = 0; kk < CHI; ++kk) {
             const ld av = A[(size_t)i * CHI + kk];
             if (av == 0.0L) continue;
@@ -1399,56 +1473,50 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
       }
     return nxt;
   };
-  // leaf group: leaf vectors times the first k-1 steps
-  {
-    std::vector<ld> cur((size_t)(1 << bits0) * CHI, 0.0L);
-    for (int s = 0; s < S0; ++s)
-      for (int j = 0; j < CHI; ++j) cur[(size_t)s * CHI + j] = a.leaf[(size_t)s * CHI + j];
-    int n_cur = 1 << bits0;
-    for (int i = 1; i < k; ++i) {
-      cur = extend(cur, n_cur, 1, a.steps[i - 1], i);
-      n_cur <<= bits0;
-    }
-    m.leaf.resize((size_t)SK * CHI);
-    for (size_t i = 0; i < m.leaf.size(); ++i) m.leaf[i] = (double)cur[i];
-  }
-  auto first_member = [&](const std::vector<double>& E) {
+  const int G = (T - (kL - 1) - (kR - 1)) / k;
+  for (int g = 0; g < G; ++g) {
+    const int t0 = kL - 1 + g * k;
     std::vector<ld> cur((size_t)(1 << bits0) * M, 0.0L);
-    for (int s = 0; s < S0; ++s)
-      for (size_t i = 0; i < M; ++i) cur[(size_t)s * M + i] = E[(size_t)s * M + i];
-    return cur;
-  };
-  // middle groups: steps [g*k - 1, g*k + k - 2]
-  const int G = (T + 2) / k;
-  for (int g = 1; g + 1 < G; ++g) {
-    std::vector<ld> cur = first_member(a.steps[g * k - 1]);
+    for (int sl = 0; sl < S0; ++sl)
+      for (size_t i = 0; i < M; ++i) cur[(size_t)sl * M + i] = a.steps[t0][(size_t)sl * M + i];
     int n_cur = 1 << bits0;
     for (int i = 1; i < k; ++i) {
-      cur = extend(cur, n_cur, CHI, a.steps[g * k - 1 + i], i);
+      cur = extend(cur, n_cur, a.steps[t0 + i], i);
       n_cur <<= bits0;
     }
     std::vector<double> E((size_t)SK * M);
     for (size_t i = 0; i < E.size(); ++i) E[i] = (double)cur[i];
     m.steps.push_back(std::move(E));
   }
-  // root group: the last k-1 steps times the root vectors
+  // ---- root table, built from the root backwards (the member nearest the leaf owns the LOW bits):
+  // R_j[s + (idx << bits0)][i] = sum_l E_j[s][i][l] R_{j+1}[idx][l]
   {
-    std::vector<ld> cur = first_member(a.steps[T - (k - 1)]);
-    int n_cur = 1 << bits0;
-    for (int i = 1; i < k - 1; ++i) {
-      cur = extend(cur, n_cur, CHI, a.steps[T - (k - 1) + i], i);
-      n_cur <<= bits0;
-    }
-    m.root.assign((size_t)nout * SK * CHI, 0.0);
-    for (int o = 0; o < nout; ++o)
-      for (int s = 0; s < n_cur; ++s)
-        for (int bsl = 0; bsl < S0; ++bsl)
-          for (int i = 0; i < CHI; ++i) {
-            ld acc = 0.0L;
-            for (int j = 0; j < CHI; ++j)
-              acc += cur[(size_t)s * M + (size_t)i * CHI + j] * (ld)a.root[((size_t)o * S0 + bsl) * CHI + j];
-            m.root[((size_t)o * SK + (s + (bsl << (bits0 * (k - 1))))) * CHI + i] = (double)acc;
+    const size_t SR = (size_t)1 << (bits0 * kR);
+    m.root.assign((size_t)nout * SR * CHI, 0.0);
+    for (int o = 0; o < nout; ++o) {
+      std::vector<double> cur((size_t)S0 * CHI);
+      for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.root[(size_t)o * S0 * CHI + i];
+      size_t n_cur = (size_t)1 << bits0;
+      for (int j = kR - 2; j >= 0; --j) { // step index T - (kR - 1) + j
+        const std::vector<double>& E = a.steps[T - (kR - 1) + j];
+        std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
+        for (int sl = 0; sl < S0; ++sl) {
+          const double* A = E.data() + (size_t)sl * M;
+          for (size_t idx = 0; idx < n_cur; ++idx) {
+            const double* Rv = cur.data() + idx * CHI;
+            double* C = nxt.data() + ((size_t)sl + (idx << bits0)) * CHI;
+            for (int i = 0; i < CHI; ++i) {
+              ld acc = 0.0L;
+              for (int l = 0; l < CHI; ++l) acc += (ld)A[(size_t)i * CHI + l] * (ld)Rv[l];
+              C[i] = (double)acc;
+            }
           }
+        }
+        cur.swap(nxt);
+        n_cur <<= bits0;
+      }
+      std::copy(cur.begin(), cur.end(), m.root.begin() + (size_t)o * SR * CHI);
+    }
   }
   return m;
 }
@@ -1529,6 +1597,28 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       }
   }
   const bool merge = kmerge > 1;
+  // Deep leaf / root groups (team-sorted kernel only): the first kL and the last kR vertices are
+  // contracted into tables of 2^(bits0 kL) leaf vectors / 2^(bits0 kR) root vectors in global memory
+  // (<= 128 MB each); a point gathers one row of each and runs only the middle groups as rounds.
+  int kL = kmerge, kR = kmerge;
+  {
+    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && p->all_base2;
+    // default: only when the two tables absorb the WHOLE chain with <= 2^16 rows each (L2-resident,
+    // built in a fraction of a second): the evaluation is then two row gathers and a dot product.
+    // TTN_MMA_DEEP=b sets the budget to 2^b rows of 16 doubles for any chain (0 disables); measured
+    // on config 2 with b = 20: 5.7 G points/s device-resident instead of 3.6 G, 2 x 128 MB of
+    // tables, 2 s of plan time, the kernel then bound by random 128-byte HBM gathers
+    int deep_bits = (n * bits0 <= 32) ? 16 : 0;
+    if (merge && v6_on && deep_bits > 0) {
+      const int lb = deep_bits - (CHI >= 32 ? 1 : 0) + (CHI <= 8 ? 1 : 0), rb = lb - (cplx ? 1 : 0);
+      kL = std::max(kmerge, std::min(lb / bits0, n / 2));
+      kR = std::max(kmerge, std::min(rb / bits0, n - kL));
+      const int mid = n - kL - kR;
+      const int delta = mid >= 0 ? (kmerge - mid % kmerge) % kmerge : 0;
+      if (mid >= 0 && kR - delta >= kmerge) kR -= delta; // whole middle groups without identity padding
+      if (n - kL - kR < 0) kL = kR = kmerge;
+    }
+  }
 
   // sites per round: as many as keep the class count <= 4 (binary digits: 2 sites -> 4 classes)
   int spr = 1;
@@ -1551,7 +1641,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // the chain is padded with identity sites (slice bits always 0) up to a whole number of rounds
   // (merged: up to an even number of positions), so that every round has exactly `spr` sites
   const int n_steps = n >= 2 ? n - 2 : 0;
-  const int n_steps_p = merge ? (n + kmerge - 1) / kmerge * kmerge - 2 : (n_steps + spr - 1) / spr * spr;
+  const int n_steps_p = merge ? kL + kR + (n - kL - kR + kmerge - 1) / kmerge * kmerge - 2 : (n_steps + spr - 1) / spr * spr;
   const int root_pos = n >= 2 ? 1 + n_steps_p : 0; // in vertices
   const int n_pos = root_pos + 1;
   const int n_words = bits0 == 0 ? 0 : (n_pos * bits0 + 63) / 64;
@@ -1635,11 +1725,11 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   const double root_flops = n >= 2 ? (cplx ? 8.0 : 2.0) * d->link_dim[order[n - 2]] : 0.0;
   p->cmma_flops_exec = flops_exec + root_flops;
   if (merge) {
-    // one product per middle group: steps [g*k - 1, g*k + k - 2]
+    // one product per middle group: steps [kL - 1 + g k, kL - 1 + g k + k - 1]
     double fm = 0.0;
-    const int G = (n_steps_p + 2) / kmerge;
-    for (int g = 1; g + 1 < G; ++g) fm += (cplx ? 8.0 : 2.0) * dim_in[g * kmerge - 1] * dim_out[g * kmerge + kmerge - 2];
-    p->cmma_flops_exec = fm + (cplx ? 8.0 : 2.0) * dim_in[n_steps_p - (kmerge - 1)];
+    const int G = (n_steps_p + 2 - kL - kR) / kmerge;
+    for (int g = 0; g < G; ++g) fm += (cplx ? 8.0 : 2.0) * dim_in[kL - 1 + g * kmerge] * dim_out[kL - 1 + g * kmerge + kmerge - 1];
+    p->cmma_flops_exec = fm + (cplx ? 8.0 : 2.0) * dim_in[n_steps_p - (kR - 1)];
   }
 
   // the unmerged image stays available for the prefix-shared grid kernel (k_grid_share.cu)
@@ -1648,7 +1738,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   c.n_vertices = n;
   c.chi = CHI;
   c.nout = nout;
-  c.root_pos = root_pos / kmerge; // in stream positions
+  c.root_pos = merge ? 1 + (n_steps_p + 2 - kL - kR) / kmerge : root_pos; // in stream positions (uniform groups only)
   int rc;
   if (NSL0 == 2) {
     ChainMmaDev& q = p->cmma_plain;
@@ -1672,7 +1762,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   }
   int NSL = NSL0, bits = bits0;
   if (merge) {
-    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0);
+    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0, kL, kR);
     if ((rc = upload_chain_image(p, mg, CHI, c))) return rc;
     NSL = mg.nsl;
     bits = bits0 * kmerge;
@@ -1688,6 +1778,8 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     c.n_steps = n_steps_p;
   }
   c.merged = merge ? kmerge : 0;
+  c.leaf_bits = merge ? bits0 * kL : bits0; // stream bits the leaf / root group consumes
+  c.root_bits = merge ? bits0 * kR : bits0;
   c.nsl = NSL;
   c.bits = bits;
   c.per_word = bits == 0 ? (1 << 30) : 64 / bits;

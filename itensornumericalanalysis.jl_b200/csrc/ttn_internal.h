@@ -99,7 +99,8 @@ struct ChainMmaDev {
   int32_t nout;     // 1 (real) or 2 (re, im)
   int32_t bits, per_word, n_words;
   int32_t root_pos; // position of the root in the packed slice stream (after identity padding)
-  int32_t merged;   // 1: vertex pairs pre-contracted into 4-slice positions (build_chain_mma)
+  int32_t merged;   // k > 0: k vertices pre-contracted into one stream position (build_chain_mma)
+  int32_t leaf_bits, root_bits; // stream bits of the leaf / root group (deep tables: up to 21)
   // per coordinate slot: "run" fast path of K1 (see build_chain_mma): L == 0 -> use the table loop
   int32_t run_L[TTN_MAX_COORDS];     // number of binary digits
   int32_t run_plow[TTN_MAX_COORDS];  // lowest stream position of the run

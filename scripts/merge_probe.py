@@ -15,7 +15,10 @@ def run(name, f, ncol, npts=npts):
     for merge in MERGES:
         os.environ["TTN_MMA_MERGE"] = merge
         f._plans.clear()
+        import time as _t
+        _t0 = _t.time()
         plan = f.plan()
+        _tb = _t.time() - _t0
         info = plan.info()
         torch.manual_seed(1)
         x = torch.rand((npts, ncol), dtype=torch.float64, device="cuda:0")
@@ -27,7 +30,7 @@ def run(name, f, ncol, npts=npts):
         res[merge] = out.clone()
         tf = info["flops_per_point"] * npts / (best * 1e-3) / 1e12
         print(f"{name:26s} merge={merge} {npts:.1e} pts {best:9.3f} ms {npts / best / 1e3:9.2f} Mpts/s  {tf:6.2f} TF algorithmic, "
-              f"{o.flops_executed / (best * 1e-3) / 1e12:6.2f} TF executed")
+              f"{o.flops_executed / (best * 1e-3) / 1e12:6.2f} TF executed, plan {_tb:.2f} s")
     a = res["1"]
     scale = a.abs().max().item()
     for m in MERGES[1:]:

@@ -49,7 +49,13 @@ def _random_network(seed):
 
 
 @pytest.mark.parametrize("seed", range(60))
-def test_random_network_all_kernels(seed):
+def test_random_network_all_kernels(seed, monkeypatch):
+    # chains: rotate the plan-time shape of the DMMA kernel's image over the seeds — default rule (short
+    # chains collapse into two tables), uniform groups (every position a DMMA round), small deep tables
+    if seed % 3 == 1:
+        monkeypatch.setenv("TTN_MMA_DEEP", "0")
+    elif seed % 3 == 2:
+        monkeypatch.setenv("TTN_MMA_DEEP", "5")
     kind, f = _random_network(seed)
     imap = f.indexmap
     dims = imap.dimensions()

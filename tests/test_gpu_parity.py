@@ -397,14 +397,19 @@ def test_evaluate_at_index_settings(which):
     assert e.value.code == _capi.TTN_ERR_INVALID
 
 
-@pytest.mark.parametrize("kmax", ["1", "2", "3", "4", "5"])
-def test_merged_chain_images(kmax, monkeypatch):
+@pytest.mark.parametrize("kmax,deep", [("1", "0"), ("2", "0"), ("3", "0"), ("4", "0"), ("5", "0"), ("4", None),
+                                       ("4", "5"), ("4", "7"), ("2", "6"), ("3", "9"), ("4", "20")])
+def test_merged_chain_images(kmax, deep, monkeypatch):
     """Plan-time group merging of the DMMA chain kernel (k vertices pre-contracted per stream
     position, k <= TTN_MMA_MERGE): every chain length 2..14 (identity padding, leaf/root groups of
     every size), real and complex, one and two digits per vertex (complex maps), ragged link dimensions — values
     against the 80-bit oracle, digits untouched, and the same point gives the same bits wherever
-    it sits in the batch."""
+    it sits in the batch.  `deep` varies the size of the leaf / root groups (tables of 2^bits vectors in
+    global memory): 0 = uniform groups (every position is a DMMA round), small budgets = tables plus
+    middle rounds, 20 = the whole chain in two tables."""
     monkeypatch.setenv("TTN_MMA_MERGE", kmax)
+    if deep is not None:   # budget (log2 rows) of the deep leaf / root tables; None = the default rule
+        monkeypatch.setenv("TTN_MMA_DEEP", deep)
     rng = np.random.default_rng(int(kmax))
     nets = []
     for L in range(2, 15):
