@@ -5,9 +5,10 @@
 //   leaf            M_v[p]    = T_v[d]                                   (row copy)
 //   one child  c    M_v[p,:]  = M_c[p,:] * T_v[d]            (W x W)      grouped GEMM, K = W
 //   two children    M_v[p,n]  = sum_{a,b} M_a[p,a] M_b[p,b] T_v[d][a,b,n]  Khatri-Rao GEMM, K = W^2:
-//                   the A operand M_a[p,a]*M_b[p,b] is never materialised — each lane multiplies
-//                   its M_a value (held in a register for a whole `a`) into the M_b fragment it
-//                   loads from shared memory (one DMUL per 4..16 DMMAs)
+//                   the A operand M_a[p,a]*M_b[p,b] is never materialised: for every `a` the b-sum
+//                   M_b[p,:] T_v[d][a,:,n] runs on DMMA into a second accumulator tile, which is then
+//                   folded in with M_a[p,a] (one DFMA per 8 DMMAs): b first, a second, like a nested
+//                   contraction (2W additions deep instead of W^2)
 //   root            value = full contraction with a parent dimension of 1  (small dot kernels)
 // CTA tile: 128 rows x W columns; both child row blocks stay in shared memory for the whole K loop,
 // only the tensor T_v[d] (B operand, fragment order) streams through a 3-stage cp.async ring.
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const uint32_t sa_base = smem_u32(Sa), sb_base = smem_u32(Sb);
   double ma[4] = {1.0, 1.0, 1.0, 1.0};
+  double inner[NCH == 2 ? 4 : 1][NT][2]; // partial sums over b for the current a (two children)
 
   for (int kc = 0; kc < NKC; ++kc) {
     if (kc + 2 < NKC) {
@@ -181,20 +183,37 @@ __global__ void __launch_bounds__(256, 1)
       for (int i = 0; i < 4; ++i) ma[i] = lds64(sa_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + a) * 8u);
     }
     const uint32_t b_st = bs_base + (uint32_t)((kc % TSTAGES) * B_STAGE_D) * 8u;
+    if (NCH == 2 && (kc % BCHUNKS) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) inner[i][j][0] = inner[i][j][1] = 0.0;
+    }
 #pragma unroll
     for (int k4 = 0; k4 < TBK / 4; ++k4) {
       double af[4], bf[NT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const double mb = lds64(sb_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + b0 + k4 * 4 + t) * 8u);
-        af[i] = (NCH == 2) ? ma[i] * mb : mb;
-      }
+      for (int i = 0; i < 4; ++i) af[i] = lds64(sb_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + b0 + k4 * 4 + t) * 8u);
 #pragma unroll
       for (int j = 0; j < NT; ++j) bf[j] = lds64(b_st + (uint32_t)((k4 * (W / 8) + wn * NT + j) * 32 + lane) * 8u);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NT; ++j) {
+          if (NCH == 2) dmma884(inner[i][j][0], inner[i][j][1], af[i], bf[j]);
+          else dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    // two children: the b-sum of one `a` is complete -> acc += M_a[p, a] * inner.  Summing b first and a
+    // second is the order a nested contraction uses (and the oracle): 2 W additions deep instead of W^2
+    if (NCH == 2 && (kc % BCHUNKS) == BCHUNKS - 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          acc[i][j][0] = fma(ma[i], inner[i][j][0], acc[i][j][0]);
+          acc[i][j][1] = fma(ma[i], inner[i][j][1], acc[i][j][1]);
+        }
     }
     __syncthreads();
   }
@@ -256,10 +275,33 @@ __global__ void tree_root_kernel(int nch, const double* __restrict__ Ma, const d
   }
 }
 
+// ---- subtree message tables (build_tree_tables): the message a subtree sends upwards depends only
+// on the digits inside the subtree; for subtrees with few bits every message is tabulated at plan time.
+// vs[3 j .. 3 j + 2] = (vertex, bit offset in the table index, slice mask) of the j-th subtree vertex.
+__global__ void tree_enum_kernel(uint8_t* __restrict__ slices, int pc, const int32_t* __restrict__ vs, int ns) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pc) return;
+  for (int j = 0; j < ns; ++j) slices[(size_t)vs[3 * j] * pc + i] = (uint8_t)((i >> vs[3 * j + 1]) & vs[3 * j + 2]);
+}
+
+__global__ void tree_table_kernel(const uint8_t* __restrict__ slices, int pc, const int32_t* __restrict__ vs, int ns,
+                                  const double* __restrict__ table, int W, double* __restrict__ M) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // one double2 per thread
+  const int per_row = W / 2;
+  if (idx >= (int64_t)pc * per_row) return;
+  const int i = (int)(idx / per_row), j = (int)(idx % per_row);
+  uint32_t t = 0;
+  for (int q = 0; q < ns; ++q) t |= (uint32_t)slices[(size_t)vs[3 * q] * pc + i] << vs[3 * q + 1];
+  reinterpret_cast<double2*>(M)[idx] = __ldg(reinterpret_cast<const double2*>(table + (size_t)t * W) + j);
+}
+
 // ------------------------------------------------------------------------------ host side
+
+static int build_tree_tables(ttn_plan* p, const ttn_desc* d);
 
 int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   p->tgemm_ok = false;
+  p->tg_tab_of.clear();
   const int n = d->n_vertices;
   if (d->is_complex || n < 2) return TTN_OK; // real networks only (for now)
   int maxchi = 1;
@@ -338,7 +380,7 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   TTN_CUDA(cudaMemcpy(d_ns, p->nslices.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   g.nslices = d_ns;
   p->tgemm_ok = true;
-  return TTN_OK;
+  return build_tree_tables(p, d);
 }
 
 template <int W, int NCH>
@@ -417,6 +459,14 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
       const double* blob = g.blob + p->tg_frag_off[v];
       const int ca = nch >= 1 ? p->child[p->child_ptr[v]] : -1;
       const int cb = nch == 2 ? p->child[p->child_ptr[v] + 1] : -1;
+      const int tab = p->tg_tab_of.empty() ? -1 : p->tg_tab_of[v];
+      if (tab == -2) continue; // inside a tabulated subtree
+      if (tab >= 0) {
+        tree_table_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices, PC, p->tg_tab_vs[tab], p->tg_tab_ns[tab],
+                                                                                          p->tg_tab[tab], W, M(v));
+        *n_launches += 1;
+        continue;
+      }
       if (v == g.root) {
         tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
                                                      slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out,
@@ -443,6 +493,166 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   }
   *n_partial = do_sum ? 1 : 0;
   return TTN_OK;
+}
+
+// Subtree message tables.  sub_bits(v) = sum of log2(nslices) over v's subtree; every non-root vertex
+// whose subtree has >= 2 vertices, only power-of-two slice counts and sub_bits <= the budget (2^bits
+// rows of W doubles <= 32 MB, bits <= 16; TTN_TREE_TABLE_BITS overrides, 0 disables) and whose parent
+// does not qualify becomes a TABLE vertex: its 2^bits possible messages are computed here, once, by
+// running the ordinary vertex-by-vertex kernels over the enumerated digit settings, and an evaluation
+// replaces the whole subtree by one row gather per point (tree_table_kernel).
+static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
+  const int n = d->n_vertices;
+  const TreeGemmDev& g = p->tgemm;
+  const int W = g.W;
+  int budget = 16;
+  while (budget > 0 && ((size_t)1 << budget) * W * 8 > ((size_t)32 << 20)) --budget;
+  if (const char* e = getenv("TTN_TREE_TABLE_BITS")) budget = std::min(atoi(e), 20);
+  p->tg_tab_of.assign(n, -1);
+  p->tg_tab.clear();
+  p->tg_tab_vs.clear();
+  p->tg_tab_ns.clear();
+  p->tg_tab_bits.clear();
+  // executed flops per point (the flop rule over the vertices that still run)
+  auto vertex_flops = [&](int v) {
+    const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
+    const double pd = v == d->root ? 1.0 : d->link_dim[v];
+    if (nch == 0) return 0.0;
+    const double ca = d->link_dim[p->child[p->child_ptr[v]]];
+    if (nch == 1) return 2.0 * ca * pd;
+    const double cb = d->link_dim[p->child[p->child_ptr[v] + 1]];
+    return 2.0 * (ca * cb * pd + cb * pd);
+  };
+  p->tgemm_flops_exec = 0.0;
+  for (int v = 0; v < n; ++v) p->tgemm_flops_exec += vertex_flops(v);
+  if (budget <= 0) return TTN_OK;
+  std::vector<int> bits(n, 0), size(n, 1);
+  std::vector<char> ok(n, 1);
+  for (int oi = 0; oi < n; ++oi) { // post order: children first
+    const int v = p->post[oi];
+    const int ns = p->nslices[v];
+    if (ns & (ns - 1)) ok[v] = 0;
+    int b = 0;
+    while ((1 << b) < ns) ++b;
+    bits[v] = b;
+    for (int c = p->child_ptr[v]; c < p->child_ptr[v + 1]; ++c) {
+      const int u = p->child[c];
+      bits[v] += bits[u];
+      size[v] += size[u];
+      ok[v] = ok[v] && ok[u];
+    }
+    if (bits[v] > budget) ok[v] = 0;
+  }
+  std::vector<int> frontier;
+  for (int v = 0; v < n; ++v) {
+    if (v == d->root || !ok[v] || size[v] < 2) continue;
+    const int par = d->parent[v];
+    if (par >= 0 && par != d->root && ok[par]) continue; // the parent's table covers it
+    frontier.push_back(v);
+  }
+  if (frontier.empty()) return TTN_OK;
+  // workspace for the largest table
+  int maxb = 0;
+  for (int v : frontier) maxb = std::max(maxb, bits[v]);
+  const int PCmax = std::max(TBM, 1 << maxb);
+  int maxsz = 0;
+  for (int v : frontier) maxsz = std::max(maxsz, size[v]);
+  double* d_msgs = nullptr;
+  uint8_t* d_slices = nullptr;
+  uint32_t* d_lists = nullptr;
+  int* d_offs = nullptr;
+  TTN_CUDA(cudaMalloc(&d_msgs, (size_t)maxsz * PCmax * W * 8));
+  TTN_CUDA(cudaMalloc(&d_slices, (size_t)n * PCmax));
+  TTN_CUDA(cudaMalloc(&d_lists, (size_t)n * PCmax * 4));
+  TTN_CUDA(cudaMalloc(&d_offs, ((size_t)n * 9 * 2 + 32) * 4));
+  int rc = TTN_OK;
+  for (size_t fi = 0; fi < frontier.size() && rc == TTN_OK; ++fi) {
+    const int v = frontier[fi];
+    const int PC = std::max(TBM, 1 << bits[v]);
+    // subtree vertices in post order, their message slots and bit offsets
+    std::vector<int> sub, slot(n, -1);
+    std::vector<int32_t> vs;
+    {
+      std::vector<char> in(n, 0);
+      in[v] = 1;
+      // a vertex is in the subtree iff its parent is (walk the post order backwards: parents first)
+      for (int oi = n - 1; oi >= 0; --oi) {
+        const int u = p->post[oi];
+        if (u != v && d->parent[u] >= 0 && in[d->parent[u]]) in[u] = 1;
+      }
+      int off = 0;
+      for (int oi = 0; oi < n; ++oi) {
+        const int u = p->post[oi];
+        if (!in[u]) continue;
+        slot[u] = (int)sub.size();
+        sub.push_back(u);
+        const int ns = p->nslices[u];
+        int b = 0;
+        while ((1 << b) < ns) ++b;
+        vs.push_back(u);
+        vs.push_back(off);
+        vs.push_back(ns - 1);
+        off += b;
+      }
+    }
+    int32_t* d_vs;
+    if (cudaMalloc(&d_vs, vs.size() * 4) != cudaSuccess) {
+      rc = TTN_ERR_CUDA;
+      break;
+    }
+    p->allocs.push_back(d_vs);
+    cudaMemcpy(d_vs, vs.data(), vs.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(d_slices, 0, (size_t)n * PC);
+    int* cls_off = d_offs;
+    int* tile_off = d_offs + (size_t)n * 9 + 16;
+    tree_enum_kernel<<<(PC + 255) / 256, 256>>>(d_slices, PC, d_vs, (int)sub.size());
+    tree_classify_kernel<<<n, 1024>>>(d_slices, PC, g.nslices, d_lists, cls_off, tile_off);
+    auto M = [&](int u) { return d_msgs + (size_t)slot[u] * PC * W; };
+    for (int u : sub) {
+      const int nch = p->child_ptr[u + 1] - p->child_ptr[u];
+      const double* blob = g.blob + p->tg_frag_off[u];
+      if (nch == 0) {
+        tree_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256>>>(d_slices + (size_t)u * PC, PC, blob, W, M(u));
+      } else {
+        const int ca = p->child[p->child_ptr[u]];
+        const int cb = nch == 2 ? p->child[p->child_ptr[u] + 1] : -1;
+        const double* Ma = nch == 2 ? M(ca) : nullptr;
+        const double* Mb = nch == 2 ? M(cb) : M(ca);
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
+        if (rc) break;
+      }
+    }
+    if (rc) break;
+    double* d_tab;
+    const size_t rows = (size_t)1 << bits[v];
+    if (cudaMalloc(&d_tab, rows * W * 8) != cudaSuccess) {
+      rc = TTN_ERR_CUDA;
+      break;
+    }
+    p->allocs.push_back(d_tab);
+    cudaMemcpy(d_tab, M(v), rows * W * 8, cudaMemcpyDeviceToDevice);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      rc = TTN_ERR_CUDA;
+      break;
+    }
+    const int ti = (int)p->tg_tab.size();
+    p->tg_tab.push_back(d_tab);
+    p->tg_tab_vs.push_back(d_vs);
+    p->tg_tab_ns.push_back((int)sub.size());
+    p->tg_tab_bits.push_back(bits[v]);
+    for (int u : sub) {
+      p->tg_tab_of[u] = u == v ? ti : -2;
+      p->tgemm_flops_exec -= vertex_flops(u);
+    }
+  }
+  cudaFree(d_msgs);
+  cudaFree(d_slices);
+  cudaFree(d_lists);
+  cudaFree(d_offs);
+  if (rc == TTN_ERR_CUDA) set_error(std::string("tree tables: ") + cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }
 
 } // namespace ttn

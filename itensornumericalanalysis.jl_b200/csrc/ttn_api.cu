@@ -480,6 +480,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     opts->kernel_ms = total;
     opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? p->cmma_flops_exec
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
+                            : (kernel == TTN_KERNEL_TREE && !p->tg_tab.empty()) ? p->tgemm_flops_exec
                                                                              : p->info.flops_per_point) *
                            (double)npts;
     int herr = 0;

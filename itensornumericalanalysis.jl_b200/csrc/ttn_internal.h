@@ -179,6 +179,12 @@ struct ttn_plan {
   ttn::TreeGemmDev tgemm{};
   bool tgemm_ok = false;
   std::vector<int64_t> tg_frag_off;
+  // subtree message tables of the tree kernel (build_tree_tables): per vertex -1 = computed, -2 = inside a
+  // tabulated subtree, >= 0 = index of its table
+  std::vector<int32_t> tg_tab_of, tg_tab_ns, tg_tab_bits;
+  std::vector<double*> tg_tab;
+  std::vector<int32_t*> tg_tab_vs;
+  double tgemm_flops_exec = 0.0;
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int* d_err = nullptr;    // domain-error flag

@@ -25,7 +25,7 @@ for _ in range(2):
     o = plan.evaluate_device(x.data_ptr(), npts, out.data_ptr())
     best = min(best, o.kernel_ms)
 tf = info["flops_per_point"] * npts / (best * 1e-3) / 1e12
-print(f"cfg3 chi={chi}: {npts:.2e} pts {best:.2f} ms {npts / best / 1e3:.3f} Mpts/s {tf:.2f} TFLOP/s ({100 * tf / dmma.value:.1f}% of DMMA peak {dmma.value:.1f}), launches {o.n_launches}")
+print(f"cfg3 chi={chi}: {npts:.2e} pts {best:.2f} ms {npts / best / 1e3:.3f} Mpts/s {tf:.2f} TFLOP/s algorithmic, {o.flops_executed / (best * 1e-3) / 1e12:.2f} TFLOP/s executed ({100 * o.flops_executed / (best * 1e-3) / 1e12 / dmma.value:.1f}% of DMMA peak {dmma.value:.1f}; {o.flops_executed / npts:.0f} flop/pt), launches {o.n_launches}")
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import oracle as orc
 idx = np.arange(0, npts, max(1, npts // 64))[:64]

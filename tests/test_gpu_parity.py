@@ -451,3 +451,40 @@ def test_merged_chain_images(kmax, deep, monkeypatch):
         got2, _ = plan.evaluate_host(coords[perm], kernel=kern)
         assert (got2 == got[perm]).all(), name
         f._plans.clear()
+
+
+def test_tree_subtree_tables(monkeypatch):
+    """Subtree message tables of the tree kernel (build_tree_tables): whatever the table budget — none,
+    tiny (only the lowest subtrees), default (whole branches) — the values are bit-for-bit the same
+    (the tables are filled by the very kernels that would otherwise run per point) and match the oracle."""
+    nets = []
+    g = t.named_binary_tree(5)
+    ws = g.vertices()[1:]
+    nets.append(("bintree5_chi20", t.rand_itn(t.continuous_siteinds(g, [ws[i::3] for i in range(3)]), link_space=20, rng=14,
+                                              normalise=True)))
+    g = t.named_binary_tree(4)
+    nets.append(("bintree4_chi12_allsites", t.rand_itn(t.continuous_siteinds(g, map_dimension=2), link_space=12, rng=15,
+                                                       normalise=True)))
+    g = t.named_comb_tree((3, 4))    # rooted at an end: <= 2 children everywhere
+    nets.append(("comb3x4_chi16", t.rand_itn(t.continuous_siteinds(g, map_dimension=2), link_space=16, rng=16, normalise=True)))
+    rng = np.random.default_rng(8)
+    for name, f in nets:
+        dims = f.indexmap.dimensions()
+        pts = cases.edge_points(8, len(dims), rng, 400)
+        base = None
+        for bits in ("0", "3", "7", "16"):
+            monkeypatch.setenv("TTN_TREE_TABLE_BITS", bits)
+            f._plans.clear()
+            plan = f.plan(dims)
+            if not plan.info()["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE):
+                break
+            got, o = plan.evaluate_host(pts, kernel="tree")
+            if base is None:
+                ref = orc.evaluate(plan.packed, pts, orc.ORACLE_LD)
+                assert orc.error_metric(got, ref).max() < TOL, name
+                base, flops0 = got, o.flops_executed
+            else:
+                assert (got == base).all(), (name, bits)
+                assert o.flops_executed <= flops0
+        f._plans.clear()
+        assert base is not None or name.startswith("comb"), name
