@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 1)
         }
     }
     // two children: the b-sum of one `a` is complete -> acc += M_a[p, a] * inner.  Summing b first and a
-    // second is the order a nested contraction uses (and the oracle): 2 W additions deep instead of W^2
+    // second is the order a nested contraction uses: 2 W additions deep instead of W^2
     if (NCH == 2 && (kc % BCHUNKS) == BCHUNKS - 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -526,29 +526,37 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
   p->tgemm_flops_exec = 0.0;
   for (int v = 0; v < n; ++v) p->tgemm_flops_exec += vertex_flops(v);
   if (budget <= 0) return TTN_OK;
-  std::vector<int> bits(n, 0), size(n, 1);
+  std::vector<int> bits(n, 0), size(n, 1), frontier;
   std::vector<char> ok(n, 1);
-  for (int oi = 0; oi < n; ++oi) { // post order: children first
-    const int v = p->post[oi];
-    const int ns = p->nslices[v];
-    if (ns & (ns - 1)) ok[v] = 0;
-    int b = 0;
-    while ((1 << b) < ns) ++b;
-    bits[v] = b;
-    for (int c = p->child_ptr[v]; c < p->child_ptr[v + 1]; ++c) {
-      const int u = p->child[c];
-      bits[v] += bits[u];
-      size[v] += size[u];
-      ok[v] = ok[v] && ok[u];
+  for (;; --budget) { // lower the per-table budget until all tables together stay under 1 GB
+    if (budget <= 0) return TTN_OK;
+    std::fill(ok.begin(), ok.end(), 1);
+    std::fill(size.begin(), size.end(), 1);
+    for (int oi = 0; oi < n; ++oi) { // post order: children first
+      const int v = p->post[oi];
+      const int ns = p->nslices[v];
+      if (ns & (ns - 1)) ok[v] = 0;
+      int b = 0;
+      while ((1 << b) < ns) ++b;
+      bits[v] = b;
+      for (int c = p->child_ptr[v]; c < p->child_ptr[v + 1]; ++c) {
+        const int u = p->child[c];
+        bits[v] += bits[u];
+        size[v] += size[u];
+        ok[v] = ok[v] && ok[u];
+      }
+      if (bits[v] > budget) ok[v] = 0;
     }
-    if (bits[v] > budget) ok[v] = 0;
-  }
-  std::vector<int> frontier;
-  for (int v = 0; v < n; ++v) {
-    if (v == d->root || !ok[v] || size[v] < 2) continue;
-    const int par = d->parent[v];
-    if (par >= 0 && par != d->root && ok[par]) continue; // the parent's table covers it
-    frontier.push_back(v);
+    frontier.clear();
+    size_t total = 0;
+    for (int v = 0; v < n; ++v) {
+      if (v == d->root || !ok[v] || size[v] < 2) continue;
+      const int par = d->parent[v];
+      if (par >= 0 && par != d->root && ok[par]) continue; // the parent's table covers it
+      frontier.push_back(v);
+      total += ((size_t)1 << bits[v]) * W * 8;
+    }
+    if (total <= ((size_t)1 << 30)) break;
   }
   if (frontier.empty()) return TTN_OK;
   // workspace for the largest table
