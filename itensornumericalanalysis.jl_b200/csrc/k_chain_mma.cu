@@ -6,20 +6,23 @@
 // 24 %, profiles/).  An m8n8k4 DMMA performs 8 FMAs per lane per (A,B) operand pair, and the B
 // (matrix) fragment is reused by every 8-point group that selected the same slice.
 //
-// Scheme (per CTA, a tile of P points):
-//   * the state of the tile lives in shared memory, one row of CHI doubles per point (16-byte
+// Common scheme:
+//   * the state of a tile of points lives in shared memory, one row of CHI doubles per point (16-byte
 //     chunks XOR-swizzled by row so that row gathers and owner accesses avoid bank conflicts);
-//   * a ROUND covers `spr` consecutive sites.  Points are counting-sorted by the slices they
-//     select at those sites (class c = sum_k d_k * nsl^k) with warp ballots; each class is padded
-//     to a multiple of 8 rows (pad rows point at a scratch row);
-//   * a warp takes a contiguous range of 8-row groups.  For a batch of up to GB groups of one
-//     class it gathers the rows as DMMA A fragments, runs the spr site products entirely in
-//     registers and scatters the rows back.  The D fragment of one site IS the A fragment of the
-//     next one: lane (g,t) holds columns 8nb+2t+e, and the k-block kb = 2nb+e of the next MMA
-//     contracts exactly those columns because the B fragments are stored row-permuted to match
-//     (host side, build_chain_mma) — no shuffles, no shared-memory round trip inside a round;
-//   * B fragments for the round's sites arrive through a ring of TMA bulk copies (UBLKCP) signalled
-//     by mbarriers, issued by a dedicated producer warp.
+//   * a ROUND covers one stream position (or `spr` consecutive sites).  Points are counting-sorted by
+//     the slice they select there; each class is padded to a multiple of 8 rows (pad rows point at an
+//     all-zero row); 8-row groups of one class are gathered as DMMA A fragments, multiplied by the
+//     class's site matrix (B fragments, fragment order prepared on the host) and scattered back.
+//   * the packed slice stream of a point (K1) is one bit string, bit position = chain position x
+//     bits per vertex, consumed a few bits per round.
+// Three kernels share it (launch_chain_mma picks):
+//   chain_mma6_kernel  merged binary chains (build_chain_mma contracts k vertices per position, and
+//                      optionally whole leaf / root groups into tables): independent 4-warp teams,
+//                      team-wide sort with shared-memory atomics, site matrices in registers;
+//   chain_mma5_kernel  width <= 16, anything else: warp-autonomous (128 points per warp, warp-local
+//                      sort), B fragments through a TMA/mbarrier ring, D fragment of one site reused
+//                      as A fragment of the next (B rows permuted on the host to match);
+//   chain_mma3_kernel  width 32, anything else: CTA-wide sort by specialised front-end warps.
 // Complex networks are embedded as real ones of twice the width: row = [re | im],
 // M -> [[Re, Im], [-Im, Re]]: exactly the 8 flops per complex MAC of the flop rule.
 #include <algorithm>
