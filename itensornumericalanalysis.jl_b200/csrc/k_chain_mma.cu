@@ -1612,6 +1612,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     // on config 2 with b = 20: 5.7 G points/s device-resident instead of 3.6 G, 2 x 128 MB of
     // tables, 2 s of plan time, the kernel then bound by random 128-byte HBM gathers
     int deep_bits = (n * bits0 <= 32) ? 16 : 0;
+    if (const char* e = getenv("TTN_MMA_DEEP")) deep_bits = std::min(atoi(e), 22);
     if (merge && v6_on && deep_bits > 0) {
       const int lb = deep_bits - (CHI >= 32 ? 1 : 0) + (CHI <= 8 ? 1 : 0), rb = lb - (cplx ? 1 : 0);
       kL = std::max(kmerge, std::min(lb / bits0, n / 2));
