@@ -1948,7 +1948,6 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     set_error("DMMA chain kernel: digit tables exceed the kernel's shared-memory copies (160 sites / 640 thresholds)");
     return TTN_ERR_UNSUPPORTED;
   }
-  static const int force_v3 = getenv("TTN_MMA_V3") ? atoi(getenv("TTN_MMA_V3")) : 0; // experiments
   // merged binary chains of width <= 16: team-sorted, B-stationary kernel (v6), 3 teams per CTA
   // (TTN_MMA_V6=0 falls back to the warp-autonomous kernel, =2 runs two teams: experiments)
   static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
@@ -1979,7 +1978,6 @@ int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
       if (f161) return launch_mma5_inst<8, 8, 4, true, 16, 1>(p, src, d_out, d_partial, n_partial, s);
       return launch_mma5_inst<8, 8, 4, false, 0, 0>(p, src, d_out, d_partial, n_partial, s);
     case 16:
-      if (f161 && force_v3) return launch_mma3_inst<16, 1024, 8, 4, true, 16, 1>(p, src, d_out, d_partial, n_partial, s);
       if (f22w) return launch_mma5_inst<16, 8, 4, true, 2, 2>(p, src, d_out, d_partial, n_partial, s);
       if (f41) return launch_mma5_inst<16, 8, 4, true, 4, 1>(p, src, d_out, d_partial, n_partial, s);
       if (f81) return launch_mma5_inst<16, 8, 4, true, 8, 1>(p, src, d_out, d_partial, n_partial, s);
