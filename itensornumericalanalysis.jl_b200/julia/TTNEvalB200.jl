@@ -110,14 +110,32 @@ mutable struct TTNPlan
   end
 end
 
-"Root choice: an end vertex for path graphs (MPS), otherwise a centre of the tree."
+"Root choice: an end vertex for path graphs (MPS); the most central vertex of degree <= 2 for trees of maximum degree 3; otherwise a centre of the tree."
 function choose_root(g, vs)
   length(vs) == 1 && return first(vs)
   if maximum(v -> length(neighbors(g, v)), vs) <= 2
     return last(filter(v -> length(neighbors(g, v)) == 1, vs))
   end
-  remaining = Set(vs)
   deg = Dict(v => length(neighbors(g, v)) for v in vs)
+  if maximum(values(deg)) == 3
+    # rooted at a vertex of degree <= 2 no vertex has more than two children (per-vertex GEMM kernel);
+    # take the most central such vertex
+    function ecc(r)
+      dist = Dict(r => 0)
+      todo = [r]
+      i = 1
+      while i <= length(todo)
+        v = todo[i]; i += 1
+        for u in neighbors(g, v)
+          haskey(dist, u) || (dist[u] = dist[v] + 1; push!(todo, u))
+        end
+      end
+      return maximum(values(dist))
+    end
+    cands = filter(v -> deg[v] <= 2, vs)
+    return cands[argmin([(ecc(v), findfirst(==(v), vs)) for v in cands])]
+  end
+  remaining = Set(vs)
   leaves = filter(v -> deg[v] == 1, vs)
   while length(remaining) > 2
     nxt = eltype(vs)[]

@@ -99,13 +99,28 @@ def _spanning_tree_edges(graph, linkdim):
 
 def _choose_root(verts, adj):
     """Path graphs (MPS): an end vertex, so the contraction is a single vector-matrix chain.
-    Other trees: a centre vertex (minimises the depth of the leaf-to-root schedule)."""
+    Trees of maximum degree 3: the most central vertex of degree <= 2 (then no vertex has more than two
+    children).  Other trees: a centre vertex (minimises the depth of the leaf-to-root schedule)."""
     if len(verts) == 1:
         return verts[0]
     deg = {v: len(adj[v]) for v in verts}
     if max(deg.values()) <= 2:
         ends = [v for v in verts if deg[v] == 1]
         return ends[-1]
+    if max(deg.values()) == 3:
+        # rooted at a vertex of degree <= 2, every vertex of such a tree has at most two children: the
+        # per-vertex GEMM kernel applies (comb trees, binary trees).  Among those take the most central.
+        def ecc(r):
+            dist = {r: 0}
+            todo = [r]
+            for v in todo:
+                for u in adj[v]:
+                    if u not in dist:
+                        dist[u] = dist[v] + 1
+                        todo.append(u)
+            return max(dist.values())
+        cands = [v for v in verts if deg[v] <= 2]
+        return min(cands, key=lambda v: (ecc(v), verts.index(v)))
     # peel leaves
     remaining = set(verts)
     d = dict(deg)
