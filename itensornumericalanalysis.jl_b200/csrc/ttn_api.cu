@@ -197,7 +197,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
-  else if (p->tgemm_ok && max_link >= 12) I.auto_kernel = TTN_KERNEL_TREE;
+  else if (p->tgemm_ok && max_link >= 8) I.auto_kernel = TTN_KERNEL_TREE; // measured cross-over (scripts/tree_small_chi.py)
   else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
