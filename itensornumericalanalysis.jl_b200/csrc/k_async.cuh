@@ -51,6 +51,12 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, double x, double y) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
+// 256-bit read-only global load (sm_100: LDG.E.256): a lane that walks its own row issues half as many
+// loads — and L1 wavefronts — as with 128-bit ones.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -1201,11 +1201,13 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         cw[k] = w0[k];
         const int row = warp * PW + k * 32 + lane;
         if (deep) {
-          const double2* L = reinterpret_cast<const double2*>(ch.leaf + (size_t)(cw[k] & LMASK) * CHI);
+          const double* L = ch.leaf + (size_t)(cw[k] & LMASK) * CHI;
 #pragma unroll
-          for (int j = 0; j < CPR; ++j) {
-            const double2 v = __ldg(L + j);
-            sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+          for (int j = 0; j < CPR; j += 2) {
+            double a0, a1, a2, a3;
+            ldg256(L + 2 * j, a0, a1, a2, a3);
+            sts128(row_chunk<CHI>(state_base, row, j), a0, a1);
+            sts128(row_chunk<CHI>(state_base, row, j + 1), a2, a3);
           }
         } else {
           const int sl = (int)(cw[k] & MASK);
@@ -1332,18 +1334,24 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       const int64_t p = p0 + k * 32 + lane;
       double o0 = 0.0, o1 = 0.0;
       if (deep) {
-        const double2* R0 = reinterpret_cast<const double2*>(ch.root + (size_t)(cw[k] & RMASK) * CHI);
-        const double2* R1 = R0 + ((size_t)1 << ch.root_bits) * CPR;
+        const double* R0 = ch.root + (size_t)(cw[k] & RMASK) * CHI;
+        const double* R1 = R0 + ((size_t)CHI << ch.root_bits);
 #pragma unroll
-        for (int j = 0; j < CPR; ++j) {
+        for (int j = 0; j < CPR; j += 2) {
           const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
-          const double2 q0 = __ldg(R0 + j);
-          o0 = fma(v.x, q0.x, o0);
-          o0 = fma(v.y, q0.y, o0);
+          const double2 w = lds128(row_chunk<CHI>(state_base, row, j + 1));
+          double q0, q1, q2, q3;
+          ldg256(R0 + 2 * j, q0, q1, q2, q3);
+          o0 = fma(v.x, q0, o0);
+          o0 = fma(v.y, q1, o0);
+          o0 = fma(w.x, q2, o0);
+          o0 = fma(w.y, q3, o0);
           if (ch.nout == 2) {
-            const double2 q1 = __ldg(R1 + j);
-            o1 = fma(v.x, q1.x, o1);
-            o1 = fma(v.y, q1.y, o1);
+            ldg256(R1 + 2 * j, q0, q1, q2, q3);
+            o1 = fma(v.x, q0, o1);
+            o1 = fma(v.y, q1, o1);
+            o1 = fma(w.x, q2, o1);
+            o1 = fma(w.y, q3, o1);
           }
         }
       } else {
