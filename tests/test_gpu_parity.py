@@ -487,3 +487,56 @@ def test_tree_subtree_tables(monkeypatch):
                 assert (got == base).all(), (name, bits)
                 assert o.flops_executed <= flops0
         f._plans.clear()
+
+
+@pytest.mark.parametrize("deep", ["0", "8", None])
+def test_team_sorted_kernel_edges(deep, monkeypatch):
+    """Edge cases straight at the team-sorted DMMA kernel (the bench kernel): batches smaller than, equal to
+    and just above a 512-point team tile and a 1536-point CTA; saturating / zero / domain-violating
+    coordinates; the fused functionals; index-setting mode with an out-of-range value; SOA layout."""
+    if deep is not None:
+        monkeypatch.setenv("TTN_MMA_DEEP", deep)
+    s = t.continuous_siteinds(t.named_grid((36, 1)), map_dimension=2)
+    f = t.rand_itn(s, link_space=16, rng=31, normalise=True)
+    f._plans.clear()
+    plan = f.plan()
+    packed = plan.packed
+    rng = np.random.default_rng(17)
+    big = rng.random((4000, 2))
+    big[:7] = [[0.0, 0.0], [1.0, 1.0], [3.5, 7.0], [1 - 2.0 ** -18, 2.0 ** -18], [0.5, np.nextafter(0.5, 0)],
+               [0.1, 0.675], [-0.0, 0.999999999]]
+    ref = orc.evaluate(packed, big, orc.ORACLE_LD)
+    full, o = plan.evaluate_host(big, kernel="dmma")
+    assert o.kernel_used == _capi.TTN_KERNEL_DMMA
+    assert orc.error_metric(full, ref).max() < TOL
+    assert full[1] == full[2]                                    # x >= 1 saturates
+    for n in (1, 7, 8, 9, 511, 512, 513, 1535, 1536, 1537, 3073):
+        got, _ = plan.evaluate_host(big[:n], kernel="dmma")
+        assert (got == full[:n]).all(), n                        # a value never depends on the batch around it
+    got, _ = plan.evaluate_host(np.ascontiguousarray(big.T), layout=_capi.TTN_LAYOUT_SOA, kernel="dmma")
+    assert (got == full).all()
+    # fused functionals
+    w = rng.random(len(big))
+    _, o = plan.evaluate_host(big, kernel="dmma", reduce_sum=True, want_values=False)
+    assert abs(o.sum_out[0] - full.sum()) <= 1e-12 * np.abs(full).sum()
+    _, o = plan.evaluate_host(big, kernel="dmma", reduce_sum=_capi.TTN_REDUCE_ABS2, want_values=False)
+    assert abs(o.sum_out[0] - (full ** 2).sum()) <= 1e-12 * (full ** 2).sum()
+    _, o = plan.evaluate_host(big, kernel="dmma", reduce_sum=_capi.TTN_REDUCE_WEIGHTED, want_values=False, weights=w)
+    assert abs(o.sum_out[0] - (w * full).sum()) <= 1e-12 * np.abs(w * full).sum()
+    # domain errors
+    for bad in (-1e-300, np.nan):
+        pts = big[:600].copy()
+        pts[577, 1] = bad
+        with pytest.raises(_capi.TTNError) as e:
+            plan.evaluate_host(pts, kernel="dmma")
+        assert e.value.code == _capi.TTN_ERR_DOMAIN
+    # index-setting mode == coordinates whose digits are those settings
+    dig = orc.digits(packed, big[:900])
+    got, _ = plan.evaluate_indices_host(dig, kernel="dmma")
+    assert (got == full[:900]).all()
+    dig2 = dig.copy()
+    dig2[333, 5] = 2
+    with pytest.raises(_capi.TTNError) as e:
+        plan.evaluate_indices_host(dig2, kernel="dmma")
+    assert e.value.code == _capi.TTN_ERR_INVALID
+    f._plans.clear()
