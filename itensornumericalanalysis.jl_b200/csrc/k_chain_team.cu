@@ -1,0 +1,466 @@
+// K4, team-sorted kernel — the bench kernel.  Host-side images (group merging, deep tables) and the
+// common scheme are described in k_chain_mma.cu.
+#include <algorithm>
+#include <cstring>
+
+#include "k_chain_common.cuh"
+
+namespace ttn {
+
+// =====================================================================================
+// v6: team-sorted, B-stationary kernel for MERGED binary chains (one stream position per round,
+// NCLS = 4, 8 or 16 slices per position).  A CTA holds NTEAM independent teams of 4 warps; a team
+// owns a tile of 512 points.
+//  * every warp is "home" to 128 points of the tile: K1, leaf rows, class counts, root;
+//  * per round the team counting-sorts its 512 points by class: per-warp match.any counts, one
+//    word of 4 byte counters per class in shared memory, ONE team barrier per round (the counts of
+//    round r+1 are published before the barrier of round r);
+//  * warp w then owns classes w, w+4, ...: the class's site matrix sits in REGISTERS as DMMA B
+//    fragments (read from L2 one class ahead) while the warp streams the class's rows through
+//    gather -> DMMA -> scatter.  No B traffic through shared memory, class padding amortised over
+//    512 points, and the teams drift apart so one team's sort hides under the other's DMMAs.
+template <int CHI, int NBAT>
+__device__ __forceinline__ void batch6(uint32_t state_base, const int (&rows)[4], int tq, int zrow,
+                                       const double (&bf)[(CHI / 4) * (CHI / 8)]) {
+  constexpr int NB = CHI / 8, KB = CHI / 4;
+  double a[NBAT][KB], d[NBAT][KB];
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const double2 v = lds128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq));
+      a[b][2 * nb] = v.x;
+      a[b][2 * nb + 1] = v.y;
+      d[b][2 * nb] = 0.0;
+      d[b][2 * nb + 1] = 0.0;
+    }
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+    for (int nbp = 0; nbp < NB; ++nbp)
+#pragma unroll
+      for (int b = 0; b < NBAT; ++b) dmma884(d[b][2 * nbp], d[b][2 * nbp + 1], a[b][kb], bf[kb * NB + nbp]);
+#pragma unroll
+  for (int b = 0; b < NBAT; ++b)
+    if (rows[b] != zrow) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) sts128(row_chunk<CHI>(state_base, rows[b], 4 * nb + tq), d[b][2 * nb], d[b][2 * nb + 1]);
+    }
+}
+
+template <int CHI, int NCLS, int PW_>
+struct Team6 {
+  static constexpr int TW = 4, PW = PW_, TP = TW * PW;
+  static constexpr int LIST_CAP = TP + 8 * NCLS;
+  static constexpr size_t STATE_BYTES = (size_t)(TP + 8) * CHI * 8;
+  static constexpr size_t BYTES = (STATE_BYTES + 2 * LIST_CAP * 2 + 3 * 2 * NCLS * 4 + 127) / 128 * 128;
+};
+
+template <int CHI, int NCLS, int NTEAM, int PW_>
+__global__ void __launch_bounds__(NTEAM * 128, 1)
+    chain_mma6_kernel(ChainMmaDev ch, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
+                      double* __restrict__ partial, int do_sum) {
+  using T6 = Team6<CHI, NCLS, PW_>;
+  constexpr int TW = T6::TW, PW = T6::PW, PPL = PW / 32, TP = T6::TP;
+  constexpr int GB = (CHI >= 32) ? 2 : 4;   // 8-row groups per batch (register budget)
+  constexpr int CPW = NCLS / TW;           // classes owned by a warp
+  constexpr int BITS = slice_bits(NCLS);
+  constexpr int NB = CHI / 8, KB = CHI / 4, CPR = CHI / 2;
+  constexpr int NBF = KB * NB;             // B-fragment doubles per lane per class
+  constexpr int LIST_CAP = T6::LIST_CAP;
+  constexpr int ZROW = TP;                 // the team's all-zero row (class padding target)
+  constexpr int NT = NTEAM * TW * 32;
+  constexpr int PAR_BIT = (CHI >= 16) ? 2 : 0;  // row bit that selects the bank half of a 64-byte piece
+  constexpr int HS = 2 * NCLS;             // counters per set: (parity, class)
+  static_assert(NCLS % TW == 0 && NCLS <= 32 && (NCLS & (NCLS - 1)) == 0, "class count");
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double red[2][NTEAM * TW];
+  __shared__ Digit2 s_d2[kFeMaxSites];
+  __shared__ int s_cptr[TTN_MAX_COORDS + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int team = tid / (TW * 32), warp = (tid >> 5) % TW;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
+  for (int i = tid; i < dg.n_sites; i += NT) {
+    const DigitEntry e = dg.entries[i];
+    Digit2 d2;
+    d2.thr1 = dg.thr[e.thr_off + 1];
+    d2.sh = (uint32_t)e.shift;
+    d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+    s_d2[i] = d2;
+  }
+  // leaf / root vectors of the CTA in shared memory (after the team regions), 16-byte chunks
+  // XOR-swizzled by the slice number: lanes reading chunk j of different slices spread over banks
+  double* s_leaf = reinterpret_cast<double*>(smem + (size_t)NTEAM * T6::BYTES);  // [NCLS][CHI]
+  double* s_root = s_leaf + NCLS * CHI;                                           // [nout][NCLS][CHI]
+  // deep leaf / root groups (build_chain_mma): tables of 2^leaf_bits / 2^root_bits vectors stay in
+  // global memory and a point gathers one row of each
+  const bool deep = ch.leaf_bits != BITS || ch.root_bits != BITS;
+  for (int i = tid; i < (deep ? 0 : NCLS * CPR); i += NT) {
+    const int sl = i / CPR, j = i % CPR, pj = j ^ (sl & (CPR - 1) & 7);
+    s_leaf[sl * CHI + 2 * pj] = ch.leaf[sl * CHI + 2 * j];
+    s_leaf[sl * CHI + 2 * pj + 1] = ch.leaf[sl * CHI + 2 * j + 1];
+    for (int o = 0; o < ch.nout; ++o) {
+      s_root[(o * NCLS + sl) * CHI + 2 * pj] = ch.root[(o * NCLS + sl) * CHI + 2 * j];
+      s_root[(o * NCLS + sl) * CHI + 2 * pj + 1] = ch.root[(o * NCLS + sl) * CHI + 2 * j + 1];
+    }
+  }
+  unsigned char* tbase = smem + (size_t)team * T6::BYTES;
+  const uint32_t state_base = smem_u32(tbase);
+  uint16_t* lists = reinterpret_cast<uint16_t*>(tbase + T6::STATE_BYTES);     // [2][LIST_CAP]
+  const uint32_t s_leaf_u32 = smem_u32(s_leaf), s_root_u32 = smem_u32(s_root);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(lists + 2 * LIST_CAP);          // [3][2][16] (class, parity) counters
+  for (int i = tid % (TW * 32); i < 3 * HS; i += TW * 32) hist[i] = 0u;
+  for (int i = tid % (TW * 32); i < 8 * CHI; i += TW * 32)
+    reinterpret_cast<double*>(tbase + (size_t)TP * CHI * 8)[i] = 0.0;
+  __syncthreads();
+
+  const int bar_id = 1 + team;
+  const int64_t n_tiles = (src.npts + TP - 1) / TP;
+  const int64_t tstride = (int64_t)gridDim.x * NTEAM;
+  const int R = ch.n_rounds;
+  const uint64_t MASK = (uint64_t)(NCLS - 1);
+  const uint64_t LMASK = (1ull << ch.leaf_bits) - 1ull, RMASK = (1ull << ch.root_bits) - 1ull;
+  const uint32_t lt = (1u << lane) - 1u;
+  double sum_re = 0.0, sum_im = 0.0;
+  int qh = 0; // global round counter of the team (rotates the counter sets)
+
+  // B fragments of class c of round r (fragment order, see build_chain_mma): 32 consecutive doubles per (kb, nb)
+  double bcur[NBF], bnxt[NBF];
+  auto load_b = [&](double (&b)[NBF], int r, int c) {
+    const double* F = ch.frags + ((size_t)r * NCLS + c) * (CHI * CHI) + lane;
+#pragma unroll
+    for (int i = 0; i < NBF; ++i) b[i] = __ldg(F + i * 32);
+  };
+  if (R > 0) load_b(bcur, 0, warp);
+
+  // ---- K1: packed slice streams of the lane's PPL home points of one tile (interleaved for ILP)
+  auto compute_words = [&](int64_t tile_, uint64_t (&w0)[PPL], uint64_t (&w1)[PPL]) {
+    const int64_t p0 = tile_ * TP + warp * PW;
+    double x[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
+    for (int c = 0; c < dg.n_coords; ++c) {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int64_t p = p0 + k * 32 + lane;
+        x[k] = 0.0;
+        if (p < src.npts) {
+          x[k] = load_coord(src, p, c);
+          if (!coord_in_domain(x[k])) {
+            atomicOr(err, 1);
+            x[k] = 0.0;
+          }
+        }
+      }
+      if (ch.run_L[c] > 0 && !src.digits) {
+        const int L = ch.run_L[c], plow = ch.run_plow[c];
+        const double scale = ch.run_scale[c];
+        const bool rev = ch.run_rev[c] != 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+          if (rev) q = __brevll(q) >> (64 - L);
+          if (plow < 64) {
+            w0[k] += q << plow;
+            if (plow + L > 64) w1[k] += q >> (64 - plow);
+          } else {
+            w1[k] += q << (plow - 64);
+          }
+        }
+      } else {
+        for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+          const Digit2 e = s_d2[e_i];
+          const uint32_t stride = e.wv & 0xffu;
+          const bool hi = ((e.wv >> 8) & 0xffu) != 0;
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {
+            const bool ge = src.digits ? (given_digit(src, p0 + k * 32 + lane, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                       : (x[k] >= e.thr1);
+            x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
+            const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+            if (hi) w1[k] += bb;
+            else w0[k] += bb;
+          }
+        }
+      }
+    }
+  };
+
+  for (int64_t tile = (int64_t)blockIdx.x * NTEAM + team; tile < n_tiles; tile += tstride) {
+    const int64_t p0 = tile * TP + warp * PW; // first home point of this warp
+    uint64_t w1[PPL], cw[PPL];
+    {
+      uint64_t w0[PPL];
+      compute_words(tile, w0, w1);
+      // ---- leaf rows
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = w0[k];
+        const int row = warp * PW + k * 32 + lane;
+        if (deep) {
+          const double* L = ch.leaf + (size_t)(cw[k] & LMASK) * CHI;
+#pragma unroll
+          for (int j = 0; j < CPR; j += 2) {
+            double a0, a1, a2, a3;
+            ldg256(L + 2 * j, a0, a1, a2, a3);
+            sts128(row_chunk<CHI>(state_base, row, j), a0, a1);
+            sts128(row_chunk<CHI>(state_base, row, j + 1), a2, a3);
+          }
+        } else {
+          const int sl = (int)(cw[k] & MASK);
+          const uint32_t L = s_leaf_u32 + (uint32_t)sl * (CHI * 8);
+#pragma unroll
+          for (int j = 0; j < CPR; ++j) {
+            const double2 v = lds128(L + (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4));
+            sts128(row_chunk<CHI>(state_base, row, j), v.x, v.y);
+          }
+        }
+      }
+    }
+    auto shift_stream = [&]() {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = (cw[k] >> BITS) | (w1[k] << (64 - BITS));
+        w1[k] >>= BITS;
+      }
+    };
+    {
+      const int lb = ch.leaf_bits; // 1..21
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        cw[k] = (cw[k] >> lb) | (w1[k] << (64 - lb));
+        w1[k] >>= lb;
+      }
+    }
+
+    // classes of the next stream position: one shared-memory atomic per point on the team's
+    // (class, parity) counters gives the point its position among the team's points of that class
+    // and parity; info[k] = class | position << 8.  `parity` is the row bit that decides which half
+    // of the bank line a 64-byte piece of the row occupies (row_chunk swizzle): it is a lane
+    // constant for home rows.  Counter sets rotate over 3 buffers (qh = global round counter).
+    uint32_t info[PPL];
+    const int par = (lane >> PAR_BIT) & 1;
+    auto count_round = [&](int hb) {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int cls = (int)(cw[k] & MASK);
+        const uint32_t pos = atomicAdd(hist + hb * HS + par * NCLS + cls, 1u);
+        info[k] = (uint32_t)cls | (pos << 8);
+      }
+      shift_stream();
+    };
+    if (R > 0) count_round(qh % 3);
+    named_bar_sync(bar_id, TW * 32); // leaf rows + counts of round 0
+
+    for (int r = 0; r < R; ++r, ++qh) {
+      const int buf = r & 1, hb = qh % 3;
+      uint16_t* list = lists + buf * LIST_CAP;
+      // ---- list of round r.  Lane c holds class c's counts.  Inside a class the rows of opposite
+      // parity are zipped into (even, odd) slot pairs — the two rows a quarter-warp gathers at once
+      // then never collide — and the surplus of the larger parity follows.
+      const int n0 = (lane < NCLS) ? (int)hist[hb * HS + lane] : 0;
+      const int n1 = (lane < NCLS) ? (int)hist[hb * HS + NCLS + lane] : 0;
+      const int total = n0 + n1, mzip = min(n0, n1);
+      const int padded = (total + 7) & ~7;
+      int incl = padded;
+#pragma unroll
+      for (int o = 1; o < NCLS; o <<= 1) {
+        const int nn = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nn;
+      }
+      const int mystart = incl - padded;
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int c = (int)(info[k] & 255u), pos = (int)(info[k] >> 8);
+        const int st = __shfl_sync(0xffffffffu, mystart, c), mm = __shfl_sync(0xffffffffu, mzip, c);
+        list[st + (pos < mm ? 2 * pos + par : mm + pos)] = (uint16_t)(warp * PW + k * 32 + lane);
+      }
+      for (int c0 = 4 * warp; c0 < NCLS; c0 += 4 * TW) { // class padding -> zero row
+        const int pc = c0 + (lane >> 3), pi = lane & 7;
+        const int cn = __shfl_sync(0xffffffffu, total, pc & 31), cs = __shfl_sync(0xffffffffu, mystart, pc & 31);
+        if (pc < NCLS && (cn & 7) && pi >= (cn & 7)) list[cs + (cn & ~7) + pi] = (uint16_t)ZROW;
+      }
+      if (r + 1 < R) count_round((qh + 1) % 3);
+      if (warp == 0)
+        for (int i = lane; i < HS; i += 32) hist[((qh + 2) % 3) * HS + i] = 0u; // last read before the previous barrier
+      named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 final
+
+      // ---- owned classes: B in registers, rows streamed through gather -> DMMA -> scatter
+#pragma unroll
+      for (int j = 0; j < CPW; ++j) {
+        const int c = warp + j * TW;
+        {
+          // prefetch the next class in the flattened (round, class) sequence; the sequence of the
+          // next tile starts again at (0, warp)
+          const int rn = (j + 1 < CPW) ? r : ((r + 1 < R) ? r + 1 : 0);
+          const int cn_ = (j + 1 < CPW) ? c + TW : warp;
+          load_b(bnxt, rn, cn_);
+        }
+        const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
+        const int ng = (n_c + 7) >> 3;
+        const uint16_t* Lc = list + st;
+        int rows_nx[4] = {0, 0, 0, 0};
+        if (ng > 0) {
+#pragma unroll
+          for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(b, ng - 1) << 3) + g];
+        }
+        for (int gi = 0; gi < ng; gi += GB) {
+          const int nbat = min(GB, ng - gi);
+          int rows[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int b = 0; b < GB; ++b) rows[b] = rows_nx[b];
+          if (gi + GB < ng) {
+#pragma unroll
+            for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(gi + GB + b, ng - 1) << 3) + g];
+          }
+          if (GB >= 4 && nbat == 4) batch6<CHI, (GB >= 4 ? 4 : 1)>(state_base, rows, tq, ZROW, bcur);
+          else if (GB >= 4 && nbat == 3) batch6<CHI, (GB >= 4 ? 3 : 1)>(state_base, rows, tq, ZROW, bcur);
+          else if (nbat == 2) batch6<CHI, 2>(state_base, rows, tq, ZROW, bcur);
+          else batch6<CHI, 1>(state_base, rows, tq, ZROW, bcur);
+        }
+#pragma unroll
+        for (int i = 0; i < NBF; ++i) bcur[i] = bnxt[i];
+      }
+    }
+    if (R > 0) named_bar_sync(bar_id, TW * 32); // rows of the last round complete
+
+    // ---- root: out = row . R[d_{n-1}] for the home rows
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+      const int row = warp * PW + k * 32 + lane;
+      const int64_t p = p0 + k * 32 + lane;
+      double o0 = 0.0, o1 = 0.0;
+      if (deep) {
+        const double* R0 = ch.root + (size_t)(cw[k] & RMASK) * CHI;
+        const double* R1 = R0 + ((size_t)CHI << ch.root_bits);
+#pragma unroll
+        for (int j = 0; j < CPR; j += 2) {
+          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+          const double2 w = lds128(row_chunk<CHI>(state_base, row, j + 1));
+          double q0, q1, q2, q3;
+          ldg256(R0 + 2 * j, q0, q1, q2, q3);
+          o0 = fma(v.x, q0, o0);
+          o0 = fma(v.y, q1, o0);
+          o0 = fma(w.x, q2, o0);
+          o0 = fma(w.y, q3, o0);
+          if (ch.nout == 2) {
+            ldg256(R1 + 2 * j, q0, q1, q2, q3);
+            o1 = fma(v.x, q0, o1);
+            o1 = fma(v.y, q1, o1);
+            o1 = fma(w.x, q2, o1);
+            o1 = fma(w.y, q3, o1);
+          }
+        }
+      } else {
+        const int sl = (int)(cw[k] & MASK);
+        const uint32_t R0 = s_root_u32 + (uint32_t)sl * (CHI * 8), R1 = R0 + (uint32_t)(NCLS * CHI * 8);
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
+          const uint32_t off = (uint32_t)((j ^ (sl & (CPR - 1) & 7)) << 4);
+          const double2 q0 = lds128(R0 + off);
+          o0 = fma(v.x, q0.x, o0);
+          o0 = fma(v.y, q0.y, o0);
+          if (ch.nout == 2) {
+            const double2 q1 = lds128(R1 + off);
+            o1 = fma(v.x, q1.x, o1);
+            o1 = fma(v.y, q1.y, o1);
+          }
+        }
+      }
+      if (p < src.npts) {
+        if (out) {
+          if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+          else out[p] = o0;
+        }
+        accumulate_point(src, p, o0, o1, sum_re, sum_im);
+      }
+    }
+    // the next tile's leaf rows overwrite home rows only: no barrier needed here, the first barrier
+    // of the next tile orders them before any other warp's gather
+  }
+
+  if (do_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
+      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
+    }
+    if (lane == 0) {
+      red[0][tid >> 5] = sum_re;
+      red[1][tid >> 5] = sum_im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double xx = 0.0, yy = 0.0;
+      for (int w = 0; w < NTEAM * TW; ++w) {
+        xx += red[0][w];
+        yy += red[1][w];
+      }
+      partial[2 * blockIdx.x] = xx;
+      partial[2 * blockIdx.x + 1] = yy;
+    }
+  }
+}
+template <int CHI, int NCLS, int NTEAM, int PW_>
+static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                            cudaStream_t s) {
+  using T6 = Team6<CHI, NCLS, PW_>;
+  const ChainMmaDev& c = p->cmma;
+  const size_t smem = (size_t)NTEAM * T6::BYTES + (size_t)3 * NCLS * CHI * 8; // teams + leaf + root (re, im)
+  auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM, PW_>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (src.npts + T6::TP - 1) / T6::TP;
+  const int grid = (int)std::min<int64_t>((n_tiles + NTEAM - 1) / NTEAM, p->sm_count);
+  const int do_sum = d_partial != nullptr;
+  kern<<<grid, NTEAM * 128, smem, s>>>(c, p->digits_mma, src, d_out, p->d_err, d_partial, do_sum);
+  TTN_CUDA(cudaGetLastError());
+  *n_partial = do_sum ? grid : 0;
+  return TTN_OK;
+}
+
+// Applies to merged binary chains (build_chain_mma) of width 8, 16 or 32.  TTN_MMA_V6=0 switches the
+// kernel off (the ring kernels then run the merged image), =2 runs two teams per CTA (experiments).
+static int team_count() {
+  static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
+  return v6;
+}
+
+bool chain_team_applicable(const ttn_plan* p) {
+  const ChainMmaDev& c = p->cmma;
+  if (!team_count() || !c.merged || !p->all_base2 || c.spr != 1) return false;
+  if (c.chi == 8 || c.chi == 16) return c.nsl == 4 || c.nsl == 8 || c.nsl == 16 || c.nsl == 32;
+  return c.chi == 32 && (c.nsl == 4 || c.nsl == 8 || c.nsl == 16);
+}
+
+int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                      cudaStream_t s) {
+  const ChainMmaDev& c = p->cmma;
+  const int v6 = team_count();
+  if (v6 && c.merged && p->all_base2 && c.spr == 1) {
+#define TTN_V6_CASE(W, N)                                                                                   \
+  if (c.chi == W && c.nsl == N)                                                                             \
+    return v6 == 2 ? launch_mma6_inst<W, N, 2, 128>(p, src, d_out, d_partial, n_partial, s)                 \
+                   : launch_mma6_inst<W, N, 3, 128>(p, src, d_out, d_partial, n_partial, s);
+    TTN_V6_CASE(16, 4)
+    TTN_V6_CASE(16, 8)
+    TTN_V6_CASE(16, 16)
+    TTN_V6_CASE(16, 32)
+    TTN_V6_CASE(8, 4)
+    TTN_V6_CASE(8, 8)
+    TTN_V6_CASE(8, 16)
+    TTN_V6_CASE(8, 32)
+#undef TTN_V6_CASE
+    // width 32: rows are 256 bytes and a class's B fragments take 64 registers -> 2 teams of 384 points
+    if (c.chi == 32 && c.nsl == 4) return launch_mma6_inst<32, 4, 2, 96>(p, src, d_out, d_partial, n_partial, s);
+    if (c.chi == 32 && c.nsl == 8) return launch_mma6_inst<32, 8, 2, 96>(p, src, d_out, d_partial, n_partial, s);
+    if (c.chi == 32 && c.nsl == 16) return launch_mma6_inst<32, 16, 2, 96>(p, src, d_out, d_partial, n_partial, s);
+  }
+  set_error("team-sorted DMMA kernel: unsupported width / slice count");
+  return TTN_ERR_UNSUPPORTED;
+}
+
+} // namespace ttn

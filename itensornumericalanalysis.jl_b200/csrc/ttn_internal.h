@@ -217,6 +217,13 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
                       int* n_partial, cudaStream_t s, int* n_launches);
 int launch_chain_mma(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out,
                      double* d_partial, int* n_partial, cudaStream_t s);
+// DMMA chain kernels behind launch_chain_mma: the team-sorted kernel (k_chain_team.cu) for merged binary
+// chains, the ring kernels (k_chain_ring.cu) for everything else
+bool chain_team_applicable(const ttn_plan* p);
+int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                      cudaStream_t s);
+int launch_chain_ring(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                      cudaStream_t s);
 bool chain_supported(int chi, int nsl, bool cplx);
 int measure_fp64_peak(int device, double* dfma, double* dmma);
 } // namespace ttn
