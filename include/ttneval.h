@@ -158,8 +158,9 @@ typedef struct ttn_opts {
   int32_t weights_mem;   /* TTN_MEM_* */
   int32_t reserved_;
   /* output */
-  double flops_executed; /* FP64 flops the kernels of this call executed (= flops_per_point * npts, except for
-                            TTN_KERNEL_GRID, whose prefix sharing executes far fewer) */
+  double flops_executed; /* FP64 flops the kernels of this call executed.  <= flops_per_point * npts (the
+                            SURVEY 8(d) rule): plan-time contraction (merged chain positions, leaf/root and
+                            subtree tables) and the grid kernel's prefix sharing remove work */
 } ttn_opts;
 
 /* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:
