@@ -83,18 +83,36 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// S[p] = L[idx(p)], idx = sum_q slices[q][p] * nsl^q over the first `npos` stream positions (npos = 1:
+// the plain leaf vectors; npos > 1: the leaf table of build_gemm_tables)
 __global__ void gemm_leaf_kernel(const uint8_t* __restrict__ slices, int pc, const double* __restrict__ leaf, int W,
-                                 double* __restrict__ S) {
+                                 double* __restrict__ S, int npos, int nsl) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // one double2 per thread
   const int per_row = W / 2;
   if (idx >= (int64_t)pc * per_row) return;
   const int i = (int)(idx / per_row), j = (int)(idx % per_row);
-  const double2 v = *reinterpret_cast<const double2*>(leaf + (size_t)slices[i] * W + 2 * j);
+  uint32_t t = 0;
+  for (int q = npos - 1; q >= 0; --q) t = t * (uint32_t)nsl + slices[(size_t)q * pc + i];
+  const double2 v = *reinterpret_cast<const double2*>(leaf + (size_t)t * W + 2 * j);
   reinterpret_cast<double2*>(S)[idx] = v;
 }
 
-__global__ void gemm_root_kernel(const uint8_t* __restrict__ slices_root, int pc, int64_t p0, int64_t npts,
-                                 const double* __restrict__ root, int W, int nsl, int nout, int n_vertices,
+// enumerated digit settings for the table builds: slices[q][i] = (i / nsl^q) % nsl
+__global__ void gemm_enum_kernel(uint8_t* __restrict__ slices, int pc, int npos, int nsl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pc) return;
+  uint32_t r = (uint32_t)i;
+  for (int q = 0; q < npos; ++q) {
+    slices[(size_t)q * pc + i] = (uint8_t)(r % (uint32_t)nsl);
+    r /= (uint32_t)nsl;
+  }
+}
+
+// out[p] = S[p] . R[idx(p)], idx = sum_q slices[last - q][p] * nsl^q over the last `npos` stream positions
+// (the root position is the lowest digit); `rows` = number of rows of one output's table
+__global__ void gemm_root_kernel(const uint8_t* __restrict__ slices_last, int pc, int64_t p0, int64_t npts,
+                                 const double* __restrict__ root, int W, int nsl, int npos, int64_t rows, int nout,
+                                 int n_vertices,
                                  const double* __restrict__ S, double* __restrict__ out, double* __restrict__ partial,
                                  int do_sum, CoordSource src) {
   // one warp per point
@@ -105,8 +123,10 @@ __global__ void gemm_root_kernel(const uint8_t* __restrict__ slices_root, int pc
     live = true;
     const double* row = S + (size_t)warp * W;
     if (n_vertices > 1) {
-      const double* R0 = root + (size_t)slices_root[warp] * W;
-      const double* R1 = R0 + (size_t)nsl * W;
+      uint32_t t = 0;
+      for (int q = npos - 1; q >= 0; --q) t = t * (uint32_t)nsl + slices_last[warp - (int64_t)q * pc];
+      const double* R0 = root + (size_t)t * W;
+      const double* R1 = R0 + (size_t)rows * W;
       for (int j = lane; j < W; j += 32) {
         o0 = fma(row[j], __ldg(R0 + j), o0);
         if (nout == 2) o1 = fma(row[j], __ldg(R1 + j), o1);
@@ -263,6 +283,8 @@ static int gemm_width(int w) {
   return 0;
 }
 
+static int build_gemm_tables(ttn_plan* p, int tabL, int tabR, const double* d_frags_rev);
+
 int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
   p->cgemm_ok = false;
   if (!p->is_chain) return TTN_OK;
@@ -374,15 +396,37 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
   const int NSLm = merge ? NSL * NSL : NSL;
   const int n_steps = merge ? (n_pad - 4) / 2 : n_steps0;
   const size_t per_site = (size_t)NSLm * M;
+  // leaf / root tables (build_gemm_tables below): how many middle positions each side absorbs.  A table has
+  // NSLm^(1 + tab) rows of W doubles; budget 2^TTN_GEMM_TABLE_BITS rows (default 16, 0 = no tables).
+  int tabL = 0, tabR = 0;
+  {
+    int tb = 16;
+    if (const char* e = getenv("TTN_GEMM_TABLE_BITS")) tb = std::min(atoi(e), 20);
+    int mmax = 0;
+    for (double rows = NSLm; tb > 0 && rows * NSLm <= std::ldexp(1.0, tb) && rows * NSLm * W * 8 <= 160e6; rows *= NSLm) ++mmax;
+    tabL = std::min(mmax, n_steps / 2);
+    tabR = std::min(mmax, n_steps - tabL);
+    if (NSLm < 2) tabL = tabR = 0;
+  }
+  auto transpose = [&](const double* A, double* At) {
+    for (int i = 0; i < W; ++i)
+      for (int j = 0; j < W; ++j) At[(size_t)j * W + i] = A[(size_t)i * W + j];
+  };
+  double* d_frags_rev = nullptr;
+  if (tabR > 0) {
+    TTN_CUDA(cudaMalloc(&d_frags_rev, per_site * tabR * 8));
+    p->allocs.push_back(d_frags_rev);
+  }
   double* d_frags;
   TTN_CUDA(cudaMalloc(&d_frags, std::max<size_t>(per_site * n_steps, 1) * 8));
   p->allocs.push_back(d_frags);
   double flops_exec = 0.0;
+  std::vector<double> step_flops; // per (merged) middle position
   const double fmul = cplx ? 8.0 : 2.0;
   auto dim_in = [&](int tI) { return tI < n - 2 ? d->link_dim[order[tI]] : d->link_dim[order[n - 2]]; };
   auto dim_out = [&](int tI) { return tI < n - 2 ? d->link_dim[order[tI + 1]] : d->link_dim[order[n - 2]]; };
   {
-    std::vector<double> F(per_site), Ea(M), Eb(M), Ec(M);
+    std::vector<double> F(per_site), Frev(tabR > 0 ? per_site : 1), Ea(M), Eb(M), Ec(M);
     if (!merge) {
       for (int tI = 0; tI < n_steps; ++tI) {
         std::fill(F.begin(), F.end(), 0.0);
@@ -391,7 +435,16 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
           to_frags(Ea.data(), F.data() + (size_t)s * M);
         }
         flops_exec += fmul * dim_in(tI) * dim_out(tI);
+        step_flops.push_back(fmul * dim_in(tI) * dim_out(tI));
         TTN_CUDA(cudaMemcpy(d_frags + per_site * tI, F.data(), per_site * 8, cudaMemcpyHostToDevice));
+        if (tI >= n_steps - tabR) { // transposed image for the right-to-left table build
+          for (int sl = 0; sl < NSL; ++sl) {
+            site_matrix(tI, sl, Ea.data());
+            transpose(Ea.data(), Eb.data());
+            to_frags(Eb.data(), F.data() + (size_t)sl * M);
+          }
+          TTN_CUDA(cudaMemcpy(d_frags_rev + per_site * (n_steps - 1 - tI), F.data(), per_site * 8, cudaMemcpyHostToDevice));
+        }
       }
     } else {
       // leaf' [s0 + NSL s1] = leaf[s0] E_0[s1];  root' [s0 + NSL s1] = E_last[s0] root[s1]
@@ -425,10 +478,17 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
             site_matrix(ta, s0, Ea.data());
             matmul(Ea.data(), Eb.data(), Ec.data());
             to_frags(Ec.data(), F.data() + (size_t)(s0 + NSL * s1) * M);
+            if (m >= n_steps - tabR) {
+              transpose(Ec.data(), Ea.data());
+              to_frags(Ea.data(), Frev.data() + (size_t)(s0 + NSL * s1) * M);
+            }
           }
         }
         flops_exec += fmul * dim_in(ta) * dim_out(tb);
+        step_flops.push_back(fmul * dim_in(ta) * dim_out(tb));
         TTN_CUDA(cudaMemcpy(d_frags + per_site * m, F.data(), per_site * 8, cudaMemcpyHostToDevice));
+        if (m >= n_steps - tabR)
+          TTN_CUDA(cudaMemcpy(d_frags_rev + per_site * (n_steps - 1 - m), Frev.data(), per_site * 8, cudaMemcpyHostToDevice));
       }
     }
   }
@@ -461,7 +521,16 @@ int build_chain_gemm(ttn_plan* p, const ttn_desc* d) {
   c.root = d_root;
   c.frags = d_frags;
   c.pos_of_vertex = d_pos;
+  c.tab_L = c.tab_R = 0;
+  c.leaf_tab = c.root_tab = nullptr;
   p->cgemm_ok = true;
+  if (tabL + tabR > 0) {
+    int rc = build_gemm_tables(p, tabL, tabR, d_frags_rev);
+    if (rc) return rc;
+    double fe = fmul * (merge ? dim_in(n_steps0 - 1) : d->link_dim[order[n - 2]]);
+    for (int tI = tabL; tI < n_steps - tabR; ++tI) fe += step_flops[tI];
+    p->cgemm_flops_exec = fe;
+  }
   return TTN_OK;
 }
 
@@ -474,6 +543,73 @@ static int launch_site(const double* Sin, double* Sout, const uint32_t* list, co
   const int grid = (pc / GBM + nsl) * (W / GBN); // upper bound on the number of tiles
   kern<<<grid, 256, smem, s>>>(Sin, Sout, list, cls_off, tile_off, frags, nsl);
   TTN_CUDA(cudaGetLastError());
+  return TTN_OK;
+}
+
+// Leaf / root tables of the GEMM-regime chain kernel.  The state after the first 1 + tabL positions depends
+// only on their slices: all nsl^(1+tabL) states are computed here, once, by running the ordinary per-site
+// kernels over the enumerated slice settings; likewise the co-vectors of the last 1 + tabR positions, by
+// running the transposed sites right to left from the root vectors.  An evaluation then gathers one row of
+// each table per point and runs only the middle sites as GEMMs.
+static int build_gemm_tables(ttn_plan* p, int tabL, int tabR, const double* d_frags_rev) {
+  ChainGemmDev& c = p->cgemm;
+  const int W = c.W, NS = c.nsl;
+  auto ipow = [&](int e) {
+    int64_t r = 1;
+    for (int q = 0; q < e; ++q) r *= NS;
+    return r;
+  };
+  const int64_t rowsL = ipow(1 + tabL), rowsR = ipow(1 + tabR);
+  const int PC = (int)((std::max(rowsL, rowsR) + GBM - 1) / GBM * GBM);
+  const int mmax = std::max(tabL, tabR);
+  double *S0 = nullptr, *S1 = nullptr, *d_ltab = nullptr, *d_rtab = nullptr;
+  uint8_t* slices = nullptr;
+  uint32_t* lists = nullptr;
+  int* offs = nullptr;
+  TTN_CUDA(cudaMalloc(&S0, (size_t)PC * W * 8));
+  TTN_CUDA(cudaMalloc(&S1, (size_t)PC * W * 8));
+  TTN_CUDA(cudaMalloc(&slices, (size_t)(mmax + 1) * PC));
+  TTN_CUDA(cudaMalloc(&lists, (size_t)std::max(mmax, 1) * PC * 4));
+  TTN_CUDA(cudaMalloc(&offs, ((size_t)std::max(mmax, 1) * kGemmOff * 2 + 16) * 4));
+  int* cls_off = offs;
+  int* tile_off = offs + (size_t)std::max(mmax, 1) * kGemmOff + 8;
+  TTN_CUDA(cudaMalloc(&d_ltab, (size_t)rowsL * W * 8));
+  p->allocs.push_back(d_ltab);
+  TTN_CUDA(cudaMalloc(&d_rtab, (size_t)c.nout * rowsR * W * 8));
+  p->allocs.push_back(d_rtab);
+  int rc = TTN_OK;
+  auto run = [&](const double* leaf, const double* frags, int m, double* dst, int64_t rows) {
+    // positions 0..m of the enumerated settings: leaf vectors, then m sites
+    gemm_enum_kernel<<<(PC + 255) / 256, 256>>>(slices, PC, m + 1, NS);
+    if (m > 0) gemm_classify_kernel<<<m, 1024>>>(slices, PC, NS, lists, cls_off, tile_off, W / GBN);
+    gemm_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256>>>(slices, PC, leaf, W, S0, 1, NS);
+    double *Sin = S0, *Sout = S1;
+    for (int t = 0; t < m && rc == TTN_OK; ++t) {
+      const double* fr = frags + (size_t)t * NS * W * W;
+      if (W == 128) rc = launch_site<128>(Sin, Sout, lists + (size_t)t * PC, cls_off + t * kGemmOff, tile_off + t * kGemmOff, fr, NS, PC, 0);
+      else rc = launch_site<256>(Sin, Sout, lists + (size_t)t * PC, cls_off + t * kGemmOff, tile_off + t * kGemmOff, fr, NS, PC, 0);
+      std::swap(Sin, Sout);
+    }
+    if (rc == TTN_OK && cudaMemcpy(dst, Sin, (size_t)rows * W * 8, cudaMemcpyDeviceToDevice) != cudaSuccess) rc = TTN_ERR_CUDA;
+  };
+  run(c.leaf, c.frags, tabL, d_ltab, rowsL);
+  for (int o = 0; o < c.nout && rc == TTN_OK; ++o)
+    run(c.root + (size_t)o * NS * W, d_frags_rev, tabR, d_rtab + (size_t)o * rowsR * W, rowsR);
+  if (rc == TTN_OK && cudaDeviceSynchronize() != cudaSuccess) rc = TTN_ERR_CUDA;
+  cudaFree(S0);
+  cudaFree(S1);
+  cudaFree(slices);
+  cudaFree(lists);
+  cudaFree(offs);
+  if (rc == TTN_ERR_CUDA) {
+    set_error(std::string("GEMM chain tables: ") + cudaGetErrorString(cudaGetLastError()));
+    return rc;
+  }
+  if (rc) return rc;
+  c.tab_L = tabL;
+  c.tab_R = tabR;
+  c.leaf_tab = d_ltab;
+  c.root_tab = d_rtab;
   return TTN_OK;
 }
 
@@ -532,10 +668,11 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
     gemm_digits_kernel<<<(pc + 255) / 256, 256, 0, s>>>(p->digits, src, p0, pc, c.pos_of_vertex, n_pos, slices, p->d_err);
     if (c.n_steps > 0)
       gemm_classify_kernel<<<c.n_steps, 1024, 0, s>>>(slices, pc, c.nsl, lists, cls_off, tile_off, W / GBN);
-    gemm_leaf_kernel<<<(unsigned)(((int64_t)pc * (W / 2) + 255) / 256), 256, 0, s>>>(slices, pc, c.leaf, W, S0);
+    gemm_leaf_kernel<<<(unsigned)(((int64_t)pc * (W / 2) + 255) / 256), 256, 0, s>>>(slices, pc, c.leaf_tab ? c.leaf_tab : c.leaf, W, S0,
+                                                                                     1 + c.tab_L, c.nsl);
     *n_launches += 3;
     double *Sin = S0, *Sout = S1;
-    for (int t = 0; t < c.n_steps; ++t) {
+    for (int t = c.tab_L; t < c.n_steps - c.tab_R; ++t) {
       const double* fr = c.frags + (size_t)t * c.nsl * W * W;
       int rc;
       if (W == 128) rc = launch_site<128>(Sin, Sout, lists + (size_t)t * pc, cls_off + t * kGemmOff, tile_off + t * kGemmOff, fr, c.nsl, pc, s);
@@ -544,8 +681,11 @@ int launch_chain_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d
       std::swap(Sin, Sout);
       *n_launches += 1;
     }
-    gemm_root_kernel<<<root_blocks, 256, 0, s>>>(slices + (size_t)(n_pos - 1) * pc, pc, p0, src.npts, c.root, W, c.nsl,
-                                                 c.nout, c.n_vertices, Sin, d_out, do_sum ? big_partial + 2 * ck * root_blocks : nullptr,
+    int64_t root_rows = c.nsl;
+    for (int q = 0; q < c.tab_R; ++q) root_rows *= c.nsl;
+    gemm_root_kernel<<<root_blocks, 256, 0, s>>>(slices + (size_t)(n_pos - 1) * pc, pc, p0, src.npts,
+                                                 c.root_tab ? c.root_tab : c.root, W, c.nsl, 1 + c.tab_R, root_rows, c.nout,
+                                                 c.n_vertices, Sin, d_out, do_sum ? big_partial + 2 * ck * root_blocks : nullptr,
                                                  do_sum, src);
     *n_launches += 1;
     TTN_CUDA(cudaGetLastError());

@@ -120,6 +120,11 @@ struct ChainGemmDev {
   const double* root;            // [nout][nsl][W]
   const double* frags;           // [n_steps][nsl][W*W], B-fragment order
   const int32_t* pos_of_vertex;  // stream position of every vertex | (bit shift inside the position) << 16
+  // leaf / root tables (build_gemm_tables): the first 1 + tab_L and the last 1 + tab_R positions are
+  // tabulated (nsl^(1+tab) rows each); only the middle steps [tab_L, n_steps - tab_R) run as GEMMs
+  int32_t tab_L, tab_R;
+  const double* leaf_tab;        // [nsl^(1+tab_L)][W] or null
+  const double* root_tab;        // [nout][nsl^(1+tab_R)][W] or null
 };
 
 // trees with <= 2 children per vertex as per-vertex (Khatri-Rao) GEMMs (k_tree_gemm.cu)

@@ -410,6 +410,7 @@ def test_merged_chain_images(kmax, deep, monkeypatch):
     monkeypatch.setenv("TTN_MMA_MERGE", kmax)
     if deep is not None:   # budget (log2 rows) of the deep leaf / root tables; None = the default rule
         monkeypatch.setenv("TTN_MMA_DEEP", deep)
+        monkeypatch.setenv("TTN_GEMM_TABLE_BITS", deep)   # same idea in the GEMM-regime chain kernel
     rng = np.random.default_rng(int(kmax))
     nets = []
     for L in range(2, 15):
@@ -426,11 +427,12 @@ def test_merged_chain_images(kmax, deep, monkeypatch):
     sc = t.complex_continuous_siteinds(t.named_grid((8, 1)), map_dimension=2)
     nets.append(("cplx_map8_2d", t.rand_itn(sc, link_space=4, rng=6, eltype=complex, normalise=True)))
     # GEMM-regime chains (width > 32): pair merging in build_chain_gemm, odd lengths get an identity vertex
-    for L in (4, 5, 7):
+    for L in (4, 5, 7, 12):
         s = t.continuous_siteinds(t.named_grid((L, 1)), map_dimension=1)
         nets.append((f"gemm_mps{L}_chi40", t.rand_itn(s, link_space=40, rng=10 + L, normalise=True)))
-    sc = t.complex_continuous_siteinds(t.named_grid((5, 1)))
-    nets.append(("gemm_cplx_map5_chi20", t.rand_itn(sc, link_space=20, rng=16, eltype=complex, normalise=True)))
+    for L in (5, 9):
+        sc = t.complex_continuous_siteinds(t.named_grid((L, 1)))
+        nets.append((f"gemm_cplx_map{L}_chi20", t.rand_itn(sc, link_space=20, rng=16 + L, eltype=complex, normalise=True)))
     for name, f in nets:
         f._plans.clear()
         dims = f.indexmap.dimensions()
