@@ -66,6 +66,17 @@ def build_workload(config: int):
         s = t.continuous_siteinds(t.named_grid((20, 1)))
         f = t.sin_itn(s, k=2.0, a=0.3, c=1.1)
         return f, 1, 10_000, "cfg1: 1-D sin QTT, 20-bit MPS, chi=2 complex, 1e4 points"
+    if config in (6, 7):
+        # the small-chi end of the north star ("add a chi=1 exp_itn product-state case so the
+        # small-chi -> HBM GB/s clause has a datapoint"): config 2's layout and point set at chi = 1 / chi = 2
+        g = t.named_comb_tree((2, 30))
+        s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+        if config == 6:
+            f = t.exp_itn(s, k=0.9, a=0.1, c=1.2, dim=1)
+            return f, 2, 100_000_000, ("hbm datapoint: exp_itn product state (chi=1) on the 2-D comb tree 2x30 bits, real, "
+                                       "1e8 random points/GPU")
+        f = t.rand_itn(s, link_space=2, rng=20267, normalise=True)
+        return f, 2, 100_000_000, "small-chi datapoint: random chi=2 chain on the 2-D comb tree 2x30 bits, real, 1e8 random points/GPU"
     raise SystemExit(f"config {config} is a parity-test case, not a bench line")
 
 
@@ -232,7 +243,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, help="2 (default, BASELINE configs[1]), 3, 4, 5 or 1")
+    ap.add_argument("--config", type=int, default=2,
+                    help="2 (default, BASELINE configs[1]), 3, 4, 5 or 1; 6 / 7 = the HBM-bound small-chi datapoints "
+                         "(chi = 1 product state / chi = 2 on config 2's layout)")
     ap.add_argument("--points", type=float, default=0, help="override points per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grid", action="store_true",
@@ -381,6 +394,24 @@ def main():
                                  "algorithmic_achieved/algorithmic_frac use the rule's flops / kernel time "
                                  "(the contract's literal definition) and exceed the pipe's peak for that reason"},
         }
+        if o_dev.kernel_used == _capi.TTN_KERNEL_TABLE:
+            # small chi: a few flops per point against 8 B per coordinate + 8 / 16 B per value -> HBM roofline
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+            try:
+                hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                hbm_src = "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth, read + write bytes)"
+            except (OSError, ValueError, KeyError):
+                pass
+            bpp = info["bytes_per_point"]
+            gbs = bpp * npts / (kernel_ms * 1e-3) / 1e9
+            line["roofline"] = {
+                "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "traffic": traffic, "algorithmic_bytes_per_point": bpp, "peak_source": hbm_src,
+                "executed_flops_per_point": o_dev.flops_executed / npts, "algorithmic_flops_per_point": flops_pp,
+                "fp64_tflops_executed": exec_tf,
+                "note": "table kernel (k_chain_table.cu): groups of chain vertices pre-contracted at plan time into "
+                        "shared-memory tables, one lookup per group; algorithmic bytes = 8 B per coordinate read + "
+                        "8 (16 complex) B per value written"}
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle as orc

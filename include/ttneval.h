@@ -83,6 +83,9 @@ enum {
                              vertex over a chunk, degree-3 vertices as Khatri-Rao FP64 DMMA GEMMs */
   TTN_KERNEL_GRID = 6,    /* ttn_evaluate_grid on a FULL dyadic grid of a binary chain: prefix-shared level-by-level
                              expansion (~L/2 times fewer flops than independent points) */
+  TTN_KERNEL_TABLE = 7,   /* narrow chains of binary site indices (chi <= 4 real / 2 complex): groups of vertices
+                             pre-contracted at plan time into shared-memory tables, one lookup per group; the
+                             HBM-bound point-streaming kernel */
   TTN_KERNEL_GEMM = 4     /* wide chains (width 33..256, e.g. complex chi = 128): per-site class-grouped FP64
                              DMMA GEMM with gathered rows, state in HBM/L2 */
 };

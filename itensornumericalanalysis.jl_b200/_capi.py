@@ -12,8 +12,8 @@ TTN_ABI_VERSION = 2
 TTN_OK, TTN_ERR_INVALID, TTN_ERR_DOMAIN, TTN_ERR_CUDA, TTN_ERR_UNSUPPORTED, TTN_ERR_NOMEM = range(6)
 TTN_LAYOUT_AOS, TTN_LAYOUT_SOA = 0, 1
 TTN_MEM_HOST, TTN_MEM_DEVICE = 0, 1
-TTN_KERNEL_AUTO, TTN_KERNEL_GENERIC, TTN_KERNEL_CHAIN, TTN_KERNEL_DMMA, TTN_KERNEL_GEMM, TTN_KERNEL_TREE, TTN_KERNEL_GRID = range(7)
-KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm", 5: "tree", 6: "grid"}
+TTN_KERNEL_AUTO, TTN_KERNEL_GENERIC, TTN_KERNEL_CHAIN, TTN_KERNEL_DMMA, TTN_KERNEL_GEMM, TTN_KERNEL_TREE, TTN_KERNEL_GRID, TTN_KERNEL_TABLE = range(8)
+KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm", 5: "tree", 6: "grid", 7: "table"}
 KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 TTN_REDUCE_NONE, TTN_REDUCE_SUM, TTN_REDUCE_ABS2, TTN_REDUCE_WEIGHTED = range(4)
 REDUCE_IDS = {None: 0, False: 0, "none": 0, True: 1, "sum": 1, "abs2": 2, "weighted": 3}

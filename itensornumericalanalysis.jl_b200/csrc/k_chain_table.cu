@@ -1,0 +1,614 @@
+// K9 — narrow chains (real chi <= 4, complex chi <= 2): the HBM-bound end of the path.
+//
+// At small bond dimension the contraction of one point (project + scalar,
+// src/itensornetworkfunction.jl:84-106) is a handful of flops against 8 bytes per coordinate read
+// and 8 / 16 bytes written, so the kernel has to stream points at HBM speed.  A point picks one
+// slice per vertex, hence a GROUP of k consecutive chain vertices acts on the state as one of
+// 2^(k b) tiny matrices (b = slice bits per vertex).  The plan tabulates those products (long
+// double, rounded once) for groups of up to 16 stream bits:
+//     leaf group  -> 2^gL row vectors      v   = Lt[s_0]
+//     middle groups -> 2^g  H x H matrices  v  <- v * Mt_g[s_g]
+//     root group  -> 2^gR column vectors   out = v . Rt[s_last]
+// sized so that ALL tables of the chain sit in the shared memory of one CTA (<= 200 KB).  The
+// kernel is one persistent CTA per SM: tables are loaded once, then every thread streams PPT
+// points per tile — coordinates with coalesced (128-bit for 2-D AoS input) loads prefetched one
+// tile ahead, K1 (k_digits.cuh semantics; the exact floor(x 2^L) run fast path for binary digits on
+// consecutive vertices) into a 128-bit packed slice stream, one table lookup per group with the
+// state in registers, one coalesced store.  A 60-bit chi = 1 chain costs 5 shared-memory lookups
+// and 5 multiplies per point; algorithmic traffic = 8 n_coords + 8 (16 complex) bytes per point.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "k_chain_common.cuh"
+
+namespace ttn {
+
+// ------------------------------------------------------------------------------ device side
+
+template <int N>
+__device__ __forceinline__ void lds_vec(uint32_t addr, double (&dst)[N]) {
+  if constexpr (N == 1) {
+    dst[0] = lds64(addr);
+  } else {
+    static_assert(N % 2 == 0, "vector length");
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const double2 t = lds128(addr + 16u * i);
+      dst[2 * i] = t.x;
+      dst[2 * i + 1] = t.y;
+    }
+  }
+}
+
+__device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2>
+__global__ void __launch_bounds__(NT, MINB)
+    chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
+                       double* __restrict__ partial, int do_sum) {
+  constexpr int E = CPLX ? 2 : 1, HE = H * E, MM = H * H * E;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ double red[2][NT / 32];
+  __shared__ Digit2 s_d2[kFeMaxSites];
+  __shared__ int s_cptr[TTN_MAX_COORDS + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
+  for (int i = tid; i < dg.n_sites; i += NT) {
+    const DigitEntry e = dg.entries[i];
+    Digit2 d2;
+    d2.thr1 = dg.thr[e.thr_off + 1];
+    d2.sh = (uint32_t)e.shift;
+    d2.wv = ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+    s_d2[i] = d2;
+  }
+  {
+    const double2* g = reinterpret_cast<const double2*>(ct.image);
+    double2* s = reinterpret_cast<double2*>(smem);
+    for (int i = tid; i < ct.total_doubles / 2; i += NT) s[i] = __ldg(g + i);
+  }
+  __syncthreads();
+
+  const uint32_t sbase = smem_u32(smem);
+  const int G = ct.n_groups;
+  constexpr int64_t TILE = (int64_t)NT * PPT;
+  const int64_t n_tiles = (src.npts + TILE - 1) / TILE;
+  double sum_re = 0.0, sum_im = 0.0;
+
+  // K1 for coordinate slot c of the PPT points of this thread (same arithmetic as compute_words of
+  // the team-sorted kernel): run fast path or the tabulated greedy loop, bits OR-ed into the stream
+  uint64_t w0[PPT], w1[PPT];
+  auto add_coord = [&](int c, double (&x)[PPT], int64_t p0) {
+#pragma unroll
+    for (int k = 0; k < PPT; ++k)
+      if (!coord_in_domain(x[k])) {
+        atomicOr(err, 1);
+        x[k] = 0.0;
+      }
+    if (ct.run_L[c] > 0 && !src.digits) {
+      const int L = ct.run_L[c], plow = ct.run_plow[c];
+      const double scale = ct.run_scale[c];
+      const bool rev = ct.run_rev[c] != 0;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+        if (rev) q = __brevll(q) >> (64 - L);
+        if (plow < 64) {
+          w0[k] += q << plow;
+          if (plow + L > 64) w1[k] += q >> (64 - plow);
+        } else {
+          w1[k] += q << (plow - 64);
+        }
+      }
+    } else {
+      for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
+        const Digit2 e = s_d2[e_i];
+        const uint32_t stride = e.wv & 0xffu;
+        const bool hi = ((e.wv >> 8) & 0xffu) != 0;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const bool ge = src.digits ? (given_digit(src, p0 + (int64_t)k * NT, dg.n_sites, (int)(e.wv >> 16), 2, err) != 0)
+                                     : (x[k] >= e.thr1);
+          x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
+          const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
+          if (hi) w1[k] += bb;
+          else w0[k] += bb;
+        }
+      }
+    }
+  };
+  // 2-D AoS input: one 128-bit load per point, issued one tile ahead
+  double2 xnext[AOS2 ? PPT : 1];
+  auto fetch_aos2 = [&](int64_t tile_) {
+#pragma unroll
+    for (int k = 0; k < (AOS2 ? PPT : 1); ++k) {
+      const int64_t p = tile_ * TILE + (int64_t)k * NT + tid;
+      xnext[k] = make_double2(0.0, 0.0);
+      if (tile_ < n_tiles && p < src.npts) xnext[k] = ldg_nc_f64x2(src.coords + 2 * p);
+    }
+  };
+  if (AOS2) fetch_aos2(blockIdx.x);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * TILE + tid; // point k of this thread: p0 + k * NT
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) w0[k] = w1[k] = 0;
+    if (AOS2) {
+      double xa[PPT], xb[PPT];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        xa[k] = xnext[k].x;
+        xb[k] = xnext[k].y;
+      }
+      fetch_aos2(tile + gridDim.x);
+      add_coord(0, xa, p0);
+      add_coord(1, xb, p0);
+    } else {
+      for (int c = 0; c < dg.n_coords; ++c) {
+        double x[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          const int64_t p = p0 + (int64_t)k * NT;
+          x[k] = p < src.npts ? load_coord(src, p, c) : 0.0;
+        }
+        add_coord(c, x, p0);
+      }
+    }
+
+    auto take = [&](int k, int lb) -> uint32_t {
+      const uint32_t s = (uint32_t)(w0[k] & ((1ull << lb) - 1ull));
+      w0[k] = (w0[k] >> lb) | (w1[k] << (64 - lb));
+      w1[k] >>= lb;
+      return s;
+    };
+    // ---- leaf group
+    double v[PPT][HE];
+    {
+      const int lb = ct.gbits[0];
+      const uint32_t base = sbase + 8u * (uint32_t)ct.goff[0];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) lds_vec<HE>(base + take(k, lb) * (uint32_t)(HE * 8), v[k]);
+    }
+    // ---- middle groups: v <- v * M[s]
+    for (int g = 1; g < G - 1; ++g) {
+      const int lb = ct.gbits[g];
+      const uint32_t base = sbase + 8u * (uint32_t)ct.goff[g];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        double m[MM], a[HE];
+        lds_vec<MM>(base + take(k, lb) * (uint32_t)(MM * 8), m);
+#pragma unroll
+        for (int j = 0; j < HE; ++j) a[j] = 0.0;
+        if constexpr (!CPLX) {
+#pragma unroll
+          for (int i = 0; i < H; ++i)
+#pragma unroll
+            for (int j = 0; j < H; ++j) a[j] = fma(v[k][i], m[i * H + j], a[j]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < H; ++i)
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+              const double mr = m[(i * H + j) * 2], mi = m[(i * H + j) * 2 + 1];
+              a[2 * j] = fma(v[k][2 * i], mr, a[2 * j]);
+              a[2 * j] = fma(-v[k][2 * i + 1], mi, a[2 * j]);
+              a[2 * j + 1] = fma(v[k][2 * i], mi, a[2 * j + 1]);
+              a[2 * j + 1] = fma(v[k][2 * i + 1], mr, a[2 * j + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HE; ++j) v[k][j] = a[j];
+      }
+    }
+    // ---- root group: out = v . R[s]
+    {
+      const int lb = ct.gbits[G - 1];
+      const uint32_t base = sbase + 8u * (uint32_t)ct.goff[G - 1];
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        double r[HE];
+        lds_vec<HE>(base + take(k, lb) * (uint32_t)(HE * 8), r);
+        double o0 = 0.0, o1 = 0.0;
+        if constexpr (!CPLX) {
+#pragma unroll
+          for (int i = 0; i < H; ++i) o0 = fma(v[k][i], r[i], o0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < H; ++i) {
+            o0 = fma(v[k][2 * i], r[2 * i], o0);
+            o0 = fma(-v[k][2 * i + 1], r[2 * i + 1], o0);
+            o1 = fma(v[k][2 * i], r[2 * i + 1], o1);
+            o1 = fma(v[k][2 * i + 1], r[2 * i], o1);
+          }
+        }
+        const int64_t p = p0 + (int64_t)k * NT;
+        if (p < src.npts) {
+          if (out) {
+            if (CPLX) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+            else out[p] = o0;
+          }
+          accumulate_point(src, p, o0, o1, sum_re, sum_im);
+        }
+      }
+    }
+  }
+
+  if (do_sum) {
+    // deterministic: fixed-order shuffle tree per warp, then thread 0 adds the warp partials in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum_re += __shfl_down_sync(0xffffffffu, sum_re, o);
+      sum_im += __shfl_down_sync(0xffffffffu, sum_im, o);
+    }
+    if (lane == 0) {
+      red[0][tid >> 5] = sum_re;
+      red[1][tid >> 5] = sum_im;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < NT / 32; ++w) {
+        a += red[0][w];
+        b += red[1][w];
+      }
+      partial[2 * blockIdx.x] = a;
+      partial[2 * blockIdx.x + 1] = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+namespace {
+struct cld {
+  long double re = 0.0L, im = 0.0L;
+};
+inline cld cmul(const cld& a, const cld& b) { return cld{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+// one chain position: slice-selected a x b matrix (leaf: a = 1, root: b = 1), slices padded to 2^bits0
+struct PosMat {
+  int a = 1, b = 1;
+  std::vector<cld> e; // [(s * a + i) * b + j]
+};
+
+// TTN_TABLE_VARIANT, read when a plan is built (experiments; 0 is what the bench runs)
+int variant_from_env() { return getenv("TTN_TABLE_VARIANT") ? atoi(getenv("TTN_TABLE_VARIANT")) : 0; }
+} // namespace
+
+// Host image of the group tables (pure function of the description: also behind the debug symbol
+// ttn_debug_table_image, which the CPU tests walk with numpy against an independent contraction).
+struct TableImage {
+  int H = 0, cplx = 0, bits0 = 0, n = 0;
+  std::vector<int> gbits, goff;    // stream bits / offset (doubles) per group; group 0 = leaf, last = root
+  std::vector<double> image;
+  std::vector<int> pos_of;         // chain position of every vertex (0 = leaf)
+  double flops_exec = 0.0;
+};
+
+static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage* out) {
+  const int n = d->n_vertices;
+  const bool cplx = d->is_complex != 0;
+  const int NC = cplx ? 2 : 1;
+  if (n < 2 || d->n_sites < 1 || d->n_sites > kFeMaxSites) return false;
+  // chain order from the parent array: every vertex has at most one child
+  std::vector<int> child(n, -1), nsl(n, 1);
+  for (int v = 0; v < n; ++v) {
+    const int q = d->parent[v];
+    if (q < 0) continue;
+    if (child[q] >= 0) return false;
+    child[q] = v;
+  }
+  std::vector<int> order(n), pos_of(n);
+  {
+    int v = d->root;
+    for (int pos = n - 1; pos >= 0; --pos) {
+      if (v < 0) return false;
+      order[pos] = v;
+      v = child[v];
+    }
+    for (int pos = 0; pos < n; ++pos) pos_of[order[pos]] = pos;
+  }
+  int maxchi = 1, maxsl = 1;
+  for (int v = 0; v < n; ++v) {
+    for (int si = d->site_ptr[v]; si < d->site_ptr[v + 1]; ++si) {
+      if (d->site_dim[si] != 2) return false; // binary digits only (bit-field slice indices)
+      nsl[v] *= 2;
+    }
+    maxchi = std::max(maxchi, d->link_dim[v]);
+    maxsl = std::max(maxsl, nsl[v]);
+  }
+  if (maxsl > 4 || maxsl < 2) return false;
+  if (maxchi > (cplx ? 2 : 4)) return false;
+  const int H = maxchi <= 1 ? 1 : (maxchi <= 2 ? 2 : 4);
+  const int bits0 = maxsl == 2 ? 1 : 2, S0 = 1 << bits0;
+  const int B = n * bits0;
+  if (B > 128) return false;
+  const int E = cplx ? 2 : 1;
+  const size_t ev = (size_t)H * E, em = (size_t)H * H * E;
+
+  // ---- group sizes: fewest groups whose tables fit the budget; among those the smallest image
+  std::vector<int> gb;
+  {
+    const size_t budget = budget_bytes / 8;
+    for (int G = 2; G <= kTabMaxGroups && gb.empty(); ++G) {
+      size_t best = 0;
+      for (int tm = bits0; tm <= 16; tm += bits0) {
+        const int rem = B - (G - 2) * tm;
+        if (rem < 2 * bits0) break;
+        const int gL = ((rem / bits0 + 1) / 2) * bits0, gR = rem - gL;
+        if (gL > 16 || gR < bits0) continue;
+        const size_t size = (((size_t)1 << gL) + ((size_t)1 << gR)) * ev + (size_t)(G - 2) * ((size_t)1 << tm) * em;
+        if (size <= budget && (gb.empty() || size < best)) {
+          best = size;
+          gb.assign(G, tm);
+          gb[0] = gL;
+          gb[G - 1] = gR;
+        }
+        if (G == 2) break;
+      }
+    }
+    if (gb.empty()) return false;
+  }
+  const int G = (int)gb.size();
+
+  // ---- per-position matrices
+  const double* T = reinterpret_cast<const double*>(d->tensors);
+  std::vector<PosMat> pm(n);
+  for (int pos = 0; pos < n; ++pos) {
+    const int v = order[pos];
+    PosMat& m = pm[pos];
+    m.a = pos == 0 ? 1 : d->link_dim[order[pos - 1]];
+    m.b = d->link_dim[v]; // 1 at the root
+    m.e.assign((size_t)S0 * m.a * m.b, cld{});
+    if (d->tensor_ptr[v + 1] - d->tensor_ptr[v] != (int64_t)nsl[v] * m.a * m.b) return false;
+    for (int s = 0; s < nsl[v]; ++s)
+      for (int i = 0; i < m.a * m.b; ++i) {
+        const int64_t idx = (d->tensor_ptr[v] + (int64_t)s * m.a * m.b + i) * NC;
+        m.e[(size_t)s * m.a * m.b + i] = cld{(long double)T[idx], cplx ? (long double)T[idx + 1] : 0.0L};
+      }
+  }
+
+  // ---- tables
+  out->gbits = gb;
+  out->goff.assign(G, 0);
+  size_t total = 0;
+  for (int g = 0; g < G; ++g) {
+    out->goff[g] = (int)total;
+    total += ((size_t)1 << gb[g]) * ((g == 0 || g == G - 1) ? ev : em);
+    total = (total + 1) & ~(size_t)1; // 16-byte alignment of every table
+  }
+  out->image.assign(total, 0.0);
+  double flops = 0.0;
+  int c0 = 0;
+  for (int g = 0; g < G; ++g) {
+    const int k = gb[g] / bits0;
+    const int rows = pm[c0].a;
+    std::vector<cld> cur = pm[c0].e;
+    size_t n_cur = S0;
+    int cols = pm[c0].b;
+    for (int i = 1; i < k; ++i) {
+      const PosMat& A = pm[c0 + i];
+      if (A.a != cols) return false;
+      std::vector<cld> nxt(n_cur * S0 * rows * A.b);
+      for (int bsl = 0; bsl < S0; ++bsl)
+        for (size_t s = 0; s < n_cur; ++s) {
+          const size_t idx = s + ((size_t)bsl << (bits0 * i));
+          for (int r = 0; r < rows; ++r)
+            for (int j = 0; j < A.b; ++j) {
+              cld acc;
+              for (int mm = 0; mm < cols; ++mm) {
+                const cld t = cmul(cur[(s * rows + r) * cols + mm], A.e[((size_t)bsl * A.a + mm) * A.b + j]);
+                acc.re += t.re;
+                acc.im += t.im;
+              }
+              nxt[(idx * rows + r) * A.b + j] = acc;
+            }
+        }
+      cur.swap(nxt);
+      n_cur *= S0;
+      cols = A.b;
+    }
+    // cur: [2^gbits][rows][cols]; leaf group rows = 1, root group cols = 1
+    const bool is_leaf = g == 0, is_root = g == G - 1;
+    if ((is_leaf && rows != 1) || (is_root && cols != 1)) return false;
+    const size_t esz = (is_leaf || is_root) ? ev : em;
+    double* dst = out->image.data() + out->goff[g];
+    for (size_t s = 0; s < n_cur; ++s)
+      for (int r = 0; r < rows; ++r)
+        for (int j = 0; j < cols; ++j) {
+          const cld x = cur[(s * rows + r) * cols + j];
+          const size_t at = is_leaf ? (size_t)j : (is_root ? (size_t)r : (size_t)r * H + j);
+          dst[s * esz + at * E] = (double)x.re;
+          if (cplx) dst[s * esz + at * E + 1] = (double)x.im;
+        }
+    if (!is_leaf) flops += (cplx ? 8.0 : 2.0) * rows * cols;
+    c0 += k;
+  }
+  out->H = H;
+  out->cplx = cplx ? 1 : 0;
+  out->bits0 = bits0;
+  out->n = n;
+  out->pos_of = pos_of;
+  out->flops_exec = flops;
+  return true;
+}
+
+static size_t table_budget_bytes(int variant) {
+  if (const char* e = getenv("TTN_TABLE_KB")) return (size_t)std::max(8, std::min(atoi(e), 200)) * 1024;
+  return (size_t)(variant == 2 ? 100 : 200) * 1024;
+}
+
+int build_chain_table(ttn_plan* p, const ttn_desc* d) {
+  p->ctab_ok = false;
+  if (!p->is_chain || !p->all_base2) return TTN_OK;
+  TableImage im;
+  p->ctab_variant = variant_from_env();
+  if (!make_table_image(d, table_budget_bytes(p->ctab_variant), &im)) return TTN_OK;
+  ChainTabDev& c = p->ctab;
+  c = ChainTabDev{};
+  c.n_groups = (int)im.gbits.size();
+  c.H = im.H;
+  c.cplx = im.cplx;
+  c.total_doubles = (int)im.image.size();
+  for (int g = 0; g < c.n_groups; ++g) {
+    c.gbits[g] = im.gbits[g];
+    c.goff[g] = im.goff[g];
+  }
+  double* d_img;
+  TTN_CUDA(cudaMalloc(&d_img, std::max<size_t>(im.image.size() * 8, 16)));
+  p->allocs.push_back(d_img);
+  TTN_CUDA(cudaMemcpy(d_img, im.image.data(), im.image.size() * 8, cudaMemcpyHostToDevice));
+  c.image = d_img;
+  p->ctab_flops_exec = im.flops_exec;
+
+  // own copy of the digit table: (word, shift) = bit position of the vertex in THIS kernel's stream
+  const int bits0 = im.bits0;
+  p->digits_tab = p->digits;
+  std::vector<DigitEntry> ent(d->n_sites);
+  TTN_CUDA(cudaMemcpy(ent.data(), p->digits.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
+  for (auto& e : ent) {
+    const int bitpos = im.pos_of[e.vertex] * bits0;
+    e.word = bitpos / 64;
+    e.shift = bitpos % 64;
+  }
+  DigitEntry* d_ent;
+  TTN_CUDA(cudaMalloc(&d_ent, sizeof(DigitEntry) * d->n_sites));
+  p->allocs.push_back(d_ent);
+  TTN_CUDA(cudaMemcpy(d_ent, ent.data(), sizeof(DigitEntry) * d->n_sites, cudaMemcpyHostToDevice));
+  p->digits_tab.entries = d_ent;
+
+  // K1 run fast path per coordinate slot — same conditions as build_chain_mma (k_chain_mma.cu): binary
+  // digits 1..L with thresholds exactly 2^-k, one site index per vertex, consecutive stream bits in
+  // increasing or decreasing order.  Then digit k = bit (L-k) of floor(x 2^L), exactly.
+  if (bits0 == 1) {
+    std::vector<int32_t> cptr(d->n_coords + 1);
+    TTN_CUDA(cudaMemcpy(cptr.data(), p->digits.coord_ptr, sizeof(int32_t) * (d->n_coords + 1), cudaMemcpyDeviceToHost));
+    for (int cidx = 0; cidx < d->n_coords; ++cidx) {
+      const int L = cptr[cidx + 1] - cptr[cidx];
+      if (L < 1 || L > 63) continue;
+      bool ok = true;
+      int step = 0, first_pos = -1;
+      for (int k = 0; k < L && ok; ++k) {
+        const DigitEntry& e = ent[cptr[cidx] + k];
+        const int pos = e.word * 64 + e.shift;
+        ok = ok && e.base == 2 && e.stride == 1 && p->nslices[e.vertex] == 2;
+        ok = ok && d->site_digit[e.site] == k + 1 && d->thr[e.thr_off + 1] == std::ldexp(1.0, -(k + 1));
+        if (k == 0) first_pos = pos;
+        else if (k == 1) step = pos - first_pos;
+        if (k >= 1) ok = ok && (pos - first_pos == step * k);
+      }
+      if (L == 1) step = 1;
+      if (!ok || (step != 1 && step != -1)) continue;
+      c.run_L[cidx] = L;
+      c.run_rev[cidx] = step == 1 ? 1 : 0;
+      c.run_plow[cidx] = step == 1 ? first_pos : first_pos - (L - 1);
+      c.run_scale[cidx] = std::ldexp(1.0, L);
+    }
+  }
+  p->ctab_ok = true;
+  return TTN_OK;
+}
+
+template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2>
+static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                           cudaStream_t s) {
+  const ChainTabDev& c = p->ctab;
+  const size_t smem = (size_t)c.total_doubles * 8;
+  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, AOS2>;
+  TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  TTN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  per_sm = std::max(1, std::min(per_sm, MINB));
+  const int64_t n_tiles = (src.npts + (int64_t)NT * PPT - 1) / ((int64_t)NT * PPT);
+  const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)p->sm_count * per_sm);
+  const int do_sum = d_partial != nullptr;
+  kern<<<grid, NT, smem, s>>>(c, p->digits_tab, src, d_out, p->d_err, d_partial, do_sum);
+  TTN_CUDA(cudaGetLastError());
+  *n_partial = do_sum ? grid : 0;
+  return TTN_OK;
+}
+
+template <int H, bool CPLX, int PPT>
+static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                              cudaStream_t s) {
+  const bool aos2 = !src.digits && !src.grid && src.coords && src.layout == TTN_LAYOUT_AOS && src.n_coords == 2 &&
+                    (reinterpret_cast<uintptr_t>(src.coords) & 15u) == 0;
+  // TTN_TABLE_VARIANT: 0 = 512 threads, 1 = 1024 threads (one CTA per SM), 2 = 2 CTAs of 512 threads per SM
+  // with tables of <= 100 KB (experiments; 0 is what the bench runs)
+  switch (p->ctab_variant) {
+    case 1:
+      return aos2 ? launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), true>(p, src, d_out, d_partial, n_partial, s)
+                  : launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), false>(p, src, d_out, d_partial, n_partial, s);
+    case 2:
+      return aos2 ? launch_tab_inst<H, CPLX, 512, 2, (PPT > 2 ? 2 : PPT), true>(p, src, d_out, d_partial, n_partial, s)
+                  : launch_tab_inst<H, CPLX, 512, 2, (PPT > 2 ? 2 : PPT), false>(p, src, d_out, d_partial, n_partial, s);
+    default:
+      return aos2 ? launch_tab_inst<H, CPLX, 512, 1, PPT, true>(p, src, d_out, d_partial, n_partial, s)
+                  : launch_tab_inst<H, CPLX, 512, 1, PPT, false>(p, src, d_out, d_partial, n_partial, s);
+  }
+}
+
+int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                       int* n_partial, cudaStream_t s) {
+  (void)st;
+  *n_partial = 0;
+  if (src.npts == 0) return TTN_OK;
+  if (!p->ctab_ok) {
+    set_error("table kernel requested but the network is not a narrow binary chain");
+    return TTN_ERR_UNSUPPORTED;
+  }
+  const ChainTabDev& c = p->ctab;
+  if (!c.cplx) {
+    if (c.H == 1) return launch_tab_variant<1, false, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 2) return launch_tab_variant<2, false, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 4) return launch_tab_variant<4, false, 2>(p, src, d_out, d_partial, n_partial, s);
+  } else {
+    if (c.H == 1) return launch_tab_variant<1, true, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 2) return launch_tab_variant<2, true, 2>(p, src, d_out, d_partial, n_partial, s);
+  }
+  set_error("table kernel: unsupported bond dimension");
+  return TTN_ERR_UNSUPPORTED;
+}
+
+// Debug / test hook (not part of the ABI in include/ttneval.h; no CUDA calls): the table image of a
+// description, so that CPU tests can walk it against an independent contraction.
+//   meta[0..7] = {applicable, H, is_complex, bits0, n_groups, total_doubles, 0, 0}; meta[8 + g] = gbits[g],
+//   meta[8 + 16 + g] = goff[g]; site_bitpos[s] = stream bit of site index s (stride included).
+int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, double* image, int64_t image_cap,
+                      int32_t* site_bitpos) {
+  TableImage im;
+  for (int i = 0; i < 8 + 2 * kTabMaxGroups; ++i) meta[i] = 0;
+  bool base2 = true;
+  for (int s = 0; s < d->n_sites; ++s) base2 = base2 && d->site_dim[s] == 2;
+  if (!base2 || !make_table_image(d, (size_t)budget_kb * 1024, &im)) return TTN_OK;
+  if ((int64_t)im.image.size() > image_cap) {
+    set_error("debug_table_image: image buffer too small");
+    return TTN_ERR_INVALID;
+  }
+  meta[0] = 1;
+  meta[1] = im.H;
+  meta[2] = im.cplx;
+  meta[3] = im.bits0;
+  meta[4] = (int)im.gbits.size();
+  meta[5] = (int)im.image.size();
+  for (size_t g = 0; g < im.gbits.size(); ++g) {
+    meta[8 + g] = im.gbits[g];
+    meta[8 + kTabMaxGroups + g] = im.goff[g];
+  }
+  std::copy(im.image.begin(), im.image.end(), image);
+  for (int v = 0; v < d->n_vertices; ++v) {
+    int stride_bits = 0;
+    for (int si = d->site_ptr[v + 1] - 1; si >= d->site_ptr[v]; --si) {
+      site_bitpos[si] = im.pos_of[v] * im.bits0 + stride_bits;
+      stride_bits += 1;
+    }
+  }
+  return TTN_OK;
+}
+
+} // namespace ttn

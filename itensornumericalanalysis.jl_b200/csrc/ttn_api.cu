@@ -180,6 +180,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   if ((rc = build_chain(p, d))) return rc;
   if ((rc = build_chain_mma(p, d))) return rc;
   if ((rc = build_chain_gemm(p, d))) return rc;
+  if ((rc = build_chain_table(p, d))) return rc;
   if ((rc = build_grid_share(p, d))) return rc;
   if (!p->is_chain && (rc = build_tree_gemm(p, d))) return rc;
 
@@ -193,7 +194,8 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   // planner: DMMA tiles once the (real-embedded) row is wide enough to fill them, the register
   // kernel for narrow chains, the generic kernel for everything that is not a chain
   const int width = (d->is_complex ? 2 : 1) * max_link;
-  if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
+  if (p->ctab_ok && width <= 4) I.auto_kernel = TTN_KERNEL_TABLE; // HBM-bound regime: group tables in shared memory
+  else if (p->cmma_ok && width >= 6) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
@@ -202,7 +204,8 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
                         (p->cmma_ok ? (1 << TTN_KERNEL_DMMA) : 0) | (p->cgemm_ok ? (1 << TTN_KERNEL_GEMM) : 0) |
-                        (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0) | (p->gshare_ok ? (1 << TTN_KERNEL_GRID) : 0);
+                        (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0) | (p->gshare_ok ? (1 << TTN_KERNEL_GRID) : 0) |
+                        (p->ctab_ok ? (1 << TTN_KERNEL_TABLE) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
@@ -252,6 +255,7 @@ static int run_kernel(ttn_plan* p, int kernel, Stream& st, const CoordSource& sr
     case TTN_KERNEL_GENERIC: return launch_generic(p, st, src, d_out, d_partial, n_partial, st.s);
     case TTN_KERNEL_CHAIN: return launch_chain(p, st, src, d_out, d_partial, n_partial, st.s);
     case TTN_KERNEL_DMMA: return launch_chain_mma(p, st, src, d_out, d_partial, n_partial, st.s);
+    case TTN_KERNEL_TABLE: return launch_chain_table(p, st, src, d_out, d_partial, n_partial, st.s);
     default: break;
   }
   return fail(TTN_ERR_UNSUPPORTED, "requested kernel is not available in this build");
@@ -348,6 +352,8 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
+  if (kernel == TTN_KERNEL_TABLE && !p->ctab_ok)
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TABLE: network is not a chain of binary site indices with chi <= 4 (real) / 2 (complex), <= 2 site indices per vertex and <= 128 slice bits");
   if (kernel == TTN_KERNEL_TREE && !p->tgemm_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a real tree with <= 2 children per vertex, chi <= 64 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_GEMM && !p->cgemm_ok)
@@ -481,6 +487,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? p->cmma_flops_exec
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
                             : (kernel == TTN_KERNEL_TREE && !p->tg_tab.empty()) ? p->tgemm_flops_exec
+                            : kernel == TTN_KERNEL_TABLE ? p->ctab_flops_exec
                                                                              : p->info.flops_per_point) *
                            (double)npts;
     int herr = 0;
@@ -667,6 +674,14 @@ int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coo
 #ifdef TTN_PHASE_CLOCKS
 int ttn_debug_phase_clocks(unsigned long long* out8, int reset) { return ttn::debug_phase_clocks(out8, reset); }
 #endif
+
+/* Test hook, not part of include/ttneval.h (no CUDA calls): the table kernel's plan-time image of a
+ * description, see debug_table_image in k_chain_table.cu. */
+int ttn_debug_table_image(const ttn_desc* desc, int32_t budget_kb, int32_t* meta, double* image, int64_t image_cap,
+                          int32_t* site_bitpos) {
+  if (!desc || !meta || !image || !site_bitpos) return fail(TTN_ERR_INVALID, "null argument");
+  return debug_table_image(desc, budget_kb, meta, image, image_cap, site_bitpos);
+}
 
 int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops) {
   if (!dfma_tflops || !dmma_tflops) return fail(TTN_ERR_INVALID, "null argument");

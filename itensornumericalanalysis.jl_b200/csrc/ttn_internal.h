@@ -127,6 +127,20 @@ struct ChainGemmDev {
   const double* root_tab;        // [nout][nsl^(1+tab_R)][W] or null
 };
 
+// narrow chains as shared-memory group tables (k_chain_table.cu)
+constexpr int kTabMaxGroups = 16;
+struct ChainTabDev {
+  int32_t n_groups;      // >= 2: group 0 = leaf vectors, last = root vectors, between: H x H matrices
+  int32_t H;             // padded bond dimension (a complex entry counts once): 1, 2 or 4
+  int32_t cplx;
+  int32_t total_doubles; // image size (even)
+  int32_t gbits[kTabMaxGroups]; // stream bits consumed by the group (<= 16)
+  int32_t goff[kTabMaxGroups];  // offset of the group's table in the image, in doubles (even)
+  int32_t run_L[TTN_MAX_COORDS], run_plow[TTN_MAX_COORDS], run_rev[TTN_MAX_COORDS]; // K1 run fast path
+  double run_scale[TTN_MAX_COORDS];
+  const double* image;
+};
+
 // trees with <= 2 children per vertex as per-vertex (Khatri-Rao) GEMMs (k_tree_gemm.cu)
 struct TreeGemmDev {
   int32_t n_vertices, W, root;
@@ -181,6 +195,11 @@ struct ttn_plan {
   bool cgemm_ok = false;
   bool gshare_ok = false;            // prefix-shared full-grid evaluation (k_grid_share.cu)
   std::vector<int> gs_coord, gs_digit, gs_L;
+  ttn::ChainTabDev ctab{};
+  bool ctab_ok = false;
+  ttn::DigitTable digits_tab{}; // same table, (word, shift) for the table kernel's stream layout
+  double ctab_flops_exec = 0.0;
+  int ctab_variant = 0; // TTN_TABLE_VARIANT at plan creation
   ttn::TreeGemmDev tgemm{};
   bool tgemm_ok = false;
   std::vector<int64_t> tg_frag_off;
@@ -229,6 +248,11 @@ int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double
                       cudaStream_t s);
 int launch_chain_ring(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                       cudaStream_t s);
+int build_chain_table(ttn_plan* p, const ttn_desc* d);
+int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
+                       int* n_partial, cudaStream_t s);
+int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, double* image, int64_t image_cap,
+                      int32_t* site_bitpos);
 bool chain_supported(int chi, int nsl, bool cplx);
 int measure_fp64_peak(int device, double* dfma, double* dmma);
 } // namespace ttn

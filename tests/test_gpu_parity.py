@@ -30,7 +30,7 @@ def coords_of(packed, pts):
 
 def kernels_for(plan):
     avail = plan.info()["kernels_available"]
-    return [n for n in ("generic", "chain", "dmma", "gemm", "tree") if avail & (1 << _capi.KERNEL_IDS[n])]
+    return [n for n in ("generic", "chain", "dmma", "gemm", "tree", "table") if avail & (1 << _capi.KERNEL_IDS[n])]
 
 
 ALL_CASES = [(c, False) for c in cases.real_cases()] + [(c, True) for c in cases.complex_cases()]
@@ -67,7 +67,9 @@ def test_chain_cases_really_use_the_chain_kernel():
               "cplx_2site", "cplx_default2d", "sum_chi3p2", "single_vertex", "two_vertices"):
         _, f, dims, _ = names[n]
         info = f.plan(dims).info()
-        assert info["auto_kernel"] in (_capi.TTN_KERNEL_CHAIN, _capi.TTN_KERNEL_DMMA), n
+        # narrow binary chains (width <= 4: sin_itn is complex chi = 2) take the HBM-bound table kernel
+        want = (_capi.TTN_KERNEL_TABLE,) if n == "sin_qtt20" else (_capi.TTN_KERNEL_CHAIN, _capi.TTN_KERNEL_DMMA)
+        assert info["auto_kernel"] in want, n
         assert info["kernels_available"] & (1 << _capi.TTN_KERNEL_CHAIN), n
         assert info["kernels_available"] & (1 << _capi.TTN_KERNEL_DMMA), n
     for n in ("mps2d_chi48_gemm", "cplx_cfg5_chi40_gemm"):
@@ -542,3 +544,105 @@ def test_team_sorted_kernel_edges(deep, monkeypatch):
         plan.evaluate_indices_host(dig2, kernel="dmma")
     assert e.value.code == _capi.TTN_ERR_INVALID
     f._plans.clear()
+
+
+def _narrow_networks():
+    g = t.named_comb_tree((2, 30))
+    s2 = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    s1 = t.continuous_siteinds(t.named_grid((20, 1)))
+    s3 = t.continuous_siteinds(t.named_grid((24, 1)), map_dimension=3)
+    sc = t.complex_continuous_siteinds(t.named_grid((12, 1)), map_dimension=2)
+    return {
+        "exp_comb2x30": t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1),                      # chi 1: 5 lookups per point
+        "cosh_comb2x30": t.cosh_itn(s2, k=0.9, a=0.1, c=1.2, dim=2),                    # chi 2 real, 60 bits
+        "rand_chi2_comb2x30": t.rand_itn(s2, link_space=2, rng=5, normalise=True),
+        "sin_qtt20": t.sin_itn(s1, k=3.0, a=0.25, c=0.8),                               # config 1: complex chi 2, 1-D
+        "rand_chi4_mps3d": t.rand_itn(s3, link_space=4, rng=6, normalise=True),         # 3 coordinates, interleaved
+        "rand_chi3_mps3d": t.rand_itn(s3, link_space=3, rng=7, normalise=True),         # padded to 4
+        "cplx_2site_chi2": t.rand_itn(sc, link_space=2, rng=8, eltype=complex, normalise=True),  # 2 bits per vertex
+        "cplx_2site_chi1": t.rand_itn(sc, link_space=1, rng=9, eltype=complex, normalise=True),
+    }
+
+
+@pytest.mark.parametrize("which", list(_narrow_networks()))
+def test_table_kernel_edges(which):
+    """The HBM-bound table kernel (k_chain_table.cu) on every instance it has (real chi 1/2/4, complex chi 1/2;
+    1 or 2 slice bits per vertex; 1, 2, 3 and 4 coordinate slots): it is the planner's choice for these
+    networks; values against the 80-bit oracle; batches around its tile sizes (512 threads x 2 or 4 points);
+    SOA layout and the device-pointer path (the 128-bit AoS coordinate loads) give bitwise the same values;
+    saturation, domain errors, functionals, index-setting mode."""
+    f = _narrow_networks()[which]
+    plan = f.plan()
+    packed = plan.packed
+    assert plan.info()["auto_kernel"] == _capi.TTN_KERNEL_TABLE
+    nc = packed.n_coords
+    rng = np.random.default_rng(23)
+    big = np.concatenate([cases.edge_points(20, nc, rng, 0), rng.random((5000, nc))])
+    big[1] = 1.0
+    big[2] = 3.5
+    ref = orc.evaluate(packed, big, orc.ORACLE_LD)
+    full, o = plan.evaluate_host(big)
+    assert o.kernel_used == _capi.TTN_KERNEL_TABLE and o.n_launches == 1
+    assert orc.error_metric(full, ref).max() < TOL
+    assert full[1] == full[2]                                    # x >= 1 saturates
+    assert (plan.digits_host(big) == orc.digits(packed, big)).all()
+    for k in kernels_for(plan):                                  # every other kernel agrees with the oracle too
+        got, _ = plan.evaluate_host(big[:700], kernel=k)
+        assert orc.error_metric(got, ref[:700]).max() < TOL, k
+    for n in (1, 31, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4097):
+        got, _ = plan.evaluate_host(big[:n], kernel="table")
+        assert (got == full[:n]).all(), n                        # a value never depends on the batch around it
+    got, _ = plan.evaluate_host(np.ascontiguousarray(big.T), layout=_capi.TTN_LAYOUT_SOA, kernel="table")
+    assert (got == full).all()
+    # device pointers (2-D AoS input takes the 128-bit coordinate loads), odd start offset inside the array
+    import torch
+    x = torch.from_numpy(big).to("cuda:0")
+    out = torch.empty(len(big), dtype=torch.complex128 if packed.is_complex else torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    o = plan.evaluate_device(x.data_ptr(), len(big), out.data_ptr(), reduce_sum=True)
+    assert (out.cpu().numpy() == full).all() and o.n_launches == 2
+    assert abs(complex(o.sum_out[0], o.sum_out[1]) - full.sum()) <= 1e-12 * np.abs(full).sum()
+    o = plan.evaluate_device(x.data_ptr() + 8 * nc * 3, len(big) - 3, out.data_ptr())
+    assert (out.cpu().numpy()[:len(big) - 3] == full[3:]).all()
+    # fused functionals
+    w = rng.random(len(big))
+    _, o = plan.evaluate_host(big, kernel="table", reduce_sum=_capi.TTN_REDUCE_ABS2, want_values=False)
+    assert abs(o.sum_out[0] - (np.abs(full) ** 2).sum()) <= 1e-12 * (np.abs(full) ** 2).sum()
+    _, o = plan.evaluate_host(big, kernel="table", reduce_sum=_capi.TTN_REDUCE_WEIGHTED, want_values=False, weights=w)
+    assert abs(complex(o.sum_out[0], o.sum_out[1]) - (w * full).sum()) <= 1e-12 * np.abs(w * full).sum()
+    # domain errors
+    for bad in (-1e-300, np.nan):
+        pts = big[:2100].copy()
+        pts[2077, nc - 1] = bad
+        with pytest.raises(_capi.TTNError) as e:
+            plan.evaluate_host(pts, kernel="table")
+        assert e.value.code == _capi.TTN_ERR_DOMAIN
+    # index-setting mode == coordinates whose digits are those settings
+    dig = orc.digits(packed, big[:900])
+    got, _ = plan.evaluate_indices_host(dig, kernel="table")
+    assert (got == full[:900]).all()
+    dig2 = dig.copy()
+    dig2[333, 5] = 2
+    with pytest.raises(_capi.TTNError) as e:
+        plan.evaluate_indices_host(dig2, kernel="table")
+    assert e.value.code == _capi.TTN_ERR_INVALID
+
+
+def test_table_kernel_known_answer_at_scale():
+    """exp_itn product state (chi = 1) on the bench layout at 2e7 points: f(x, y) = c exp(a + k x_trunc), the
+    closed form of src/elementary_functions.jl:30-53, to 1e-12; every group-table budget gives the same
+    function (different group sizes, same values to rounding)."""
+    import torch
+    g = t.named_comb_tree((2, 30))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    f = t.exp_itn(s, k=0.9, a=0.1, c=1.2, dim=1)
+    plan = f.plan()
+    n = 20_000_000
+    x = torch.rand((n, 2), dtype=torch.float64, device="cuda:0")
+    out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    o = plan.evaluate_device(x.data_ptr(), n, out.data_ptr())
+    assert o.kernel_used == _capi.TTN_KERNEL_TABLE
+    xt = torch.floor(x[:, 0] * 2.0 ** 30) / 2.0 ** 30
+    want = 1.2 * torch.exp(0.1 + 0.9 * xt)
+    assert float(((out - want).abs() / want.abs()).max()) < 1e-12
