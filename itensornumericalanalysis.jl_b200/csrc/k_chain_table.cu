@@ -47,7 +47,9 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
   return r;
 }
 
-template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2>
+// W2: the packed slice stream needs its second 64-bit word (more than 64 slice bits); chains of up to 64
+// bits (config 2's layout: 2 x 30) keep the stream in one register pair and shift half as much.
+template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2, bool W2>
 __global__ void __launch_bounds__(NT, MINB)
     chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                        double* __restrict__ partial, int do_sum) {
@@ -100,8 +102,8 @@ __global__ void __launch_bounds__(NT, MINB)
         if (rev) q = __brevll(q) >> (64 - L);
         if (plow < 64) {
           w0[k] += q << plow;
-          if (plow + L > 64) w1[k] += q >> (64 - plow);
-        } else {
+          if (W2 && plow + L > 64) w1[k] += q >> (64 - plow);
+        } else if (W2) {
           w1[k] += q << (plow - 64);
         }
       }
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(NT, MINB)
                                      : (x[k] >= e.thr1);
           x[k] = __dsub_rn(x[k], ge ? e.thr1 : 0.0);
           const uint64_t bb = (uint64_t)(ge ? stride : 0u) << e.sh;
-          if (hi) w1[k] += bb;
+          if (W2 && hi) w1[k] += bb;
           else w0[k] += bb;
         }
       }
@@ -162,8 +164,12 @@ __global__ void __launch_bounds__(NT, MINB)
 
     auto take = [&](int k, int lb) -> uint32_t {
       const uint32_t s = (uint32_t)(w0[k] & ((1ull << lb) - 1ull));
-      w0[k] = (w0[k] >> lb) | (w1[k] << (64 - lb));
-      w1[k] >>= lb;
+      if constexpr (W2) {
+        w0[k] = (w0[k] >> lb) | (w1[k] << (64 - lb));
+        w1[k] >>= lb;
+      } else {
+        w0[k] >>= lb;
+      }
       return s;
     };
     // ---- leaf group
@@ -440,7 +446,8 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
 
 static size_t table_budget_bytes(int variant) {
   if (const char* e = getenv("TTN_TABLE_KB")) return (size_t)std::max(8, std::min(atoi(e), 200)) * 1024;
-  return (size_t)(variant == 2 ? 100 : 200) * 1024;
+  (void)variant;
+  return (size_t)200 * 1024;
 }
 
 int build_chain_table(ttn_plan* p, const ttn_desc* d) {
@@ -514,12 +521,12 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   return TTN_OK;
 }
 
-template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2>
+template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2, bool W2>
 static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                            cudaStream_t s) {
   const ChainTabDev& c = p->ctab;
   const size_t smem = (size_t)c.total_doubles * 8;
-  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, AOS2>;
+  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, AOS2, W2>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   TTN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -533,24 +540,28 @@ static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
   return TTN_OK;
 }
 
-template <int H, bool CPLX, int PPT>
+template <int H, bool CPLX, int PPT, bool AOS2, bool W2>
 static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                               cudaStream_t s) {
+  // TTN_TABLE_VARIANT (read at plan creation): 0 = 512 threads x PPT points (what the bench runs),
+  // 1 = 1024 threads x <= 2 points; one persistent CTA per SM either way
+  if (p->ctab_variant == 1)
+    return launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+  return launch_tab_inst<H, CPLX, 512, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+}
+
+template <int H, bool CPLX, int PPT>
+static int launch_tab_shape(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
+                            cudaStream_t s) {
   const bool aos2 = !src.digits && !src.grid && src.coords && src.layout == TTN_LAYOUT_AOS && src.n_coords == 2 &&
                     (reinterpret_cast<uintptr_t>(src.coords) & 15u) == 0;
-  // TTN_TABLE_VARIANT: 0 = 512 threads, 1 = 1024 threads (one CTA per SM), 2 = 2 CTAs of 512 threads per SM
-  // with tables of <= 100 KB (experiments; 0 is what the bench runs)
-  switch (p->ctab_variant) {
-    case 1:
-      return aos2 ? launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), true>(p, src, d_out, d_partial, n_partial, s)
-                  : launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), false>(p, src, d_out, d_partial, n_partial, s);
-    case 2:
-      return aos2 ? launch_tab_inst<H, CPLX, 512, 2, (PPT > 2 ? 2 : PPT), true>(p, src, d_out, d_partial, n_partial, s)
-                  : launch_tab_inst<H, CPLX, 512, 2, (PPT > 2 ? 2 : PPT), false>(p, src, d_out, d_partial, n_partial, s);
-    default:
-      return aos2 ? launch_tab_inst<H, CPLX, 512, 1, PPT, true>(p, src, d_out, d_partial, n_partial, s)
-                  : launch_tab_inst<H, CPLX, 512, 1, PPT, false>(p, src, d_out, d_partial, n_partial, s);
-  }
+  int bits = 0;
+  for (int g = 0; g < p->ctab.n_groups; ++g) bits += p->ctab.gbits[g];
+  const bool w2 = bits > 64;
+  if (aos2) return w2 ? launch_tab_variant<H, CPLX, PPT, true, true>(p, src, d_out, d_partial, n_partial, s)
+                      : launch_tab_variant<H, CPLX, PPT, true, false>(p, src, d_out, d_partial, n_partial, s);
+  return w2 ? launch_tab_variant<H, CPLX, PPT, false, true>(p, src, d_out, d_partial, n_partial, s)
+            : launch_tab_variant<H, CPLX, PPT, false, false>(p, src, d_out, d_partial, n_partial, s);
 }
 
 int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
@@ -564,12 +575,12 @@ int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* 
   }
   const ChainTabDev& c = p->ctab;
   if (!c.cplx) {
-    if (c.H == 1) return launch_tab_variant<1, false, 4>(p, src, d_out, d_partial, n_partial, s);
-    if (c.H == 2) return launch_tab_variant<2, false, 4>(p, src, d_out, d_partial, n_partial, s);
-    if (c.H == 4) return launch_tab_variant<4, false, 2>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 1) return launch_tab_shape<1, false, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 2) return launch_tab_shape<2, false, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 4) return launch_tab_shape<4, false, 2>(p, src, d_out, d_partial, n_partial, s);
   } else {
-    if (c.H == 1) return launch_tab_variant<1, true, 4>(p, src, d_out, d_partial, n_partial, s);
-    if (c.H == 2) return launch_tab_variant<2, true, 2>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 1) return launch_tab_shape<1, true, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 2) return launch_tab_shape<2, true, 2>(p, src, d_out, d_partial, n_partial, s);
   }
   set_error("table kernel: unsupported bond dimension");
   return TTN_ERR_UNSUPPORTED;

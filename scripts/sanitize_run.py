@@ -17,6 +17,10 @@ g = t.named_binary_tree(4)
 ws = g.vertices()[1:]
 sb = t.continuous_siteinds(g, [ws[i::3] for i in range(3)])
 nets.append(("bintree chi20 (tree)", t.rand_itn(sb, link_space=20, rng=5, normalise=True), 3, 700))
+s2 = t.continuous_siteinds(t.named_grid((30, 1)), map_dimension=2)
+nets.append(("mps chi2 (table)", t.rand_itn(s2, link_space=2, rng=6, normalise=True), 2, 5000))
+sc = t.complex_continuous_siteinds(t.named_grid((12, 1)), map_dimension=2)
+nets.append(("complex mps chi2, 2 site indices per vertex (table)", t.rand_itn(sc, link_space=2, rng=7, eltype=complex, normalise=True), 4, 3000))
 skip = os.environ.get('SAN_SKIP', '')
 only = os.environ.get('SAN_ONLY', '')
 # default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
