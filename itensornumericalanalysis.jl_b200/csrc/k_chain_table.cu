@@ -26,15 +26,32 @@ namespace ttn {
 
 // ------------------------------------------------------------------------------ device side
 
+// Table entries of C = 2, 4 or 8 16-byte chunks (H x H matrices, wide vectors): entry s starts at bank group
+// (s C) mod 8, so chunk j of EVERY entry would sit in the same few banks and the lanes of a quarter-warp —
+// which read chunk j of different entries at once — would serialise (measured: 128-byte entries ran 3x
+// slower than the conflict model predicts).  Chunk j is therefore stored at position j ^ x(s), with x taken
+// from the entry-index bits just above those that pick the start group: a random s then spreads every
+// chunk over all 8 bank groups.  Same function on the host (image builder) and the device.
 template <int N>
-__device__ __forceinline__ void lds_vec(uint32_t addr, double (&dst)[N]) {
+__host__ __device__ __forceinline__ uint32_t entry_swizzle(uint32_t s) {
+  constexpr int C = N / 2;
+  if constexpr (C <= 1) return 0u;
+  else if constexpr (C == 2) return (s >> 2) & 1u;
+  else if constexpr (C == 4) return (s >> 1) & 3u;
+  else return s & 7u;
+}
+
+// dst = entry s (N doubles) of the table at shared address `base` (128-byte aligned)
+template <int N>
+__device__ __forceinline__ void lds_entry(uint32_t base, uint32_t s, double (&dst)[N]) {
   if constexpr (N == 1) {
-    dst[0] = lds64(addr);
+    dst[0] = lds64(base + s * 8u);
   } else {
-    static_assert(N % 2 == 0, "vector length");
+    static_assert(N % 2 == 0 && N <= 16, "entry length");
+    const uint32_t a = (base + s * (uint32_t)(N * 8)) ^ (entry_swizzle<N>(s) << 4); // entry-aligned: + == ^
 #pragma unroll
     for (int i = 0; i < N / 2; ++i) {
-      const double2 t = lds128(addr + 16u * i);
+      const double2 t = lds128(a ^ (16u * i));
       dst[2 * i] = t.x;
       dst[2 * i + 1] = t.y;
     }
@@ -54,7 +71,7 @@ __global__ void __launch_bounds__(NT, MINB)
     chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                        double* __restrict__ partial, int do_sum) {
   constexpr int E = CPLX ? 2 : 1, HE = H * E, MM = H * H * E;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NT / 32];
   __shared__ Digit2 s_d2[kFeMaxSites];
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
@@ -162,23 +179,27 @@ __global__ void __launch_bounds__(NT, MINB)
       }
     }
 
-    auto take = [&](int k, int lb) -> uint32_t {
-      const uint32_t s = (uint32_t)(w0[k] & ((1ull << lb) - 1ull));
+    // slice index of the group at stream offset `off` (lb bits): one funnel shift + mask on a one-word
+    // stream; the two-word stream is consumed by shifting (groups are visited in stream order)
+    auto take = [&](int k, int off, int lb) -> uint32_t {
       if constexpr (W2) {
+        const uint32_t s = (uint32_t)w0[k] & ((1u << lb) - 1u);
         w0[k] = (w0[k] >> lb) | (w1[k] << (64 - lb));
         w1[k] >>= lb;
+        return s;
       } else {
-        w0[k] >>= lb;
+        return (uint32_t)(w0[k] >> off) & ((1u << lb) - 1u);
       }
-      return s;
     };
+    int off = 0;
     // ---- leaf group
     double v[PPT][HE];
     {
       const int lb = ct.gbits[0];
       const uint32_t base = sbase + 8u * (uint32_t)ct.goff[0];
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) lds_vec<HE>(base + take(k, lb) * (uint32_t)(HE * 8), v[k]);
+      for (int k = 0; k < PPT; ++k) lds_entry<HE>(base, take(k, off, lb), v[k]);
+      off += lb;
     }
     // ---- middle groups: v <- v * M[s]
     for (int g = 1; g < G - 1; ++g) {
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         double m[MM], a[HE];
-        lds_vec<MM>(base + take(k, lb) * (uint32_t)(MM * 8), m);
+        lds_entry<MM>(base, take(k, off, lb), m);
 #pragma unroll
         for (int j = 0; j < HE; ++j) a[j] = 0.0;
         if constexpr (!CPLX) {
@@ -210,6 +231,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
         for (int j = 0; j < HE; ++j) v[k][j] = a[j];
       }
+      off += lb;
     }
     // ---- root group: out = v . R[s]
     {
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         double r[HE];
-        lds_vec<HE>(base + take(k, lb) * (uint32_t)(HE * 8), r);
+        lds_entry<HE>(base, take(k, off, lb), r);
         double o0 = 0.0, o1 = 0.0;
         if constexpr (!CPLX) {
 #pragma unroll
@@ -238,7 +260,7 @@ __global__ void __launch_bounds__(NT, MINB)
             if (CPLX) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
             else out[p] = o0;
           }
-          accumulate_point(src, p, o0, o1, sum_re, sum_im);
+          if (do_sum) accumulate_point(src, p, o0, o1, sum_re, sum_im);
         }
       }
     }
@@ -348,7 +370,8 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
         if (rem < 2 * bits0) break;
         const int gL = ((rem / bits0 + 1) / 2) * bits0, gR = rem - gL;
         if (gL > 16 || gR < bits0) continue;
-        const size_t size = (((size_t)1 << gL) + ((size_t)1 << gR)) * ev + (size_t)(G - 2) * ((size_t)1 << tm) * em;
+        const size_t size = (((size_t)1 << gL) + ((size_t)1 << gR)) * ev + (size_t)(G - 2) * ((size_t)1 << tm) * em +
+                            (size_t)G * 15; // + alignment padding
         if (size <= budget && (gb.empty() || size < best)) {
           best = size;
           gb.assign(G, tm);
@@ -386,7 +409,7 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
   for (int g = 0; g < G; ++g) {
     out->goff[g] = (int)total;
     total += ((size_t)1 << gb[g]) * ((g == 0 || g == G - 1) ? ev : em);
-    total = (total + 1) & ~(size_t)1; // 16-byte alignment of every table
+    total = (total + 15) & ~(size_t)15; // 128-byte alignment of every table (entry_swizzle, bank groups)
   }
   out->image.assign(total, 0.0);
   double flops = 0.0;
@@ -429,8 +452,12 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
         for (int j = 0; j < cols; ++j) {
           const cld x = cur[(s * rows + r) * cols + j];
           const size_t at = is_leaf ? (size_t)j : (is_root ? (size_t)r : (size_t)r * H + j);
-          dst[s * esz + at * E] = (double)x.re;
-          if (cplx) dst[s * esz + at * E + 1] = (double)x.im;
+          // element e of the entry lives in 16-byte chunk e / 2, stored at chunk position (e / 2) ^ swizzle(s)
+          const uint32_t sw = esz == 16 ? entry_swizzle<16>((uint32_t)s) : esz == 8 ? entry_swizzle<8>((uint32_t)s)
+                              : esz == 4 ? entry_swizzle<4>((uint32_t)s) : 0u;
+          auto put = [&](size_t e, double val) { dst[s * esz + (((e >> 1) ^ sw) << 1) + (e & 1)] = val; };
+          put(at * E, (double)x.re);
+          if (cplx) put(at * E + 1, (double)x.im);
         }
     if (!is_leaf) flops += (cplx ? 8.0 : 2.0) * rows * cols;
     c0 += k;
@@ -543,11 +570,14 @@ static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
 template <int H, bool CPLX, int PPT, bool AOS2, bool W2>
 static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                               cudaStream_t s) {
-  // TTN_TABLE_VARIANT (read at plan creation): 0 = 512 threads x PPT points (what the bench runs),
-  // 1 = 1024 threads x <= 2 points; one persistent CTA per SM either way
+  // TTN_TABLE_VARIANT (read at plan creation; one persistent CTA per SM in every variant):
+  //   0 = 1024 threads x <= 2 points per tile (what the bench runs: measured 13-25 % faster than 1),
+  //   1 = 512 threads x PPT points, 2 = 1024 threads x PPT points
   if (p->ctab_variant == 1)
-    return launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
-  return launch_tab_inst<H, CPLX, 512, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+    return launch_tab_inst<H, CPLX, 512, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+  if (p->ctab_variant == 2)
+    return launch_tab_inst<H, CPLX, 1024, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+  return launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
 }
 
 template <int H, bool CPLX, int PPT>

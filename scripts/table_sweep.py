@@ -7,16 +7,16 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200"), ("1", "200"), ("0", "100"), ("2", "100"), ("2", "48"), ("0", "48")]
+SWEEP = [("0", "200"), ("1", "200"), ("2", "200"), ("0", "64")]
 
 
 def run(name, f, ncol):
     x = torch.rand((npts, ncol), dtype=torch.float64, device="cuda:0")
     ref = None
-    for variant, kb in SWEEP + [("chain", "")]:
+    for variant, kb in SWEEP + [("chain", ""), ("dmma", "")]:
         kernel = "table"
-        if variant == "chain":
-            kernel = "chain"
+        if variant in ("chain", "dmma"):
+            kernel = variant
         else:
             os.environ["TTN_TABLE_VARIANT"], os.environ["TTN_TABLE_KB"] = variant, kb
         f._plans.clear()

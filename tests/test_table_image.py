@@ -41,6 +41,10 @@ def walk(im, digits):
     def entry(g, s, shape):
         n = int(np.prod(shape)) * E
         raw = im["image"][im["goff"][g] + s * n: im["goff"][g] + (s + 1) * n]
+        c = n // 2                       # 16-byte chunks; chunk j is stored at position j ^ swizzle(s)
+        if c >= 2:
+            sw = {2: (s >> 2) & 1, 4: (s >> 1) & 3, 8: s & 7}[c]
+            raw = raw.reshape(c, 2)[[j ^ sw for j in range(c)]].reshape(-1)
         return (raw[0::2] + 1j * raw[1::2]).reshape(shape) if E == 2 else raw.reshape(shape)
 
     out = []
@@ -92,7 +96,7 @@ def test_table_image_walk_matches_oracle(case):
     im = table_image(packed, kb)
     assert im is not None, name
     assert sum(im["gbits"]) == packed.n_vertices * im["bits0"]
-    assert im["image"].size * 8 <= kb * 1024 and all(o % 2 == 0 for o in im["goff"])
+    assert im["image"].size * 8 <= kb * 1024 and all(o % 16 == 0 for o in im["goff"])
     rng = np.random.default_rng(3)
     nc = packed.n_coords
     pts = np.concatenate([rng.random((300, nc)), cases.edge_points(20, nc, rng, 0)])
