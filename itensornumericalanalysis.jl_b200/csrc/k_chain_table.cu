@@ -66,7 +66,9 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
 
 // W2: the packed slice stream needs its second 64-bit word (more than 64 slice bits); chains of up to 64
 // bits (config 2's layout: 2 x 30) keep the stream in one register pair and shift half as much.
-template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2, bool W2>
+// NCV: coordinates fetched with vector loads one tile ahead — 2: 2-D AoS input (one 128-bit load per point),
+// 1: 1-D input (one 64-bit load per point), 0: any layout / grid generator / index-setting mode (load_coord).
+template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2>
 __global__ void __launch_bounds__(NT, MINB)
     chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                        double* __restrict__ partial, int do_sum) {
@@ -102,20 +104,25 @@ __global__ void __launch_bounds__(NT, MINB)
   // K1 for coordinate slot c of the PPT points of this thread (same arithmetic as compute_words of
   // the team-sorted kernel): run fast path or the tabulated greedy loop, bits OR-ed into the stream
   uint64_t w0[PPT], w1[PPT];
+  // Domain violations (x < 0, NaN: the reference's loop never terminates) are only FLAGGED here — one atomic
+  // per thread at the end of the kernel; the call then fails with TTN_ERR_DOMAIN.  Such an x yields digit 0
+  // everywhere (the compares are false, the conversion saturates at 0), so no table index goes out of range.
+  bool bad = false;
   auto add_coord = [&](int c, double (&x)[PPT], int64_t p0) {
 #pragma unroll
-    for (int k = 0; k < PPT; ++k)
-      if (!coord_in_domain(x[k])) {
-        atomicOr(err, 1);
-        x[k] = 0.0;
-      }
+    for (int k = 0; k < PPT; ++k) bad = bad || !coord_in_domain(x[k]);
     if (ct.run_L[c] > 0 && !src.digits) {
       const int L = ct.run_L[c], plow = ct.run_plow[c];
       const double scale = ct.run_scale[c];
       const bool rev = ct.run_rev[c] != 0;
+      // x >= 1 saturates to all ones.  For L <= 53 a clamp does it: (1 - 2^-53) 2^L = 2^L - 2^(L-53) truncates
+      // to 2^L - 1, and every x < 1 is <= 1 - 2^-53 already (one DMNMX instead of a compare and two selects).
+      const bool clamp = L <= 53;
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
-        unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
+        unsigned long long q;
+        if (clamp) q = (unsigned long long)(fmin(x[k], 0x1.fffffffffffffp-1) * scale);
+        else q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
         if (rev) q = __brevll(q) >> (64 - L);
         if (plow < 64) {
           w0[k] += q << plow;
@@ -141,32 +148,35 @@ __global__ void __launch_bounds__(NT, MINB)
       }
     }
   };
-  // 2-D AoS input: one 128-bit load per point, issued one tile ahead
-  double2 xnext[AOS2 ? PPT : 1];
-  auto fetch_aos2 = [&](int64_t tile_) {
+  // vector coordinate loads, issued one tile ahead
+  double2 xnext[NCV ? PPT : 1];
+  auto fetch_next = [&](int64_t tile_) {
 #pragma unroll
-    for (int k = 0; k < (AOS2 ? PPT : 1); ++k) {
+    for (int k = 0; k < (NCV ? PPT : 1); ++k) {
       const int64_t p = tile_ * TILE + (int64_t)k * NT + tid;
       xnext[k] = make_double2(0.0, 0.0);
-      if (tile_ < n_tiles && p < src.npts) xnext[k] = ldg_nc_f64x2(src.coords + 2 * p);
+      if (tile_ < n_tiles && p < src.npts) {
+        if constexpr (NCV == 2) xnext[k] = ldg_nc_f64x2(src.coords + 2 * p);
+        else xnext[k].x = __ldg(src.coords + p);
+      }
     }
   };
-  if (AOS2) fetch_aos2(blockIdx.x);
+  if (NCV) fetch_next(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t p0 = tile * TILE + tid; // point k of this thread: p0 + k * NT
 #pragma unroll
     for (int k = 0; k < PPT; ++k) w0[k] = w1[k] = 0;
-    if (AOS2) {
+    if (NCV) {
       double xa[PPT], xb[PPT];
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         xa[k] = xnext[k].x;
         xb[k] = xnext[k].y;
       }
-      fetch_aos2(tile + gridDim.x);
+      fetch_next(tile + gridDim.x);
       add_coord(0, xa, p0);
-      add_coord(1, xb, p0);
+      if (NCV == 2) add_coord(1, xb, p0);
     } else {
       for (int c = 0; c < dg.n_coords; ++c) {
         double x[PPT];
@@ -234,6 +244,7 @@ __global__ void __launch_bounds__(NT, MINB)
       off += lb;
     }
     // ---- root group: out = v . R[s]
+    double res[PPT][2];
     {
       const int lb = ct.gbits[G - 1];
       const uint32_t base = sbase + 8u * (uint32_t)ct.goff[G - 1];
@@ -254,17 +265,29 @@ __global__ void __launch_bounds__(NT, MINB)
             o1 = fma(v[k][2 * i + 1], r[2 * i], o1);
           }
         }
+        res[k][0] = o0;
+        res[k][1] = o1;
+      }
+    }
+    if (out) {
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
         const int64_t p = p0 + (int64_t)k * NT;
         if (p < src.npts) {
-          if (out) {
-            if (CPLX) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
-            else out[p] = o0;
-          }
-          if (do_sum) accumulate_point(src, p, o0, o1, sum_re, sum_im);
+          if (CPLX) reinterpret_cast<double2*>(out)[p] = make_double2(res[k][0], res[k][1]);
+          else out[p] = res[k][0];
         }
       }
     }
+    if (do_sum) {
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int64_t p = p0 + (int64_t)k * NT;
+        if (p < src.npts) accumulate_point(src, p, res[k][0], res[k][1], sum_re, sum_im);
+      }
+    }
   }
+  if (bad) atomicOr(err, 1);
 
   if (do_sum) {
     // deterministic: fixed-order shuffle tree per warp, then thread 0 adds the warp partials in order
@@ -548,12 +571,12 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   return TTN_OK;
 }
 
-template <int H, bool CPLX, int NT, int MINB, int PPT, bool AOS2, bool W2>
+template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2>
 static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                            cudaStream_t s) {
   const ChainTabDev& c = p->ctab;
   const size_t smem = (size_t)c.total_doubles * 8;
-  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, AOS2, W2>;
+  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, NCV, W2>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   TTN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -567,31 +590,33 @@ static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
   return TTN_OK;
 }
 
-template <int H, bool CPLX, int PPT, bool AOS2, bool W2>
+template <int H, bool CPLX, int PPT, int NCV, bool W2>
 static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                               cudaStream_t s) {
-  // TTN_TABLE_VARIANT (read at plan creation; one persistent CTA per SM in every variant):
-  //   0 = 1024 threads x <= 2 points per tile (what the bench runs: measured 13-25 % faster than 1),
-  //   1 = 512 threads x PPT points, 2 = 1024 threads x PPT points
+  // One persistent CTA of 1024 threads per SM, PPT points per thread and tile (64 registers per thread; measured
+  // 13-25 % faster than 512 threads with twice the points).  TTN_TABLE_VARIANT=1 (read at plan creation) runs
+  // the 512-thread shape for experiments.
   if (p->ctab_variant == 1)
-    return launch_tab_inst<H, CPLX, 512, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
-  if (p->ctab_variant == 2)
-    return launch_tab_inst<H, CPLX, 1024, 1, PPT, AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
-  return launch_tab_inst<H, CPLX, 1024, 1, (PPT > 2 ? 2 : PPT), AOS2, W2>(p, src, d_out, d_partial, n_partial, s);
+    return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2>(p, src, d_out, d_partial, n_partial, s);
+  return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2>(p, src, d_out, d_partial, n_partial, s);
 }
 
 template <int H, bool CPLX, int PPT>
 static int launch_tab_shape(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                             cudaStream_t s) {
-  const bool aos2 = !src.digits && !src.grid && src.coords && src.layout == TTN_LAYOUT_AOS && src.n_coords == 2 &&
-                    (reinterpret_cast<uintptr_t>(src.coords) & 15u) == 0;
+  const bool vec = !src.digits && !src.grid && src.coords;
+  const bool aos2 = vec && src.layout == TTN_LAYOUT_AOS && src.n_coords == 2 && (reinterpret_cast<uintptr_t>(src.coords) & 15u) == 0;
+  const bool one = vec && src.n_coords == 1;
   int bits = 0;
   for (int g = 0; g < p->ctab.n_groups; ++g) bits += p->ctab.gbits[g];
   const bool w2 = bits > 64;
-  if (aos2) return w2 ? launch_tab_variant<H, CPLX, PPT, true, true>(p, src, d_out, d_partial, n_partial, s)
-                      : launch_tab_variant<H, CPLX, PPT, true, false>(p, src, d_out, d_partial, n_partial, s);
-  return w2 ? launch_tab_variant<H, CPLX, PPT, false, true>(p, src, d_out, d_partial, n_partial, s)
-            : launch_tab_variant<H, CPLX, PPT, false, false>(p, src, d_out, d_partial, n_partial, s);
+#define TTN_TAB_GO(NCV_)                                                                                    \
+  return w2 ? launch_tab_variant<H, CPLX, PPT, NCV_, true>(p, src, d_out, d_partial, n_partial, s)         \
+            : launch_tab_variant<H, CPLX, PPT, NCV_, false>(p, src, d_out, d_partial, n_partial, s)
+  if (aos2) TTN_TAB_GO(2);
+  if (one) TTN_TAB_GO(1);
+  TTN_TAB_GO(0);
+#undef TTN_TAB_GO
 }
 
 int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
@@ -606,10 +631,10 @@ int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* 
   const ChainTabDev& c = p->ctab;
   if (!c.cplx) {
     if (c.H == 1) return launch_tab_shape<1, false, 4>(p, src, d_out, d_partial, n_partial, s);
-    if (c.H == 2) return launch_tab_shape<2, false, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 2) return launch_tab_shape<2, false, 2>(p, src, d_out, d_partial, n_partial, s);
     if (c.H == 4) return launch_tab_shape<4, false, 2>(p, src, d_out, d_partial, n_partial, s);
   } else {
-    if (c.H == 1) return launch_tab_shape<1, true, 4>(p, src, d_out, d_partial, n_partial, s);
+    if (c.H == 1) return launch_tab_shape<1, true, 2>(p, src, d_out, d_partial, n_partial, s);
     if (c.H == 2) return launch_tab_shape<2, true, 2>(p, src, d_out, d_partial, n_partial, s);
   }
   set_error("table kernel: unsupported bond dimension");

@@ -7,7 +7,7 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200"), ("1", "200"), ("2", "200"), ("0", "64")]
+SWEEP = [("0", "200"), ("1", "200")]
 
 
 def run(name, f, ncol):
