@@ -11,7 +11,7 @@
 //     root group  -> 2^gR column vectors   out = v . Rt[s_last]
 // sized so that ALL tables of the chain sit in the shared memory of one CTA (<= 200 KB).  The
 // kernel is one persistent CTA per SM: tables are loaded once, then every thread streams PPT
-// points per tile — coordinates with coalesced (128-bit for 2-D AoS input) loads prefetched one
+// points per tile — coordinates with coalesced (128-bit for 2-D AoS input) loads issued one
 // tile ahead, K1 (k_digits.cuh semantics; the exact floor(x 2^L) run fast path for binary digits on
 // consecutive vertices) into a 128-bit packed slice stream, one table lookup per group with the
 // state in registers, one coalesced store.  A 60-bit chi = 1 chain costs 5 shared-memory lookups
@@ -68,7 +68,8 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
 // bits (config 2's layout: 2 x 30) keep the stream in one register pair and shift half as much.
 // NCV: coordinates fetched with vector loads one tile ahead — 2: 2-D AoS input (one 128-bit load per point),
 // 1: 1-D input (one 64-bit load per point), 0: any layout / grid generator / index-setting mode (load_coord).
-template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2>
+// REP (chi = 1 only): tables in the replicated, conflict-free layout (make_table_image).
+template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2, bool REP>
 __global__ void __launch_bounds__(NT, MINB)
     chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
                        double* __restrict__ partial, int do_sum) {
@@ -95,8 +96,22 @@ __global__ void __launch_bounds__(NT, MINB)
   }
   __syncthreads();
 
-  const uint32_t sbase = smem_u32(smem);
+  // REP: this lane's copy inside every 128-byte line
+  const uint32_t sbase = smem_u32(smem) + (REP ? (CPLX ? (uint32_t)(lane & 7) * 16u : (uint32_t)(lane & 15) * 8u) : 0u);
   const int G = ct.n_groups;
+  auto entry = [&](uint32_t base, uint32_t s, auto& dst) {
+    constexpr int N = sizeof(dst) / sizeof(double);
+    if constexpr (REP) {
+      if constexpr (N == 1) dst[0] = lds64(base + (s << 7));
+      else {
+        const double2 t = lds128(base + (s << 7));
+        dst[0] = t.x;
+        dst[1] = t.y;
+      }
+    } else {
+      lds_entry<N>(base, s, dst);
+    }
+  };
   constexpr int64_t TILE = (int64_t)NT * PPT;
   const int64_t n_tiles = (src.npts + TILE - 1) / TILE;
   double sum_re = 0.0, sum_im = 0.0;
@@ -208,7 +223,7 @@ __global__ void __launch_bounds__(NT, MINB)
       const int lb = ct.gbits[0];
       const uint32_t base = sbase + 8u * (uint32_t)ct.goff[0];
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) lds_entry<HE>(base, take(k, off, lb), v[k]);
+      for (int k = 0; k < PPT; ++k) entry(base, take(k, off, lb), v[k]);
       off += lb;
     }
     // ---- middle groups: v <- v * M[s]
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         double m[MM], a[HE];
-        lds_entry<MM>(base, take(k, off, lb), m);
+        entry(base, take(k, off, lb), m);
 #pragma unroll
         for (int j = 0; j < HE; ++j) a[j] = 0.0;
         if constexpr (!CPLX) {
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         double r[HE];
-        lds_entry<HE>(base, take(k, off, lb), r);
+        entry(base, take(k, off, lb), r);
         double o0 = 0.0, o1 = 0.0;
         if constexpr (!CPLX) {
 #pragma unroll
@@ -335,13 +350,14 @@ int variant_from_env() { return getenv("TTN_TABLE_VARIANT") ? atoi(getenv("TTN_T
 // ttn_debug_table_image, which the CPU tests walk with numpy against an independent contraction).
 struct TableImage {
   int H = 0, cplx = 0, bits0 = 0, n = 0;
+  int rep = 0;                     // 1: chi = 1 tables replicated per lane (conflict-free layout)
   std::vector<int> gbits, goff;    // stream bits / offset (doubles) per group; group 0 = leaf, last = root
   std::vector<double> image;
   std::vector<int> pos_of;         // chain position of every vertex (0 = leaf)
   double flops_exec = 0.0;
 };
 
-static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage* out) {
+static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_rep, TableImage* out) {
   const int n = d->n_vertices;
   const bool cplx = d->is_complex != 0;
   const int NC = cplx ? 2 : 1;
@@ -406,6 +422,34 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
     }
     if (gb.empty()) return false;
   }
+  // chi = 1 (every entry is one real or complex number): the lookups of a warp hit random banks — measured 6.35
+  // wavefronts per LDS.64 against the conflict-free 2, which made the kernel LSU-bound at 80 % of the HBM
+  // roofline.  Replicated layout: a table is stored once per lane of a half-warp (8-byte entries, 16 copies) or
+  // quarter-warp (16-byte entries, 8 copies), entry s of copy c at byte 128 s + 8 (16) c, so lane l always reads
+  // bank group (l mod 16 | 8) and NO lookup conflicts.  A table then costs 2^bits x 128 bytes, so groups shrink to
+  // 6..9 bits and a point takes more (but 3x cheaper) lookups: used when it at most doubles the group count.
+  bool rep = false;
+  if (allow_rep && H == 1) {
+    const size_t units = budget_bytes / 128;
+    const int npos = B / bits0;
+    for (int Gr = 2; Gr <= kTabMaxGroups; ++Gr) {
+      if (Gr > npos) break;
+      std::vector<int> cand(Gr);
+      size_t size = 0;
+      bool ok = true;
+      for (int g = 0; g < Gr; ++g) { // bits as even as possible, the larger groups first
+        cand[g] = (npos / Gr + (g < npos % Gr ? 1 : 0)) * bits0;
+        ok = ok && cand[g] <= 16;
+        size += (size_t)1 << cand[g];
+      }
+      if (!ok || size > units) continue;
+      if (Gr <= 2 * (int)gb.size() && cand[0] >= 7) {
+        gb = cand;
+        rep = true;
+      }
+      break;
+    }
+  }
   const int G = (int)gb.size();
 
   // ---- per-position matrices
@@ -431,7 +475,7 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
   size_t total = 0;
   for (int g = 0; g < G; ++g) {
     out->goff[g] = (int)total;
-    total += ((size_t)1 << gb[g]) * ((g == 0 || g == G - 1) ? ev : em);
+    total += ((size_t)1 << gb[g]) * (rep ? (size_t)16 : ((g == 0 || g == G - 1) ? ev : em));
     total = (total + 15) & ~(size_t)15; // 128-byte alignment of every table (entry_swizzle, bank groups)
   }
   out->image.assign(total, 0.0);
@@ -479,6 +523,13 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
           const uint32_t sw = esz == 16 ? entry_swizzle<16>((uint32_t)s) : esz == 8 ? entry_swizzle<8>((uint32_t)s)
                               : esz == 4 ? entry_swizzle<4>((uint32_t)s) : 0u;
           auto put = [&](size_t e, double val) { dst[s * esz + (((e >> 1) ^ sw) << 1) + (e & 1)] = val; };
+          if (rep) { // H = 1: 16 / E copies of the entry in one 128-byte line
+            for (int c = 0; c < 16 / E; ++c) {
+              dst[s * 16 + (size_t)c * E] = (double)x.re;
+              if (cplx) dst[s * 16 + (size_t)c * E + 1] = (double)x.im;
+            }
+            continue;
+          }
           put(at * E, (double)x.re);
           if (cplx) put(at * E + 1, (double)x.im);
         }
@@ -486,6 +537,7 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, TableImage*
     c0 += k;
   }
   out->H = H;
+  out->rep = rep ? 1 : 0;
   out->cplx = cplx ? 1 : 0;
   out->bits0 = bits0;
   out->n = n;
@@ -505,12 +557,14 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   if (!p->is_chain || !p->all_base2) return TTN_OK;
   TableImage im;
   p->ctab_variant = variant_from_env();
-  if (!make_table_image(d, table_budget_bytes(p->ctab_variant), &im)) return TTN_OK;
+  const bool allow_rep = !(getenv("TTN_TABLE_REP") && atoi(getenv("TTN_TABLE_REP")) == 0);
+  if (!make_table_image(d, table_budget_bytes(p->ctab_variant), allow_rep, &im)) return TTN_OK;
   ChainTabDev& c = p->ctab;
   c = ChainTabDev{};
   c.n_groups = (int)im.gbits.size();
   c.H = im.H;
   c.cplx = im.cplx;
+  c.rep = im.rep;
   c.total_doubles = (int)im.image.size();
   for (int g = 0; g < c.n_groups; ++g) {
     c.gbits[g] = im.gbits[g];
@@ -571,12 +625,12 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   return TTN_OK;
 }
 
-template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2>
+template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2, bool REP>
 static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                            cudaStream_t s) {
   const ChainTabDev& c = p->ctab;
   const size_t smem = (size_t)c.total_doubles * 8;
-  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, NCV, W2>;
+  auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, NCV, W2, REP>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   TTN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -593,12 +647,19 @@ static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, d
 template <int H, bool CPLX, int PPT, int NCV, bool W2>
 static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                               cudaStream_t s) {
-  // One persistent CTA of 1024 threads per SM, PPT points per thread and tile (64 registers per thread; measured
-  // 13-25 % faster than 512 threads with twice the points).  TTN_TABLE_VARIANT=1 (read at plan creation) runs
-  // the 512-thread shape for experiments.
+  // One persistent CTA per SM: 512 threads x 2 PPT points per thread and tile (up to 128 registers: 8 points
+  // in flight per thread for chi = 1; measured 5-10 % faster than 1024 threads x PPT points, which
+  // TTN_TABLE_VARIANT=1 — read at plan creation — still runs for experiments).
+  if constexpr (H == 1) {
+    if (p->ctab.rep) {
+      if (p->ctab_variant == 1)
+        return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
+      return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
+    }
+  }
   if (p->ctab_variant == 1)
-    return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2>(p, src, d_out, d_partial, n_partial, s);
-  return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2>(p, src, d_out, d_partial, n_partial, s);
+    return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, false>(p, src, d_out, d_partial, n_partial, s);
+  return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, false>(p, src, d_out, d_partial, n_partial, s);
 }
 
 template <int H, bool CPLX, int PPT>
@@ -643,7 +704,7 @@ int launch_chain_table(ttn_plan* p, Stream& st, const CoordSource& src, double* 
 
 // Debug / test hook (not part of the ABI in include/ttneval.h; no CUDA calls): the table image of a
 // description, so that CPU tests can walk it against an independent contraction.
-//   meta[0..7] = {applicable, H, is_complex, bits0, n_groups, total_doubles, 0, 0}; meta[8 + g] = gbits[g],
+//   meta[0..7] = {applicable, H, is_complex, bits0, n_groups, total_doubles, replicated layout, 0}; meta[8 + g] = gbits[g],
 //   meta[8 + 16 + g] = goff[g]; site_bitpos[s] = stream bit of site index s (stride included).
 int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, double* image, int64_t image_cap,
                       int32_t* site_bitpos) {
@@ -651,7 +712,9 @@ int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, doubl
   for (int i = 0; i < 8 + 2 * kTabMaxGroups; ++i) meta[i] = 0;
   bool base2 = true;
   for (int s = 0; s < d->n_sites; ++s) base2 = base2 && d->site_dim[s] == 2;
-  if (!base2 || !make_table_image(d, (size_t)budget_kb * 1024, &im)) return TTN_OK;
+  const bool allow_rep = budget_kb >= 0;
+  if (budget_kb < 0) budget_kb = -budget_kb; // negative budget: plain layout only
+  if (!base2 || !make_table_image(d, (size_t)budget_kb * 1024, allow_rep, &im)) return TTN_OK;
   if ((int64_t)im.image.size() > image_cap) {
     set_error("debug_table_image: image buffer too small");
     return TTN_ERR_INVALID;
@@ -662,6 +725,7 @@ int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, doubl
   meta[3] = im.bits0;
   meta[4] = (int)im.gbits.size();
   meta[5] = (int)im.image.size();
+  meta[6] = im.rep;
   for (size_t g = 0; g < im.gbits.size(); ++g) {
     meta[8 + g] = im.gbits[g];
     meta[8 + kTabMaxGroups + g] = im.goff[g];

@@ -133,6 +133,7 @@ struct ChainTabDev {
   int32_t n_groups;      // >= 2: group 0 = leaf vectors, last = root vectors, between: H x H matrices
   int32_t H;             // padded bond dimension (a complex entry counts once): 1, 2 or 4
   int32_t cplx;
+  int32_t rep;           // 1: chi = 1 tables replicated per lane (one 128-byte line per entry; conflict-free)
   int32_t total_doubles; // image size (even)
   int32_t gbits[kTabMaxGroups]; // stream bits consumed by the group (<= 16)
   int32_t goff[kTabMaxGroups];  // offset of the group's table in the image, in doubles (even)

@@ -7,18 +7,18 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200"), ("1", "200")]
+SWEEP = [("0", "200", "1"), ("1", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
 
 
 def run(name, f, ncol):
     x = torch.rand((npts, ncol), dtype=torch.float64, device="cuda:0")
     ref = None
-    for variant, kb in SWEEP + [("chain", ""), ("dmma", "")]:
+    for variant, kb, rep in SWEEP + [("chain", "", ""), ("dmma", "", "")]:
         kernel = "table"
         if variant in ("chain", "dmma"):
             kernel = variant
         else:
-            os.environ["TTN_TABLE_VARIANT"], os.environ["TTN_TABLE_KB"] = variant, kb
+            os.environ["TTN_TABLE_VARIANT"], os.environ["TTN_TABLE_KB"], os.environ["TTN_TABLE_REP"] = variant, kb, rep
         f._plans.clear()
         plan = f.plan()
         info = plan.info()
@@ -32,10 +32,11 @@ def run(name, f, ncol):
             ref = out.clone()
         dev = (out - ref[: out.numel()]).abs().max().item() / ref.abs().max().item()
         gbs = info["bytes_per_point"] * n / (best * 1e-3) / 1e9
-        print(f"{name:22s} kernel={kernel:5s} variant={variant:5s} kb={kb:3s} {n:.1e} pts {best:8.3f} ms "
+        print(f"{name:22s} kernel={kernel:5s} variant={variant:5s} kb={kb:3s} rep={rep:1s} {n:.1e} pts {best:8.3f} ms "
               f"{n / best / 1e6:8.2f} G pts/s {gbs:8.1f} GB/s  (max dev from first {dev:.1e})", flush=True)
     os.environ.pop("TTN_TABLE_VARIANT", None)
     os.environ.pop("TTN_TABLE_KB", None)
+    os.environ.pop("TTN_TABLE_REP", None)
     f._plans.clear()
 
 
@@ -44,5 +45,7 @@ s2 = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
 run("exp chi1 2x30", t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1), 2)
 run("rand chi2 2x30", t.rand_itn(s2, link_space=2, rng=20267, normalise=True), 2)
 run("rand chi4 2x30", t.rand_itn(s2, link_space=4, rng=20268, normalise=True), 2)
+sc = t.complex_continuous_siteinds(t.named_grid((30, 1)), map_dimension=1)
+run("complex chi1 1-D 2x30", t.rand_itn(sc, link_space=1, rng=20269, eltype=complex, normalise=True), 2)
 s1 = t.continuous_siteinds(t.named_grid((20, 1)))
 run("sin_qtt20 (cfg1 net)", t.sin_itn(s1, k=2.0, a=0.3, c=1.1), 1)

@@ -19,7 +19,7 @@ MAXG = 16
 def table_image(packed, budget_kb=200):
     L = _capi.lib()
     meta = (C.c_int32 * (8 + 2 * MAXG))()
-    cap = 1 << 16
+    cap = 1 << 17
     img = np.zeros(cap, dtype=np.float64)
     bitpos = np.zeros(max(len(packed.site_dim), 1), dtype=np.int32)
     rc = L.ttn_debug_table_image(C.byref(packed.desc()), budget_kb, meta, img.ctypes.data_as(C.c_void_p),
@@ -29,7 +29,7 @@ def table_image(packed, budget_kb=200):
     if not meta[0]:
         return None
     G = meta[4]
-    return dict(H=meta[1], cplx=meta[2], bits0=meta[3], gbits=meta[8:8 + G], goff=meta[8 + MAXG:8 + MAXG + G],
+    return dict(H=meta[1], cplx=meta[2], bits0=meta[3], rep=meta[6], gbits=meta[8:8 + G], goff=meta[8 + MAXG:8 + MAXG + G],
                 image=img[:meta[5]].copy(), bitpos=bitpos)
 
 
@@ -40,6 +40,10 @@ def walk(im, digits):
 
     def entry(g, s, shape):
         n = int(np.prod(shape)) * E
+        if im["rep"]:                    # chi = 1: 16 / E identical copies of the entry in one 128-byte line
+            line = im["image"][im["goff"][g] + s * 16: im["goff"][g] + (s + 1) * 16].reshape(16 // E, E)
+            assert (line == line[0]).all()
+            return (line[0, 0] + 1j * line[0, 1]) * np.ones(shape) if E == 2 else line[0, 0] * np.ones(shape)
         raw = im["image"][im["goff"][g] + s * n: im["goff"][g] + (s + 1) * n]
         c = n // 2                       # 16-byte chunks; chunk j is stored at position j ^ swizzle(s)
         if c >= 2:
@@ -86,6 +90,9 @@ def narrow_cases():
     sa = t.complex_continuous_siteinds(t.named_grid((10, 1)), [[(i, 1) for i in range(1, 11, 2)]],
                                        [[(i, 1) for i in range(2, 11, 2)]])
     out.append(("cplx_alt_chi2", t.rand_itn(sa, link_space=2, rng=10, eltype=complex, normalise=True), 8))
+    # chi = 1 with the plain (not replicated) layout: negative budget
+    out.append(("exp_comb2x30_plain", t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1), -200))
+    out.append(("cplx_2site_chi1_plain", t.rand_itn(sc, link_space=1, rng=9, eltype=complex, normalise=True), -16))
     return out
 
 
@@ -96,7 +103,8 @@ def test_table_image_walk_matches_oracle(case):
     im = table_image(packed, kb)
     assert im is not None, name
     assert sum(im["gbits"]) == packed.n_vertices * im["bits0"]
-    assert im["image"].size * 8 <= kb * 1024 and all(o % 16 == 0 for o in im["goff"])
+    assert im["image"].size * 8 <= abs(kb) * 1024 and all(o % 16 == 0 for o in im["goff"])
+    assert im["rep"] == (1 if (im["H"] == 1 and kb > 0 and name != "cplx_2site_chi1") else 0), (name, im["gbits"])
     rng = np.random.default_rng(3)
     nc = packed.n_coords
     pts = np.concatenate([rng.random((300, nc)), cases.edge_points(20, nc, rng, 0)])
