@@ -127,24 +127,42 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
     for (int k = 0; k < PPT; ++k) bad = bad || !coord_in_domain(x[k]);
     if (ct.run_L[c] > 0 && !src.digits) {
+      // digits = bits of floor(x 2^L), x >= 1 saturating to all ones (see build_chain_mma).  Every branch below
+      // is uniform and sits OUTSIDE the per-point loops.
       const int L = ct.run_L[c], plow = ct.run_plow[c];
       const double scale = ct.run_scale[c];
       const bool rev = ct.run_rev[c] != 0;
-      // x >= 1 saturates to all ones.  For L <= 53 a clamp does it: (1 - 2^-53) 2^L = 2^L - 2^(L-53) truncates
-      // to 2^L - 1, and every x < 1 is <= 1 - 2^-53 already (one DMNMX instead of a compare and two selects).
-      const bool clamp = L <= 53;
+      uint64_t q[PPT];
+      if (L <= 31) {
+        // 32-bit conversion: cvt.rzi.u32.f64 saturates (x 2^L >= 2^32 -> 0xffffffff, negative / NaN -> 0), so one
+        // unsigned min with 2^L - 1 gives the all-ones pattern of x >= 1; one 32-bit BREV where the run is reversed
+        const uint32_t qmax = (1u << L) - 1u;
+        const int rs = 32 - L;
+        if (rev) {
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        unsigned long long q;
-        if (clamp) q = (unsigned long long)(fmin(x[k], 0x1.fffffffffffffp-1) * scale);
-        else q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
-        if (rev) q = __brevll(q) >> (64 - L);
-        if (plow < 64) {
-          w0[k] += q << plow;
-          if (W2 && plow + L > 64) w1[k] += q >> (64 - plow);
-        } else if (W2) {
-          w1[k] += q << (plow - 64);
+          for (int k = 0; k < PPT; ++k) q[k] = __brev(min(__double2uint_rz(x[k] * scale), qmax)) >> rs;
+        } else {
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) q[k] = min(__double2uint_rz(x[k] * scale), qmax);
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          unsigned long long t = (unsigned long long)(x[k] * scale);
+          t = x[k] >= 1.0 ? ((1ull << L) - 1ull) : t;
+          q[k] = rev ? (__brevll(t) >> (64 - L)) : t;
+        }
+      }
+      if (plow < 64) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) w0[k] += q[k] << plow;
+        if (W2 && plow + L > 64) {
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) w1[k] += q[k] >> (64 - plow);
+        }
+      } else if (W2) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) w1[k] += q[k] << (plow - 64);
       }
     } else {
       for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
@@ -166,13 +184,22 @@ __global__ void __launch_bounds__(NT, MINB)
   // vector coordinate loads, issued one tile ahead
   double2 xnext[NCV ? PPT : 1];
   auto fetch_next = [&](int64_t tile_) {
+    const double* cp = src.coords + (NCV == 2 ? 2 : 1) * (tile_ * TILE + tid);
+    if ((tile_ + 1) * TILE <= src.npts) { // whole tile inside the batch: no per-point predicates
 #pragma unroll
-    for (int k = 0; k < (NCV ? PPT : 1); ++k) {
-      const int64_t p = tile_ * TILE + (int64_t)k * NT + tid;
-      xnext[k] = make_double2(0.0, 0.0);
-      if (tile_ < n_tiles && p < src.npts) {
-        if constexpr (NCV == 2) xnext[k] = ldg_nc_f64x2(src.coords + 2 * p);
-        else xnext[k].x = __ldg(src.coords + p);
+      for (int k = 0; k < (NCV ? PPT : 1); ++k) {
+        if constexpr (NCV == 2) xnext[k] = ldg_nc_f64x2(cp + 2 * k * NT);
+        else xnext[k] = make_double2(__ldg(cp + k * NT), 0.0);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (NCV ? PPT : 1); ++k) {
+        const int64_t p = tile_ * TILE + (int64_t)k * NT + tid;
+        xnext[k] = make_double2(0.0, 0.0);
+        if (tile_ < n_tiles && p < src.npts) {
+          if constexpr (NCV == 2) xnext[k] = ldg_nc_f64x2(cp + 2 * k * NT);
+          else xnext[k].x = __ldg(cp + k * NT);
+        }
       }
     }
   };
@@ -285,12 +312,21 @@ __global__ void __launch_bounds__(NT, MINB)
       }
     }
     if (out) {
+      const bool full = (tile + 1) * TILE <= src.npts;
+      double* op = out + (CPLX ? 2 : 1) * p0;
+      if (full) {
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int64_t p = p0 + (int64_t)k * NT;
-        if (p < src.npts) {
-          if (CPLX) reinterpret_cast<double2*>(out)[p] = make_double2(res[k][0], res[k][1]);
-          else out[p] = res[k][0];
+        for (int k = 0; k < PPT; ++k) {
+          if (CPLX) *reinterpret_cast<double2*>(op + 2 * k * NT) = make_double2(res[k][0], res[k][1]);
+          else op[k * NT] = res[k][0];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+          if (p0 + (int64_t)k * NT < src.npts) {
+            if (CPLX) *reinterpret_cast<double2*>(op + 2 * k * NT) = make_double2(res[k][0], res[k][1]);
+            else op[k * NT] = res[k][0];
+          }
         }
       }
     }

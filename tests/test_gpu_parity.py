@@ -649,3 +649,28 @@ def test_table_kernel_known_answer_at_scale(rep, variant, monkeypatch):
     xt = torch.floor(x[:, 0] * 2.0 ** 30) / 2.0 ** 30
     want = 1.2 * torch.exp(0.1 + 0.9 * xt)
     assert float(((out - want).abs() / want.abs()).max()) < 1e-12
+
+
+@pytest.mark.parametrize("which", ["rand_chi2_comb2x30", "exp_comb2x30", "rand_chi4_mps3d"])
+def test_table_kernel_digit_boundaries(which):
+    """The table kernel's K1 run path takes the digits of a coordinate as the bits of floor(x 2^L) through a
+    saturating 32-bit conversion (L <= 31).  Any digit mismatch changes the value by O(1): exercise the
+    boundaries of every digit, denormals, x >= 1, huge x, on a forward and a reversed run."""
+    f = _narrow_networks()[which]
+    plan = f.plan()
+    packed = plan.packed
+    nc, L = packed.n_coords, 30
+    xs = [0.0, -0.0, 5e-324, 2.0 ** -1074, 2.0 ** -31, 2.0 ** -30, np.nextafter(2.0 ** -30, 1), 1 - 2.0 ** -53,
+          1 - 2.0 ** -30, np.nextafter(1 - 2.0 ** -30, 0), 1.0, 1.0 + 2.0 ** -52, 7.25, 1e300, 4294967296.0, 0.1, 1 / 3, 2 / 3]
+    for k in range(1, L + 1):
+        xs += [2.0 ** -k, np.nextafter(2.0 ** -k, 0), np.nextafter(2.0 ** -k, 1), 1 - 2.0 ** -k]
+    xs = np.array(xs)
+    pts = np.stack([np.roll(xs, 5 * c)[::(-1 if c % 2 else 1)] for c in range(nc)], axis=1)
+    ref = orc.evaluate(packed, pts, orc.ORACLE_LD)
+    assert (plan.digits_host(pts) == orc.digits(packed, pts)).all()
+    got, o = plan.evaluate_host(pts)
+    assert o.kernel_used == _capi.TTN_KERNEL_TABLE
+    assert orc.error_metric(got, ref).max() < TOL
+    # index-setting mode with the oracle's digits gives bitwise the same values
+    got2, _ = plan.evaluate_indices_host(orc.digits(packed, pts), kernel="table")
+    assert (got2 == got).all()
