@@ -58,6 +58,18 @@ __device__ __forceinline__ void lds_entry(uint32_t base, uint32_t s, double (&ds
   }
 }
 
+// Parallel bit deposit (the "expand" network of Hacker's Delight 7-5, 64-bit): bit j of x moves to the j-th
+// lowest set bit of m0.  The six step masks mv depend only on m0 and come from the host (expand_masks).
+__device__ __forceinline__ uint64_t expand64(uint64_t x, const uint64_t* mv, uint64_t m0) {
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    const uint64_t m = mv[i];
+    const uint64_t t = x << (1 << i);
+    x = (x & ~m) | (t & m);
+  }
+  return x & m0;
+}
+
 __device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
   double2 r;
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(NT, MINB)
   auto add_coord = [&](int c, double (&x)[PPT], int64_t p0) {
 #pragma unroll
     for (int k = 0; k < PPT; ++k) bad = bad || !coord_in_domain(x[k]);
-    if (ct.run_L[c] > 0 && !src.digits) {
+    if (ct.run_kind[c] > 0 && !src.digits) {
       // digits = bits of floor(x 2^L), x >= 1 saturating to all ones (see build_chain_mma).  Every branch below
       // is uniform and sits OUTSIDE the per-point loops.
       const int L = ct.run_L[c], plow = ct.run_plow[c];
@@ -153,7 +165,17 @@ __global__ void __launch_bounds__(NT, MINB)
           q[k] = rev ? (__brevll(t) >> (64 - L)) : t;
         }
       }
-      if (plow < 64) {
+      if (ct.run_kind[c] == 2) {
+        // digits scattered over the stream (interleaved dimensions, Real + Imag index on one vertex)
+        const int cm = c & (kTabMaskCoords - 1);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) w0[k] += expand64(q[k], ct.exp_mv[cm][0], ct.exp_m[cm][0]);
+        if (W2 && ct.exp_m[cm][1] != 0) {
+          const int nlo = ct.exp_nlo[cm];
+#pragma unroll
+          for (int k = 0; k < PPT; ++k) w1[k] += expand64(q[k] >> nlo, ct.exp_mv[cm][1], ct.exp_m[cm][1]);
+        }
+      } else if (plow < 64) {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) w0[k] += q[k] << plow;
         if (W2 && plow + L > 64) {
@@ -582,6 +604,51 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_
   return true;
 }
 
+// Step masks of the 64-bit expand network (Hacker's Delight 7-5) for target mask m.
+static void expand_masks(uint64_t m, uint64_t (&mv_out)[6]) {
+  uint64_t mk = ~m << 1;
+  for (int i = 0; i < 6; ++i) {
+    uint64_t mp = mk ^ (mk << 1);
+    mp ^= mp << 2;
+    mp ^= mp << 4;
+    mp ^= mp << 8;
+    mp ^= mp << 16;
+    mp ^= mp << 32;
+    const uint64_t mv = mp & m;
+    mv_out[i] = mv;
+    m = (m ^ mv) | (mv >> (1 << i));
+    mk &= ~mp;
+  }
+}
+static uint64_t expand_host(uint64_t x, const uint64_t (&mv)[6], uint64_t m0) {
+  for (int i = 5; i >= 0; --i) {
+    const uint64_t t = x << (1 << i);
+    x = (x & ~mv[i]) | (t & mv[i]);
+  }
+  return x & m0;
+}
+// the network against a bit-by-bit deposit: all ones, every single bit, a few patterns
+static bool expand_selfcheck(uint64_t m0, const uint64_t (&mv)[6]) {
+  auto naive = [&](uint64_t x) {
+    uint64_t r = 0;
+    int j = 0;
+    for (int b = 0; b < 64; ++b)
+      if (m0 >> b & 1) {
+        if (x >> j & 1) r |= 1ull << b;
+        ++j;
+      }
+    return r;
+  };
+  const int n = __builtin_popcountll(m0);
+  std::vector<uint64_t> xs = {0ull, ~0ull, 0x5555555555555555ull, 0x123456789abcdef1ull, 0xfedcba9876543210ull};
+  for (int j = 0; j < n; ++j) xs.push_back(1ull << j);
+  for (uint64_t x : xs) {
+    const uint64_t xm = n >= 64 ? x : (x & ((1ull << n) - 1ull));
+    if (expand_host(xm, mv, m0) != naive(xm)) return false;
+  }
+  return true;
+}
+
 static size_t table_budget_bytes(int variant) {
   if (const char* e = getenv("TTN_TABLE_KB")) return (size_t)std::max(8, std::min(atoi(e), 200)) * 1024;
   (void)variant;
@@ -629,31 +696,49 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   TTN_CUDA(cudaMemcpy(d_ent, ent.data(), sizeof(DigitEntry) * d->n_sites, cudaMemcpyHostToDevice));
   p->digits_tab.entries = d_ent;
 
-  // K1 run fast path per coordinate slot — same conditions as build_chain_mma (k_chain_mma.cu): binary
-  // digits 1..L with thresholds exactly 2^-k, one site index per vertex, consecutive stream bits in
-  // increasing or decreasing order.  Then digit k = bit (L-k) of floor(x 2^L), exactly.
-  if (bits0 == 1) {
+  // K1 run fast path per coordinate slot.  Conditions (checked bitwise): every site index of the slot is binary,
+  // the digit numbers are exactly 1..L with thresholds exactly 2^-k, L <= 53, and the stream bits of the digits
+  // are strictly increasing or strictly decreasing in the digit number.  Then the greedy loop
+  // (abstractindexmap.jl:121-138) yields digit k = bit (L-k) of floor(x 2^L), exactly (build_chain_mma has the
+  // argument).  Consecutive bits -> kind 1 (one shift); anything else monotone -> kind 2 (bit deposit).
+  {
     std::vector<int32_t> cptr(d->n_coords + 1);
     TTN_CUDA(cudaMemcpy(cptr.data(), p->digits.coord_ptr, sizeof(int32_t) * (d->n_coords + 1), cudaMemcpyDeviceToHost));
     for (int cidx = 0; cidx < d->n_coords; ++cidx) {
       const int L = cptr[cidx + 1] - cptr[cidx];
-      if (L < 1 || L > 63) continue;
-      bool ok = true;
-      int step = 0, first_pos = -1;
+      if (L < 1 || L > 53) continue;
+      bool ok = true, inc = true, dec = true, contiguous = true;
+      std::vector<int> bp(L);
       for (int k = 0; k < L && ok; ++k) {
         const DigitEntry& e = ent[cptr[cidx] + k];
-        const int pos = e.word * 64 + e.shift;
-        ok = ok && e.base == 2 && e.stride == 1 && p->nslices[e.vertex] == 2;
+        ok = ok && e.base == 2 && (e.stride == 1 || e.stride == 2);
         ok = ok && d->site_digit[e.site] == k + 1 && d->thr[e.thr_off + 1] == std::ldexp(1.0, -(k + 1));
-        if (k == 0) first_pos = pos;
-        else if (k == 1) step = pos - first_pos;
-        if (k >= 1) ok = ok && (pos - first_pos == step * k);
+        bp[k] = e.word * 64 + e.shift + (e.stride == 2 ? 1 : 0);
+        if (k >= 1) {
+          inc = inc && bp[k] > bp[k - 1];
+          dec = dec && bp[k] < bp[k - 1];
+          contiguous = contiguous && std::abs(bp[k] - bp[k - 1]) == 1;
+        }
       }
-      if (L == 1) step = 1;
-      if (!ok || (step != 1 && step != -1)) continue;
+      if (!ok || !(inc || dec)) continue;
+      const bool rev = inc; // digit 1 on the LOWEST stream bit: reverse the bits of floor(x 2^L)
+      if (!contiguous) {
+        if (cidx >= kTabMaskCoords) continue;
+        uint64_t m[2] = {0, 0};
+        for (int k = 0; k < L; ++k) m[bp[k] / 64] |= 1ull << (bp[k] % 64);
+        bool good = true;
+        for (int w = 0; w < 2; ++w) {
+          expand_masks(m[w], c.exp_mv[cidx][w]);
+          c.exp_m[cidx][w] = m[w];
+          good = good && expand_selfcheck(m[w], c.exp_mv[cidx][w]);
+        }
+        c.exp_nlo[cidx] = __builtin_popcountll(m[0]);
+        if (!good) continue; // never observed; the tabulated loop is always correct
+      }
+      c.run_kind[cidx] = contiguous ? 1 : 2;
       c.run_L[cidx] = L;
-      c.run_rev[cidx] = step == 1 ? 1 : 0;
-      c.run_plow[cidx] = step == 1 ? first_pos : first_pos - (L - 1);
+      c.run_rev[cidx] = rev ? 1 : 0;
+      c.run_plow[cidx] = rev ? bp[0] : bp[L - 1];
       c.run_scale[cidx] = std::ldexp(1.0, L);
     }
   }
@@ -688,6 +773,8 @@ static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out
   // TTN_TABLE_VARIANT=1 — read at plan creation — still runs for experiments).
   if constexpr (H == 1) {
     if (p->ctab.rep) {
+      if (p->ctab_variant == 2) // experiment: 24 warps per SM
+        return launch_tab_inst<H, CPLX, 768, 1, PPT + PPT / 2, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
       if (p->ctab_variant == 1)
         return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
       return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);

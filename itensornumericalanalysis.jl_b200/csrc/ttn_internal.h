@@ -129,6 +129,7 @@ struct ChainGemmDev {
 
 // narrow chains as shared-memory group tables (k_chain_table.cu)
 constexpr int kTabMaxGroups = 16;
+constexpr int kTabMaskCoords = 8; // coordinate slots that can use the masked K1 run path
 struct ChainTabDev {
   int32_t n_groups;      // >= 2: group 0 = leaf vectors, last = root vectors, between: H x H matrices
   int32_t H;             // padded bond dimension (a complex entry counts once): 1, 2 or 4
@@ -139,6 +140,13 @@ struct ChainTabDev {
   int32_t goff[kTabMaxGroups];  // offset of the group's table in the image, in doubles (even)
   int32_t run_L[TTN_MAX_COORDS], run_plow[TTN_MAX_COORDS], run_rev[TTN_MAX_COORDS]; // K1 run fast path
   double run_scale[TTN_MAX_COORDS];
+  // run_kind: 0 = tabulated greedy loop, 1 = digits on consecutive stream bits (shift), 2 = digits on any
+  // monotone set of stream bits (interleaved dimensions, two site indices per vertex): the bits of
+  // floor(x 2^L) are deposited into the mask exp_m by a 6-step shift/select network (masks exp_mv)
+  int32_t run_kind[TTN_MAX_COORDS];
+  int32_t exp_nlo[kTabMaskCoords];        // popcount(exp_m[c][0])
+  uint64_t exp_m[kTabMaskCoords][2];      // stream bits of the coordinate's digits (word 0, word 1)
+  uint64_t exp_mv[kTabMaskCoords][2][6];
   const double* image;
 };
 

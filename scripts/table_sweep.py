@@ -7,7 +7,7 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200", "1"), ("1", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
+SWEEP = [("0", "200", "1"), ("2", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
 
 
 def run(name, f, ncol):
@@ -47,5 +47,8 @@ run("rand chi2 2x30", t.rand_itn(s2, link_space=2, rng=20267, normalise=True), 2
 run("rand chi4 2x30", t.rand_itn(s2, link_space=4, rng=20268, normalise=True), 2)
 sc = t.complex_continuous_siteinds(t.named_grid((30, 1)), map_dimension=1)
 run("complex chi1 1-D 2x30", t.rand_itn(sc, link_space=1, rng=20269, eltype=complex, normalise=True), 2)
+si = t.continuous_siteinds(t.named_grid((60, 1)), map_dimension=2)
+run("exp chi1 mps60 interleaved", t.exp_itn(si, k=0.9, a=0.1, c=1.2, dim=2), 2)
+run("rand chi2 mps60 interleaved", t.rand_itn(si, link_space=2, rng=20270, normalise=True), 2)
 s1 = t.continuous_siteinds(t.named_grid((20, 1)))
 run("sin_qtt20 (cfg1 net)", t.sin_itn(s1, k=2.0, a=0.3, c=1.1), 1)
