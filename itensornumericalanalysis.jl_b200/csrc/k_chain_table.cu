@@ -80,7 +80,7 @@ __device__ __forceinline__ double2 ldg_nc_f64x2(const double* p) {
 // bits (config 2's layout: 2 x 30) keep the stream in one register pair and shift half as much.
 // NCV: coordinates fetched with vector loads one tile ahead — 2: 2-D AoS input (one 128-bit load per point),
 // 1: 1-D input (one 64-bit load per point), 0: any layout / grid generator / index-setting mode (load_coord).
-// REP (chi = 1 only): tables in the replicated, conflict-free layout (make_table_image).
+// REP: tables in the replicated, conflict-free layout (make_table_image).
 template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2, bool REP>
 __global__ void __launch_bounds__(NT, MINB)
     chain_table_kernel(ChainTabDev ct, DigitTable dg, CoordSource src, double* __restrict__ out, int* err,
@@ -109,16 +109,20 @@ __global__ void __launch_bounds__(NT, MINB)
   __syncthreads();
 
   // REP: this lane's copy inside every 128-byte line
-  const uint32_t sbase = smem_u32(smem) + (REP ? (CPLX ? (uint32_t)(lane & 7) * 16u : (uint32_t)(lane & 15) * 8u) : 0u);
+  const uint32_t sbase = smem_u32(smem) + (REP ? (HE > 1 ? (uint32_t)(lane & 7) * 16u : (uint32_t)(lane & 15) * 8u) : 0u);
   const int G = ct.n_groups;
   auto entry = [&](uint32_t base, uint32_t s, auto& dst) {
     constexpr int N = sizeof(dst) / sizeof(double);
     if constexpr (REP) {
       if constexpr (N == 1) dst[0] = lds64(base + (s << 7));
       else {
-        const double2 t = lds128(base + (s << 7));
-        dst[0] = t.x;
-        dst[1] = t.y;
+        const uint32_t a = base + s * (uint32_t)(N / 2 * 128);
+#pragma unroll
+        for (int j = 0; j < N / 2; ++j) {
+          const double2 t = lds128(a + 128u * j);
+          dst[2 * j] = t.x;
+          dst[2 * j + 1] = t.y;
+        }
       }
     } else {
       lds_entry<N>(base, s, dst);
@@ -480,32 +484,51 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_
     }
     if (gb.empty()) return false;
   }
-  // chi = 1 (every entry is one real or complex number): the lookups of a warp hit random banks — measured 6.35
-  // wavefronts per LDS.64 against the conflict-free 2, which made the kernel LSU-bound at 80 % of the HBM
-  // roofline.  Replicated layout: a table is stored once per lane of a half-warp (8-byte entries, 16 copies) or
-  // quarter-warp (16-byte entries, 8 copies), entry s of copy c at byte 128 s + 8 (16) c, so lane l always reads
-  // bank group (l mod 16 | 8) and NO lookup conflicts.  A table then costs 2^bits x 128 bytes, so groups shrink to
-  // 6..9 bits and a point takes more (but 3x cheaper) lookups: used when it at most doubles the group count.
+  // Replicated layout.  The lookups of a warp hit random banks: measured 6.35 wavefronts per LDS.64 (conflict-free: 2)
+  // and 10.4 per LDS.128 (conflict-free: 4), which makes the kernel LSU-bound.  Here every 16-byte chunk of an entry is
+  // stored once per lane of a quarter-warp in one 128-byte line (8-byte entries: once per lane of a half-warp), chunk j
+  // of entry s of copy c at byte 128 (s C + j) + 16 c, so lane l always reads bank group l mod 8 and NO lookup
+  // conflicts.  An entry then costs C x 128 bytes: groups shrink and a point takes more — but 2.6-3x cheaper —
+  // lookups.  Chosen when the estimated LSU cost (wavefronts + 3 per lookup for its instructions) drops by > 10 %.
   bool rep = false;
-  if (allow_rep && H == 1) {
+  if (allow_rep) {
     const size_t units = budget_bytes / 128;
+    const size_t lv = std::max<size_t>(1, ev / 2), lm = std::max<size_t>(1, em / 2); // 128-byte lines per entry
+    const double wv_plain = ev == 1 ? 6.35 : 10.4 * (double)(ev / 2), wm_plain = em == 1 ? 6.35 : 10.4 * (double)(em / 2);
+    const double wv_rep = ev == 1 ? 2.0 : 4.0 * (double)(ev / 2), wm_rep = em == 1 ? 2.0 : 4.0 * (double)(em / 2);
+    const double plain_cost = 2.0 * (wv_plain + 3.0) + (double)(gb.size() - 2) * (wm_plain + 3.0);
     const int npos = B / bits0;
-    for (int Gr = 2; Gr <= kTabMaxGroups; ++Gr) {
-      if (Gr > npos) break;
-      std::vector<int> cand(Gr);
-      size_t size = 0;
-      bool ok = true;
-      for (int g = 0; g < Gr; ++g) { // bits as even as possible, the larger groups first
-        cand[g] = (npos / Gr + (g < npos % Gr ? 1 : 0)) * bits0;
-        ok = ok && cand[g] <= 16;
-        size += (size_t)1 << cand[g];
-      }
-      if (!ok || size > units) continue;
-      if (Gr <= 2 * (int)gb.size() && cand[0] >= 7) {
-        gb = cand;
+    std::vector<int> best;
+    for (int Gr = 2; Gr <= kTabMaxGroups && best.empty(); ++Gr) {
+      const int nm = Gr - 2;
+      size_t best_size = 0;
+      for (int pL = 1; pL * bits0 <= 16; ++pL)
+        for (int pR = std::max(1, pL - 1); pR <= pL; ++pR) {
+          const int rem = npos - pL - pR;
+          if (rem < nm || (nm == 0 && rem != 0)) continue;
+          std::vector<int> cand(Gr);
+          cand[0] = pL * bits0;
+          cand[Gr - 1] = pR * bits0;
+          size_t size = (((size_t)1 << cand[0]) + ((size_t)1 << cand[Gr - 1])) * lv;
+          bool ok = true;
+          for (int i = 0; i < nm; ++i) { // middle bits as even as possible
+            cand[1 + i] = (rem / nm + (i < rem % nm ? 1 : 0)) * bits0;
+            ok = ok && cand[1 + i] <= 16;
+            size += ((size_t)1 << cand[1 + i]) * lm;
+          }
+          if (!ok || size > units) continue;
+          if (best.empty() || size < best_size) {
+            best = cand;
+            best_size = size;
+          }
+        }
+    }
+    if (!best.empty()) {
+      const double rep_cost = 2.0 * (wv_rep + 3.0) + (double)(best.size() - 2) * (wm_rep + 3.0);
+      if (rep_cost < 0.9 * plain_cost) {
+        gb = best;
         rep = true;
       }
-      break;
     }
   }
   const int G = (int)gb.size();
@@ -533,7 +556,10 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_
   size_t total = 0;
   for (int g = 0; g < G; ++g) {
     out->goff[g] = (int)total;
-    total += ((size_t)1 << gb[g]) * (rep ? (size_t)16 : ((g == 0 || g == G - 1) ? ev : em));
+    {
+      const size_t e_g = (g == 0 || g == G - 1) ? ev : em; // doubles per entry; replicated: 16 doubles per line
+      total += ((size_t)1 << gb[g]) * (rep ? (size_t)16 * std::max<size_t>(1, e_g / 2) : e_g);
+    }
     total = (total + 15) & ~(size_t)15; // 128-byte alignment of every table (entry_swizzle, bank groups)
   }
   out->image.assign(total, 0.0);
@@ -581,11 +607,17 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_
           const uint32_t sw = esz == 16 ? entry_swizzle<16>((uint32_t)s) : esz == 8 ? entry_swizzle<8>((uint32_t)s)
                               : esz == 4 ? entry_swizzle<4>((uint32_t)s) : 0u;
           auto put = [&](size_t e, double val) { dst[s * esz + (((e >> 1) ^ sw) << 1) + (e & 1)] = val; };
-          if (rep) { // H = 1: 16 / E copies of the entry in one 128-byte line
-            for (int c = 0; c < 16 / E; ++c) {
-              dst[s * 16 + (size_t)c * E] = (double)x.re;
-              if (cplx) dst[s * 16 + (size_t)c * E + 1] = (double)x.im;
-            }
+          if (rep) {
+            // element e of the entry: chunk e / 2 -> line s C + e / 2, 8 copies 16 bytes apart (a single-double
+            // entry: 16 copies 8 bytes apart)
+            const size_t C = std::max<size_t>(1, esz / 2);
+            auto put_rep = [&](size_t e, double val) {
+              double* line = dst + (s * C + e / 2) * 16;
+              if (esz == 1) for (int c = 0; c < 16; ++c) line[c] = val;
+              else for (int c = 0; c < 8; ++c) line[2 * c + (e & 1)] = val;
+            };
+            put_rep(at * E, (double)x.re);
+            if (cplx) put_rep(at * E + 1, (double)x.im);
             continue;
           }
           put(at * E, (double)x.re);
@@ -771,10 +803,8 @@ static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out
   // One persistent CTA per SM: 512 threads x 2 PPT points per thread and tile (up to 128 registers: 8 points
   // in flight per thread for chi = 1; measured 5-10 % faster than 1024 threads x PPT points, which
   // TTN_TABLE_VARIANT=1 — read at plan creation — still runs for experiments).
-  if constexpr (H == 1) {
+  {
     if (p->ctab.rep) {
-      if (p->ctab_variant == 2) // experiment: 24 warps per SM
-        return launch_tab_inst<H, CPLX, 768, 1, PPT + PPT / 2, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
       if (p->ctab_variant == 1)
         return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
       return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);

@@ -7,7 +7,7 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200", "1"), ("2", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
+SWEEP = [("0", "200", "1"), ("1", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
 
 
 def run(name, f, ncol):
@@ -45,6 +45,8 @@ s2 = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
 run("exp chi1 2x30", t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1), 2)
 run("rand chi2 2x30", t.rand_itn(s2, link_space=2, rng=20267, normalise=True), 2)
 run("rand chi4 2x30", t.rand_itn(s2, link_space=4, rng=20268, normalise=True), 2)
+s24 = t.continuous_siteinds(t.named_grid((24, 1)), map_dimension=3)
+run("rand chi4 mps24 3-D", t.rand_itn(s24, link_space=4, rng=20271, normalise=True), 3)
 sc = t.complex_continuous_siteinds(t.named_grid((30, 1)), map_dimension=1)
 run("complex chi1 1-D 2x30", t.rand_itn(sc, link_space=1, rng=20269, eltype=complex, normalise=True), 2)
 si = t.continuous_siteinds(t.named_grid((60, 1)), map_dimension=2)

