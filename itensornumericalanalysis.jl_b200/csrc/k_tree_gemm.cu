@@ -412,8 +412,11 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   }
   const TreeGemmDev& g = p->tgemm;
   const int n = g.n_vertices, W = g.W;
-  // chunk size: the per-vertex tile count (<= PC/128 + 8 classes) fills a whole number of waves
-  const int PC = (int)std::min<int64_t>((int64_t)(4 * p->sm_count - 8) * TBM, (src.npts + TBM - 1) / TBM * TBM);
+  // chunk size: the per-vertex tile count (<= PC/128 + 8 classes) fills a whole number of waves.  Narrow rows
+  // (W = 16, 32) take 4x / 2x the points per chunk: their per-vertex launches are otherwise too small to
+  // cover the launch latency (measured: a 60-vertex comb tree at chi = 8 and chi = 16 ran at the same
+  // 258 M points/s); the message workspace per chunk stays what a W = 64 tree of the same size takes.
+  const int PC = (int)std::min<int64_t>((int64_t)(4 * (64 / W) * p->sm_count - 8) * TBM, (src.npts + TBM - 1) / TBM * TBM);
   const size_t msg_b = (size_t)PC * W * 8;
   const size_t slices_b = ((size_t)n * PC + 255) / 256 * 256;
   const size_t lists_b = (size_t)n * PC * 4;

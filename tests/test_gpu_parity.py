@@ -674,3 +674,26 @@ def test_table_kernel_digit_boundaries(which):
     # index-setting mode with the oracle's digits gives bitwise the same values
     got2, _ = plan.evaluate_indices_host(orc.digits(packed, pts), kernel="table")
     assert (got2 == got).all()
+
+
+@pytest.mark.parametrize("chi", [12, 24])
+def test_tree_kernel_many_chunks(chi):
+    """The per-vertex GEMM tree kernel over several chunks (chunk size scales with 64 / W): a 3-tooth comb tree
+    (examples/construct_multi_dimensional_function.jl topology) at 7e5 points, against the generic kernel on the
+    whole batch and against the 80-bit oracle on a slice that straddles a chunk boundary."""
+    L = 8
+    g = t.named_comb_tree((3, L))
+    s = t.continuous_siteinds(g, [[(j, i) for i in range(1, L + 1)] for j in range(1, 4)])
+    f = t.rand_itn(s, link_space=chi, rng=40 + chi, normalise=True)
+    plan = f.plan()
+    assert plan.info()["auto_kernel"] == _capi.TTN_KERNEL_TREE
+    rng = np.random.default_rng(5)
+    pts = rng.random((700_001, 3))
+    got, o = plan.evaluate_host(pts, kernel="tree", chunk_points=700_001)
+    ref_g, _ = plan.evaluate_host(pts, kernel="generic")
+    scale = np.sqrt(np.mean(ref_g ** 2))
+    assert (np.abs(got - ref_g) / np.maximum(np.abs(ref_g), 1e-3 * scale)).max() < 2e-12
+    for lo in (0, 299_000, 149_000, 699_000):
+        sl = slice(lo, lo + 1001)
+        ref = orc.evaluate(plan.packed, pts[sl], orc.ORACLE_LD)
+        assert orc.error_metric(got[sl], ref).max() < TOL, lo
