@@ -70,13 +70,21 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
   __syncthreads();
   if (nsl > 1) {
+    // 4 independent loads per thread and trip: the block walks the chunk alone, so the global-load latency of
+    // every trip is exposed
     int local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i0 = threadIdx.x - lane; i0 < pc; i0 += blockDim.x) { // warp-uniform bounds
-      const int i = i0 + lane;
-      const int sv = i < pc ? (int)sl[i] : -1;
+    for (int i0 = threadIdx.x - lane; i0 < pc; i0 += 4 * blockDim.x) { // warp-uniform bounds
+      int sv[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < nsl) local[c] += __popc(__ballot_sync(0xffffffffu, sv == c));
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x + lane;
+        sv[u] = i < pc ? (int)sl[i] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < nsl) local[c] += __popc(__ballot_sync(0xffffffffu, sv[u] == c));
     }
     if (lane == 0) {
 #pragma unroll
@@ -103,18 +111,26 @@ __global__ void __launch_bounds__(1024)
   }
   __syncthreads();
   if (nsl > 1) {
-    for (int i0 = threadIdx.x - lane; i0 < pc; i0 += blockDim.x) {
-      const int i = i0 + lane;
-      const int sv = i < pc ? (int)sl[i] : -1;
+    for (int i0 = threadIdx.x - lane; i0 < pc; i0 += 4 * blockDim.x) {
+      int sv[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c < nsl) {
-          const uint32_t m = __ballot_sync(0xffffffffu, sv == c);
-          if (m) { // warp-uniform
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&cursor[c], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (sv == c) list[base + __popc(m & lt)] = (uint32_t)i;
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x + lane;
+        sv[u] = i < pc ? (int)sl[i] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x + lane;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c < nsl) {
+            const uint32_t m = __ballot_sync(0xffffffffu, sv[u] == c);
+            if (m) { // warp-uniform
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&cursor[c], __popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (sv[u] == c) list[base + __popc(m & lt)] = (uint32_t)i;
+            }
           }
         }
       }
