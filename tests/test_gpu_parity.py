@@ -552,7 +552,18 @@ def _narrow_networks():
     s1 = t.continuous_siteinds(t.named_grid((20, 1)))
     s3 = t.continuous_siteinds(t.named_grid((24, 1)), map_dimension=3)
     sc = t.complex_continuous_siteinds(t.named_grid((12, 1)), map_dimension=2)
+    # more than 64 slice bits: two-word streams
+    g40 = t.named_comb_tree((2, 40))
+    s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])   # runs of 40 bits (64-bit K1), one straddles the words
+    s90 = t.continuous_siteinds(t.named_grid((90, 1)), map_dimension=3)                   # interleaved: masked K1 over both words
+    sc40 = t.complex_continuous_siteinds(t.named_grid((40, 1)), map_dimension=1)          # 2 bits per vertex, 80 bits
     return {
+        "rand_chi2_comb2x40": t.rand_itn(s40, link_space=2, rng=11, normalise=True),
+        "exp_comb2x40": t.exp_itn(s40, k=-0.7, a=0.2, c=0.9, dim=2),
+        "rand_chi2_mps90_3d": t.rand_itn(s90, link_space=2, rng=12, normalise=True),
+        "exp_mps90_3d": t.exp_itn(s90, k=0.4, a=-0.1, c=1.3, dim=3),
+        "cplx_2site_chi1_40": t.rand_itn(sc40, link_space=1, rng=13, eltype=complex, normalise=True),
+        "cplx_2site_chi2_40": t.rand_itn(sc40, link_space=2, rng=14, eltype=complex, normalise=True),
         "exp_comb2x30": t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1),                      # chi 1: 5 lookups per point
         "cosh_comb2x30": t.cosh_itn(s2, k=0.9, a=0.1, c=1.2, dim=2),                    # chi 2 real, 60 bits
         "rand_chi2_comb2x30": t.rand_itn(s2, link_space=2, rng=5, normalise=True),
@@ -651,7 +662,8 @@ def test_table_kernel_known_answer_at_scale(rep, variant, monkeypatch):
     assert float(((out - want).abs() / want.abs()).max()) < 1e-12
 
 
-@pytest.mark.parametrize("which", ["rand_chi2_comb2x30", "exp_comb2x30", "rand_chi4_mps3d"])
+@pytest.mark.parametrize("which", ["rand_chi2_comb2x30", "exp_comb2x30", "rand_chi4_mps3d", "rand_chi2_comb2x40",
+                                   "rand_chi2_mps90_3d", "cplx_2site_chi1_40"])
 def test_table_kernel_digit_boundaries(which):
     """The table kernel's K1 run path takes the digits of a coordinate as the bits of floor(x 2^L) through a
     saturating 32-bit conversion (L <= 31).  Any digit mismatch changes the value by O(1): exercise the
@@ -659,7 +671,7 @@ def test_table_kernel_digit_boundaries(which):
     f = _narrow_networks()[which]
     plan = f.plan()
     packed = plan.packed
-    nc, L = packed.n_coords, 30
+    nc, L = packed.n_coords, 40 if which.endswith("40") else 30
     xs = [0.0, -0.0, 5e-324, 2.0 ** -1074, 2.0 ** -31, 2.0 ** -30, np.nextafter(2.0 ** -30, 1), 1 - 2.0 ** -53,
           1 - 2.0 ** -30, np.nextafter(1 - 2.0 ** -30, 0), 1.0, 1.0 + 2.0 ** -52, 7.25, 1e300, 4294967296.0, 0.1, 1 / 3, 2 / 3]
     for k in range(1, L + 1):

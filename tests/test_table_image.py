@@ -19,7 +19,7 @@ MAXG = 16
 def table_image(packed, budget_kb=200):
     L = _capi.lib()
     meta = (C.c_int32 * (8 + 2 * MAXG))()
-    cap = 1 << 17
+    cap = 1 << 18
     img = np.zeros(cap, dtype=np.float64)
     bitpos = np.zeros(max(len(packed.site_dim), 1), dtype=np.int32)
     rc = L.ttn_debug_table_image(C.byref(packed.desc()), budget_kb, meta, img.ctypes.data_as(C.c_void_p),
@@ -96,6 +96,14 @@ def narrow_cases():
     sa = t.complex_continuous_siteinds(t.named_grid((10, 1)), [[(i, 1) for i in range(1, 11, 2)]],
                                        [[(i, 1) for i in range(2, 11, 2)]])
     out.append(("cplx_alt_chi2", t.rand_itn(sa, link_space=2, rng=10, eltype=complex, normalise=True), 8))
+    # more than 64 slice bits
+    g40 = t.named_comb_tree((2, 40))
+    s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
+    out.append(("rand_chi2_comb2x40", t.rand_itn(s40, link_space=2, rng=11, normalise=True), 200))
+    s90 = t.continuous_siteinds(t.named_grid((90, 1)), map_dimension=3)
+    out.append(("exp_mps90_3d", t.exp_itn(s90, k=0.4, a=-0.1, c=1.3, dim=3), 200))
+    sc40 = t.complex_continuous_siteinds(t.named_grid((40, 1)), map_dimension=1)
+    out.append(("cplx_2site_chi2_40", t.rand_itn(sc40, link_space=2, rng=14, eltype=complex, normalise=True), 200))
     # chi = 1 with the plain (not replicated) layout: negative budget
     out.append(("exp_comb2x30_plain", t.exp_itn(s2, k=0.9, a=0.1, c=1.2, dim=1), -200))
     out.append(("cplx_2site_chi1_plain", t.rand_itn(sc, link_space=1, rng=9, eltype=complex, normalise=True), -16))
@@ -113,7 +121,7 @@ def test_table_image_walk_matches_oracle(case):
     assert im["rep"] in (0, 1) and (kb > 0 or im["rep"] == 0), (name, im["gbits"])
     rng = np.random.default_rng(3)
     nc = packed.n_coords
-    pts = np.concatenate([rng.random((300, nc)), cases.edge_points(20, nc, rng, 0)])
+    pts = np.concatenate([rng.random((300 if packed.n_vertices <= 60 else 60, nc)), cases.edge_points(20, nc, rng, 0)])
     dig = orc.digits(packed, pts)
     ref = orc.evaluate(packed, pts, orc.ORACLE_LD)
     got = walk(im, dig)
