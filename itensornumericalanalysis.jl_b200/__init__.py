@@ -22,4 +22,5 @@ from .elementary_functions import (const_itn, exp_itn, cosh_itn, sinh_itn, tanh_
                                    tanh_itensornetwork, cos_itensornetwork, sin_itensornetwork,
                                    random_itensornetwork)
 from .packer import pack, PackedNetwork
+from .ttn_io import save_ttn, load_ttn
 from . import _capi
