@@ -557,7 +557,10 @@ def _narrow_networks():
     s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])   # runs of 40 bits (64-bit K1), one straddles the words
     s90 = t.continuous_siteinds(t.named_grid((90, 1)), map_dimension=3)                   # interleaved: masked K1 over both words
     sc40 = t.complex_continuous_siteinds(t.named_grid((40, 1)), map_dimension=1)          # 2 bits per vertex, 80 bits
+    # vertices without a site index inside the chain (their stream bits stay 0), digits on scattered positions
+    sgap = t.continuous_siteinds(t.named_grid((9, 1)), [[(1, 1), (4, 1), (7, 1)], [(2, 1), (8, 1)]])
     return {
+        "rand_chi3_siteless": t.rand_itn(sgap, link_space=3, rng=3, normalise=True),
         "rand_chi2_comb2x40": t.rand_itn(s40, link_space=2, rng=11, normalise=True),
         "exp_comb2x40": t.exp_itn(s40, k=-0.7, a=0.2, c=0.9, dim=2),
         "rand_chi2_mps90_3d": t.rand_itn(s90, link_space=2, rng=12, normalise=True),

@@ -96,6 +96,9 @@ def narrow_cases():
     sa = t.complex_continuous_siteinds(t.named_grid((10, 1)), [[(i, 1) for i in range(1, 11, 2)]],
                                        [[(i, 1) for i in range(2, 11, 2)]])
     out.append(("cplx_alt_chi2", t.rand_itn(sa, link_space=2, rng=10, eltype=complex, normalise=True), 8))
+    # vertices without a site index inside the chain
+    sgap = t.continuous_siteinds(t.named_grid((9, 1)), [[(1, 1), (4, 1), (7, 1)], [(2, 1), (8, 1)]])
+    out.append(("rand_chi3_siteless", t.rand_itn(sgap, link_space=3, rng=3, normalise=True), 200))
     # more than 64 slice bits
     g40 = t.named_comb_tree((2, 40))
     s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
