@@ -10,12 +10,21 @@
 //     middle groups -> 2^g  H x H matrices  v  <- v * Mt_g[s_g]
 //     root group  -> 2^gR column vectors   out = v . Rt[s_last]
 // sized so that ALL tables of the chain sit in the shared memory of one CTA (<= 200 KB).  The
-// kernel is one persistent CTA per SM: tables are loaded once, then every thread streams PPT
-// points per tile — coordinates with coalesced (128-bit for 2-D AoS input) loads issued one
-// tile ahead, K1 (k_digits.cuh semantics; the exact floor(x 2^L) run fast path for binary digits on
-// consecutive vertices) into a 128-bit packed slice stream, one table lookup per group with the
-// state in registers, one coalesced store.  A 60-bit chi = 1 chain costs 5 shared-memory lookups
-// and 5 multiplies per point; algorithmic traffic = 8 n_coords + 8 (16 complex) bytes per point.
+// kernel is one persistent CTA per SM: tables are loaded once, then every thread streams several
+// points per tile — coordinates with coalesced vector loads issued one tile ahead; K1 (k_digits.cuh
+// semantics) as the bits of floor(x 2^L), shifted into place when a coordinate's digits sit on
+// consecutive stream bits and deposited by a 6-step shift/select network when they are scattered
+// (interleaved dimensions, Real + Imag index on one vertex), into a 128-bit packed slice stream;
+// one table lookup per group with the state in registers; one coalesced store.
+//
+// Table layouts (make_table_image picks per plan):
+//   replicated — every 16-byte chunk of an entry once per lane of a quarter-warp in one 128-byte line
+//                (8-byte entries: per lane of a half-warp): no lookup has a bank conflict.  A 60-bit
+//                chi = 1 chain: 8 lookups of 7-8 bits, 5.7-6.0 TB/s of the 24 algorithmic B/point;
+//                chi = 2: 10 lookups of 6 bits, shared-memory pipe at its conflict-free rate;
+//   plain      — entries back to back, their 16-byte chunks XOR-swizzled by the entry index (when the
+//                replicated tables do not fit: chi = 4 on long chains).
+// Measurements, ncu summaries and the history of the kernel: DESIGN.md, profiles/r01_table_*.txt.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -681,9 +690,8 @@ static bool expand_selfcheck(uint64_t m0, const uint64_t (&mv)[6]) {
   return true;
 }
 
-static size_t table_budget_bytes(int variant) {
+static size_t table_budget_bytes() {
   if (const char* e = getenv("TTN_TABLE_KB")) return (size_t)std::max(8, std::min(atoi(e), 200)) * 1024;
-  (void)variant;
   return (size_t)200 * 1024;
 }
 
@@ -693,7 +701,7 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   TableImage im;
   p->ctab_variant = variant_from_env();
   const bool allow_rep = !(getenv("TTN_TABLE_REP") && atoi(getenv("TTN_TABLE_REP")) == 0);
-  if (!make_table_image(d, table_budget_bytes(p->ctab_variant), allow_rep, &im)) return TTN_OK;
+  if (!make_table_image(d, table_budget_bytes(), allow_rep, &im)) return TTN_OK;
   ChainTabDev& c = p->ctab;
   c = ChainTabDev{};
   c.n_groups = (int)im.gbits.size();
