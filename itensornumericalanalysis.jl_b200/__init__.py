@@ -23,4 +23,5 @@ from .elementary_functions import (const_itn, exp_itn, cosh_itn, sinh_itn, tanh_
                                    random_itensornetwork)
 from .packer import pack, PackedNetwork
 from .ttn_io import save_ttn, load_ttn
+from .integration import partial_integrate, integrate
 from . import _capi
