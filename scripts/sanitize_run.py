@@ -21,6 +21,11 @@ s2 = t.continuous_siteinds(t.named_grid((30, 1)), map_dimension=2)
 nets.append(("mps chi2 (table)", t.rand_itn(s2, link_space=2, rng=6, normalise=True), 2, 5000))
 sc = t.complex_continuous_siteinds(t.named_grid((12, 1)), map_dimension=2)
 nets.append(("complex mps chi2, 2 site indices per vertex (table)", t.rand_itn(sc, link_space=2, rng=7, eltype=complex, normalise=True), 4, 3000))
+s90 = t.continuous_siteinds(t.named_grid((90, 1)), map_dimension=3)
+nets.append(("mps90 chi2 3-D, two-word stream (table)", t.rand_itn(s90, link_space=2, rng=8, normalise=True), 3, 5000))
+g40 = t.named_comb_tree((2, 40))
+s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
+nets.append(("comb2x40 chi1, 40-bit runs (table)", t.exp_itn(s40, k=-0.7, a=0.2, c=0.9, dim=2), 2, 5000))
 skip = os.environ.get('SAN_SKIP', '')
 only = os.environ.get('SAN_ONLY', '')
 # default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
