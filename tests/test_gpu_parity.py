@@ -737,3 +737,27 @@ def test_marginals_through_partial_integrate(which):
         full = np.concatenate([np.tile(row, (len(xs), 1)), xs[:, None]], axis=1)
         mean = t.evaluate(f, full, dims).mean()
         assert abs(val - mean) <= 1e-11 * max(abs(mean), 1e-3)
+
+
+def test_table_kernel_grid_mode():
+    """ttn_evaluate_grid through the table kernel (coordinates generated on the device, grid_points semantics of
+    src/IndexMaps/realindexmap.jl:78-86): bitwise the explicit points, sharded halves, fused sum; a grid that is
+    NOT the full dyadic one (N = 48 points per dimension), so the prefix-shared kernel does not take it."""
+    s = t.continuous_siteinds(t.named_grid((16, 1)), map_dimension=2)
+    f = t.rand_itn(s, link_space=2, rng=15, normalise=True)
+    plan = f.plan()
+    assert plan.info()["auto_kernel"] == _capi.TTN_KERNEL_TABLE
+    n = 48
+    xs, ys = s.grid_points(n, 1), s.grid_points(n, 2)
+    pts = np.array([[x, y] for x in xs for y in ys])
+    vals, o = plan.evaluate_grid([xs[1], ys[1]], [len(xs), len(ys)], want_values=True, reduce_sum=True)
+    assert o.kernel_used == _capi.TTN_KERNEL_TABLE
+    explicit, _ = plan.evaluate_host(pts, kernel="table")
+    assert (vals == explicit).all()
+    ref = orc.evaluate(plan.packed, pts, orc.ORACLE_LD)
+    assert orc.error_metric(vals, ref).max() < TOL
+    assert abs(o.sum_out[0] - ref.sum()) <= 1e-12 * np.abs(ref).sum()
+    half = len(pts) // 2
+    a, _ = plan.evaluate_grid([xs[1], ys[1]], [len(xs), len(ys)], first=0, npts=half, want_values=True)
+    b, _ = plan.evaluate_grid([xs[1], ys[1]], [len(xs), len(ys)], first=half, npts=len(pts) - half, want_values=True)
+    assert (np.concatenate([a, b]) == vals).all()
