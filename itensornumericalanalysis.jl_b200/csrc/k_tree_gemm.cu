@@ -466,7 +466,10 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   // (W = 16, 32) take 4x / 2x the points per chunk: their per-vertex launches are otherwise too small to
   // cover the launch latency (measured: a 60-vertex comb tree at chi = 8 and chi = 16 ran at the same
   // 258 M points/s); the message workspace per chunk stays what a W = 64 tree of the same size takes.
-  const int PC = (int)std::min<int64_t>((int64_t)(4 * (64 / W) * p->sm_count - 8) * TBM, (src.npts + TBM - 1) / TBM * TBM);
+  // The message workspace is n x PC x W doubles: keep it under 8 GB for trees of many vertices.
+  const int64_t pc_mem = std::max<int64_t>((int64_t)p->sm_count * TBM, (int64_t)(8e9 / ((double)n * W * 8)) / TBM * TBM);
+  const int PC = (int)std::min<int64_t>(std::min<int64_t>((int64_t)(4 * (64 / W) * p->sm_count - 8) * TBM, pc_mem),
+                                        (src.npts + TBM - 1) / TBM * TBM);
   const size_t msg_b = (size_t)PC * W * 8;
   const size_t slices_b = ((size_t)n * PC + 255) / 256 * 256;
   const size_t lists_b = (size_t)n * PC * 4;
