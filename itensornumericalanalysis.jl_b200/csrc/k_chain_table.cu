@@ -413,8 +413,7 @@ struct PosMat {
   std::vector<cld> e; // [(s * a + i) * b + j]
 };
 
-// TTN_TABLE_VARIANT, read when a plan is built (experiments; 0 is what the bench runs)
-int variant_from_env() { return getenv("TTN_TABLE_VARIANT") ? atoi(getenv("TTN_TABLE_VARIANT")) : 0; }
+
 } // namespace
 
 // Host image of the group tables (pure function of the description: also behind the debug symbol
@@ -699,7 +698,6 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   p->ctab_ok = false;
   if (!p->is_chain || !p->all_base2) return TTN_OK;
   TableImage im;
-  p->ctab_variant = variant_from_env();
   const bool allow_rep = !(getenv("TTN_TABLE_REP") && atoi(getenv("TTN_TABLE_REP")) == 0);
   if (!make_table_image(d, table_budget_bytes(), allow_rep, &im)) return TTN_OK;
   ChainTabDev& c = p->ctab;
@@ -809,17 +807,9 @@ template <int H, bool CPLX, int PPT, int NCV, bool W2>
 static int launch_tab_variant(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                               cudaStream_t s) {
   // One persistent CTA per SM: 512 threads x 2 PPT points per thread and tile (up to 128 registers: 8 points
-  // in flight per thread for chi = 1; measured 5-10 % faster than 1024 threads x PPT points, which
-  // TTN_TABLE_VARIANT=1 — read at plan creation — still runs for experiments).
-  {
-    if (p->ctab.rep) {
-      if (p->ctab_variant == 1)
-        return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
-      return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
-    }
-  }
-  if (p->ctab_variant == 1)
-    return launch_tab_inst<H, CPLX, 1024, 1, PPT, NCV, W2, false>(p, src, d_out, d_partial, n_partial, s);
+  // in flight per thread for chi = 1).  Measured 5-10 % faster than 1024 threads x PPT points and the same as
+  // 768 x 1.5 PPT (scripts/table_sweep.py history in DESIGN.md); only this shape is instantiated.
+  if (p->ctab.rep) return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, true>(p, src, d_out, d_partial, n_partial, s);
   return launch_tab_inst<H, CPLX, 512, 1, 2 * PPT, NCV, W2, false>(p, src, d_out, d_partial, n_partial, s);
 }
 

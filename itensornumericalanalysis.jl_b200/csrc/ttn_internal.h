@@ -208,7 +208,6 @@ struct ttn_plan {
   bool ctab_ok = false;
   ttn::DigitTable digits_tab{}; // same table, (word, shift) for the table kernel's stream layout
   double ctab_flops_exec = 0.0;
-  int ctab_variant = 0; // TTN_TABLE_VARIANT at plan creation
   ttn::TreeGemmDev tgemm{};
   bool tgemm_ok = false;
   std::vector<int64_t> tg_frag_off;

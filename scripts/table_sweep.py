@@ -7,7 +7,7 @@ import torch
 import itna_b200 as t
 
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
-SWEEP = [("0", "200", "1"), ("1", "200", "1"), ("0", "200", "0")]   # (launch variant, table KB, replicated chi=1 layout)
+SWEEP = [("0", "200", "1"), ("0", "200", "0"), ("0", "100", "1")]   # (unused, table KB, replicated layout on / off)
 
 
 def run(name, f, ncol):
