@@ -65,8 +65,10 @@ mutable struct TTNOpts
   reserved_::Int32
   flops_executed::Float64
 end
-TTNOpts(; reduce_sum=false) =
-  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, reduce_sum ? 1 : 0, 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, C_NULL, TTN_MEM_HOST, 0, 0.0)
+# reduce: TTN_REDUCE_NONE = 0, _SUM = 1 (sum f), _ABS2 = 2 (sum |f|^2), _WEIGHTED = 3 (sum w f)
+const REDUCE_MODES = Dict(:none => Int32(0), :sum => Int32(1), :abs2 => Int32(2), :weighted => Int32(3))
+TTNOpts(; reduce::Symbol=:none, weights::Ptr{Float64}=Ptr{Float64}(C_NULL)) =
+  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, REDUCE_MODES[reduce], 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, weights, TTN_MEM_HOST, 0, 0.0)
 
 "Flat arrays of one packed network; keeps everything the C side points at alive."
 struct PackedNetwork
@@ -84,6 +86,7 @@ struct PackedNetwork
   n_coords::Int32
   is_complex::Bool
   complex_coords::Bool
+  site_inds::Vector{Index}   # site index of column s of the description (evaluate_indices, ind_values)
 end
 
 mutable struct TTNPlan
@@ -188,6 +191,7 @@ function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn)
   site_ptr = Int32[0]; site_dim = Int32[]; site_coord = Int32[]; site_digit = Int32[]
   thr_ptr = Int32[0]; thr = Float64[]
   tensor_ptr = Int64[0]; tensors = T[]
+  site_inds = Index[]
   for v in vs
     i = vid[v]
     sites = collect(s[v])
@@ -210,13 +214,14 @@ function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn)
       pos = findfirst(==(dimension(imap, ind)), dims) - 1
       slot = cmap ? 2 * pos + (is_real(imap, ind) ? 0 : 1) : pos
       push!(site_dim, dim(ind)); push!(site_coord, slot); push!(site_digit, digit(imap, ind))
+      push!(site_inds, ind)
       append!(thr, [abs(index_value_to_scalar(imap, ind, k)) for k in 0:(dim(ind) - 1)])
       push!(thr_ptr, length(thr))
     end
     push!(site_ptr, length(site_dim))
   end
   return PackedNetwork(parent, link_dim, site_ptr, site_dim, site_coord, site_digit, thr_ptr, thr,
-    tensor_ptr, tensors, vid[root], (cmap ? 2 : 1) * length(dims), eltype_c, cmap)
+    tensor_ptr, tensors, vid[root], (cmap ? 2 : 1) * length(dims), eltype_c, cmap, site_inds)
 end
 
 const _plan_cache = IdDict{Any,Any}()
@@ -236,35 +241,129 @@ function coords_matrix(packed::PackedNetwork, points::AbstractMatrix)
 end
 
 """
-    evaluate(fitn, points::AbstractMatrix, dims; reduce=:none, device=0)
+    evaluate(fitn, points::AbstractMatrix, dims; reduce=:none, weights=nothing, device=0)
     evaluate(fitn, points::Vector{<:Vector}, dims; ...)
 
 Batched `evaluate`: column `j` of `points` (or `points[j]`) holds the coordinates of point `j`
 along `dims`.  Returns `Vector{Float64}` for real networks and `Vector{ComplexF64}` for complex
-ones; `reduce=:sum` returns the sum over all points.  Negative or NaN coordinates raise an error
-(the reference's digit loop does not terminate on them).
+ones.  `reduce = :sum` returns the sum over all points, `:abs2` the sum of |f|^2, `:weighted` (with
+`weights`, one real weight per point) the weighted sum — the fused quadrature functionals, computed in
+the kernels' epilogues without writing the values.  Negative or NaN coordinates raise an error (the
+reference's digit loop does not terminate on them).
 """
 function evaluate(fitn::ITensorNetworkFunction, points::AbstractMatrix,
-  dims::Vector{<:Int}=dimensions(fitn); alg=default_contraction_alg(), reduce::Symbol=:none, device=0)
+  dims::Vector{<:Int}=dimensions(fitn); alg=default_contraction_alg(), reduce::Symbol=:none,
+  weights::Union{Nothing,Vector{Float64}}=nothing, device=0)
   @assert size(points, 1) == length(dims)
   pl = plan(fitn, dims; device)
   coords = coords_matrix(pl.packed, points)
   npts = size(coords, 2)
   T = pl.packed.is_complex ? ComplexF64 : Float64
-  out = reduce == :sum ? T[] : Vector{T}(undef, npts)
-  opts = TTNOpts(; reduce_sum=(reduce == :sum))
-  GC.@preserve coords out pl begin
+  out = reduce == :none ? Vector{T}(undef, npts) : T[]
+  w = weights === nothing ? Float64[] : weights
+  reduce == :weighted && @assert length(w) == npts
+  opts = TTNOpts(; reduce, weights=(reduce == :weighted ? pointer(w) : Ptr{Float64}(C_NULL)))
+  GC.@preserve coords out pl w begin
     rc = ccall((:ttn_evaluate, LIBTTNEVAL), Cint,
       (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Cvoid}, Ref{TTNOpts}),
       pl.handle, coords, npts, size(coords, 1), TTN_LAYOUT_AOS,
-      reduce == :sum ? C_NULL : pointer(out), opts)
+      reduce == :none ? pointer(out) : C_NULL, opts)
   end
   rc == 0 || error("ttn_evaluate: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
-  reduce == :sum && return pl.packed.is_complex ? complex(opts.sum_re, opts.sum_im) : opts.sum_re
-  return out
+  reduce == :none && return out
+  return (pl.packed.is_complex && reduce != :abs2) ? complex(opts.sum_re, opts.sum_im) : opts.sum_re
 end
 
 function evaluate(fitn::ITensorNetworkFunction, points::Vector{<:Vector},
   dims::Vector{<:Int}=dimensions(fitn); kwargs...)
   return evaluate(fitn, reduce(hcat, points), dims; kwargs...)
+end
+
+# mirror of `struct ttn_grid`
+struct TTNGrid
+  n_coords::Int32
+  step::Ptr{Float64}
+  count::Ptr{Int64}
+  first::Int64
+  npts::Int64
+end
+
+"""
+    evaluate_grid(fitn, N::Int, dims=dimensions(fitn); reduce=:sum, values=false, device=0)
+
+`fitn` on the Cartesian product of `grid_points(fitn, N, d)`, `d in dims`
+(src/IndexMaps/realindexmap.jl:78-86; first dimension slowest), generated on the device: no coordinate
+array exists on either side.  Returns the reduction (`reduce = :sum`: with `N = base^L` this is
+`integrate(fitn; take_sum=true)`, src/integration.jl:6-17), the values (`values = true`), or both as a tuple.
+The loop it replaces: examples/2d_laplace_solver.jl:46-53.  On the full dyadic grid of an MPS the
+library shares the common digit prefixes of neighbouring grid points.
+"""
+function evaluate_grid(fitn::ITensorNetworkFunction, N::Int, dims::Vector{<:Int}=dimensions(fitn);
+  reduce::Symbol=:sum, values::Bool=false, device=0)
+  imap = indexmap(fitn)
+  @assert imap isa RealIndexMap "grid evaluation is defined for real index maps (grid_points)"
+  pl = plan(fitn, dims; device)
+  grids = [grid_points(imap, N, d) for d in dims]
+  steps = Float64[length(g) > 1 ? g[2] : 0.0 for g in grids]
+  counts = Int64[length(g) for g in grids]
+  npts = prod(counts)
+  T = pl.packed.is_complex ? ComplexF64 : Float64
+  out = values ? Vector{T}(undef, npts) : T[]
+  opts = TTNOpts(; reduce)
+  GC.@preserve steps counts out pl begin
+    grid = TTNGrid(Int32(length(dims)), pointer(steps), pointer(counts), 0, npts)
+    rc = ccall((:ttn_evaluate_grid, LIBTTNEVAL), Cint, (Ptr{Cvoid}, Ref{TTNGrid}, Ptr{Cvoid}, Ref{TTNOpts}),
+      pl.handle, grid, values ? pointer(out) : C_NULL, opts)
+  end
+  rc == 0 || error("ttn_evaluate_grid: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
+  red = (pl.packed.is_complex && reduce != :abs2) ? complex(opts.sum_re, opts.sum_im) : opts.sum_re
+  return reduce == :none ? out : (values ? (red, out) : red)
+end
+
+"""
+    evaluate_indices(fitn, ind_to_ind_value_maps::Vector; device=0)
+
+Batched `project` + `scalar` (src/itensornetworkfunction.jl:84-106) at given index settings — what
+`calculate_ind_values` returns, one dictionary per point — without the coordinate -> digit step: the inner
+loop of TCI (ext/ITensorNumericalAnalysisTCIExt/tci_util.jl:21-55) evaluates its pivots and fibres this way.
+"""
+function evaluate_indices(fitn::ITensorNetworkFunction, ind_to_ind_value_maps::Vector; device=0)
+  pl = plan(fitn, dimensions(fitn); device)
+  sites = pl.packed.site_inds
+  npts = length(ind_to_ind_value_maps)
+  iv = Matrix{UInt8}(undef, length(sites), npts)       # column-major [site, point] == C [point][site]
+  for (j, m) in enumerate(ind_to_ind_value_maps), (i, ind) in enumerate(sites)
+    iv[i, j] = UInt8(m[ind])
+  end
+  T = pl.packed.is_complex ? ComplexF64 : Float64
+  out = Vector{T}(undef, npts)
+  opts = TTNOpts()
+  GC.@preserve iv out pl begin
+    rc = ccall((:ttn_evaluate_indices, LIBTTNEVAL), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ptr{Cvoid}, Ref{TTNOpts}),
+      pl.handle, iv, npts, pointer(out), opts)
+  end
+  rc == 0 || error("ttn_evaluate_indices: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
+  return out
+end
+
+"""
+    ind_values(fitn, points::AbstractMatrix, dims=dimensions(fitn)) -> (Matrix{UInt8}, Vector{Index})
+
+Batched `calculate_ind_values` (src/IndexMaps/realindexmap.jl:67-76, complexindexmap.jl:116-132): entry
+`[s, j]` is the value chosen for site index `site_inds[s]` at point `j`; bit-identical to the reference's
+greedy loop (the thresholds come from the reference's own `index_value_to_scalar`).
+"""
+function ind_values(fitn::ITensorNetworkFunction, points::AbstractMatrix, dims::Vector{<:Int}=dimensions(fitn); device=0)
+  pl = plan(fitn, dims; device)
+  coords = coords_matrix(pl.packed, points)
+  npts = size(coords, 2)
+  dig = Matrix{UInt8}(undef, length(pl.packed.site_inds), npts)
+  opts = TTNOpts()
+  GC.@preserve coords dig pl begin
+    rc = ccall((:ttn_digits, LIBTTNEVAL), Cint,
+      (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{UInt8}, Ref{TTNOpts}),
+      pl.handle, coords, npts, size(coords, 1), TTN_LAYOUT_AOS, dig, opts)
+  end
+  rc == 0 || error("ttn_digits: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
+  return dig, pl.packed.site_inds
 end
