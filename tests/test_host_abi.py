@@ -116,3 +116,40 @@ def test_grid_points_matches_reference_formula():
     assert gp == [i / 16 for i in range(16)]
     gp = s.grid_points(5, 1)       # a = round(16/5) = 3
     assert gp == [i * (3 / 16) for i in range(6)]
+
+
+def test_julia_struct_mirrors_match_the_ctypes_layouts():
+    """The Julia side (julia/TTNEvalB200.jl) is written, not executed here: keep its struct mirrors of ttn_desc /
+    ttn_opts / ttn_grid in lock-step with the ctypes structs (which test_struct_layouts_match_header pins to the
+    header) — same field order, same sizes — and its ccall symbols inside the exported set."""
+    src = open(os.path.join(ROOT, "itensornumericalanalysis.jl_b200", "julia", "TTNEvalB200.jl")).read()
+    size = {"Int32": 4, "Int64": 8, "Float32": 4, "Float64": 8}
+
+    def julia_fields(name):
+        body = re.search(r"struct " + name + r"\n(.*?)\nend", src, re.S).group(1)
+        out = []
+        for line in body.splitlines():
+            m = re.match(r"\s*(\w+)::([\w{}]+)", line)
+            if m:
+                out.append((m.group(1), 8 if m.group(2).startswith("Ptr") else size[m.group(2)]))
+        return out
+
+    def ctypes_fields(st):
+        out = []
+        for fname, ftype in st._fields_:
+            n = C.sizeof(ftype)
+            if issubclass(ftype, C.Array):      # sum_out[2] is two Float64 fields on the Julia side
+                out += [(fname, C.sizeof(ftype._type_))] * ftype._length_
+            else:
+                out.append((fname, n))
+        return out
+
+    for jl, st in (("TTNDesc", _capi.ttn_desc), ("TTNOpts", _capi.ttn_opts), ("TTNGrid", _capi.ttn_grid)):
+        a, b = julia_fields(jl), ctypes_fields(st)
+        assert [s for _, s in a] == [s for _, s in b], (jl, a, b)
+        for (ja, _), (cb, _) in zip(a, b):
+            assert ja == cb or cb == "sum_out" and ja in ("sum_re", "sum_im"), (jl, ja, cb)
+    called = set(re.findall(r"ccall\(\(:(ttn_\w+), LIBTTNEVAL\)", src))
+    assert called <= set(_capi.EXPORTS)
+    assert {"ttn_plan_create", "ttn_plan_destroy", "ttn_evaluate", "ttn_evaluate_grid", "ttn_evaluate_indices",
+            "ttn_digits", "ttn_last_error"} <= called
