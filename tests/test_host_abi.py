@@ -153,3 +153,25 @@ def test_julia_struct_mirrors_match_the_ctypes_layouts():
     assert called <= set(_capi.EXPORTS)
     assert {"ttn_plan_create", "ttn_plan_destroy", "ttn_evaluate", "ttn_evaluate_grid", "ttn_evaluate_indices",
             "ttn_digits", "ttn_last_error"} <= called
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/ttneval.h must be usable from any FFI: compile examples/c_abi_example.c as strict C11 against it,
+    link libttneval.so and run it.  Without a GPU the example reports TTN_ERR_CUDA from ttn_plan_create (no CPU
+    fallback) and exits 0; with one it prints f(x) = 1 + x_trunc."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    csrc = os.path.join(ROOT, "itensornumericalanalysis.jl_b200", "csrc")
+    exe = str(tmp_path / "c_abi_example")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L" + csrc, "-lttneval",
+                           "-Wl,-rpath," + csrc, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "libttneval ABI %d" % _capi.TTN_ABI_VERSION in r.stdout
+    if _capi.lib().ttn_device_count() == 0:
+        assert "no CUDA device" in r.stdout
+    else:
+        assert "f(0.375) = 1.375000" in r.stdout and "f(0.999) = 1.875000" in r.stdout
