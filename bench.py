@@ -16,6 +16,9 @@ the network replicated; there is no data-path collective, SURVEY §8 e).
           measured in this very run (MEASURED_PEAKS.json has no FP64 entry).  Plan-time group merging
           makes executed < the SURVEY §8(d) rule; the rule-based figure is reported beside it as
           algorithmic_achieved / algorithmic_frac
+          Small-chi workloads (--config 6: chi = 1 product state, --config 7: chi = 2, both on config 2's layout and
+          point set) run the table kernel and report an HBM roofline instead: algorithmic bytes (8 B per coordinate
+          read + 8 / 16 B per value written) / kernel time against MEASURED_PEAKS.json's hbm_gbs
   cpu_baseline  the oracle's reference-style evaluation (two-way BP + exp(sum log), what
           scalar(alg="bp") does per point) timed on this box's host cores on a bounded sample
 
