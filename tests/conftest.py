@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # built artefacts are git-ignored: on a fresh checkout compile them first (nvcc cross-compiles without a GPU)
+    so = os.path.join(ROOT, "itensornumericalanalysis.jl_b200", "csrc", "libttneval.so")
+    orc_so = os.path.join(ROOT, "oracle", "libttn_oracle.so")
+    if not (os.path.exists(so) and os.path.exists(orc_so)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu():
