@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TTN_ABI_VERSION 2
+#define TTN_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------ */
 enum {
@@ -59,6 +59,24 @@ enum {
 enum {
   TTN_MEM_HOST = 0,  /* host pointers; H2D / D2H copies happen inside the call */
   TTN_MEM_DEVICE = 1 /* device pointers on the plan's device; no copies */
+};
+
+/* ---- pageable host buffers (ABI 3).  cudaMemcpyAsync from pageable memory is staged by the driver on one thread
+ * and collapses the H2D / kernel / D2H pipeline, so ttn_evaluate copies pageable buffers through an internal
+ * pinned ring with several host threads (TTN_HOST_THREADS, default min(8, cores)).  Buffers the caller pinned
+ * (cudaHostAlloc / ttn_host_register) are used in place.  A registration is never cached across calls: a stale
+ * one would outlive a freed Julia / numpy array. */
+enum {
+  TTN_STAGE_AUTO = 0, /* pinned buffers in place, pageable buffers through the staging ring */
+  TTN_STAGE_OFF = 1   /* hand every host pointer straight to cudaMemcpyAsync */
+};
+
+/* ---- accuracy modes (ABI 3) */
+enum {
+  TTN_ACCURACY_FP64 = 0,    /* plain FP64 kernels (every BASELINE number) */
+  TTN_ACCURACY_REFINED = 1  /* FP64 kernels, then the points whose value is small against the RMS of the batch
+                               (cancellation: the only points whose floored relative error can exceed 1e-12) are
+                               re-evaluated by a double-double kernel and overwritten */
 };
 
 /* ---- fused quadrature functionals: what is accumulated over the evaluated points.
@@ -164,6 +182,15 @@ typedef struct ttn_opts {
   double flops_executed; /* FP64 flops the kernels of this call executed.  <= flops_per_point * npts (the
                             SURVEY 8(d) rule): plan-time contraction (merged chain positions, leaf/root and
                             subtree tables) and the grid kernel's prefix sharing remove work */
+  /* inputs (appended in ABI 3) */
+  int32_t host_staging;  /* TTN_STAGE_*: what to do with PAGEABLE host buffers (a Julia Array, a numpy array) */
+  int32_t accuracy;      /* TTN_ACCURACY_* */
+  double refine_tau;     /* TTN_ACCURACY_REFINED: points with |f| < refine_tau * rms(f over this call) are
+                            re-evaluated in double-double arithmetic; 0 = default (0.02) */
+  /* outputs (ABI 3) */
+  int32_t n_devices_used; /* GPUs that took part in this call (multi-device plans shard the points) */
+  int32_t staged;         /* bit 0: coords went through the pinned staging ring, bit 1: out did */
+  int64_t n_refined;      /* points re-evaluated by TTN_ACCURACY_REFINED */
 } ttn_opts;
 
 /* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:
@@ -185,7 +212,7 @@ typedef struct ttn_info {
   int32_t auto_kernel;       /* TTN_KERNEL_* chosen by the planner */
   int32_t device;
   int32_t kernels_available; /* bit k set: TTN_KERNEL_k can run this network */
-  int32_t reserved_;
+  int32_t n_devices;         /* 1, or the number of GPUs of a ttn_plan_create_multi plan */
   double flops_per_point;    /* SURVEY §8(d) flop rule: 2 (real) / 8 (complex) * sum of MACs */
   double bytes_per_point;    /* 8 * n_coords read + 8/16 written */
   int64_t tensor_bytes;
@@ -196,6 +223,13 @@ typedef struct ttn_plan ttn_plan; /* opaque; owns all device memory and streams 
 /* Build a plan on CUDA device `device` (>= 0).  Replaces the per-point `copy(fitn)` +
  * dictionary construction of the reference (itensornetworkfunction.jl:85, realindexmap.jl:69). */
 int ttn_plan_create(const ttn_desc* desc, int32_t device, ttn_plan** out);
+/* The same plan replicated on n_devices GPUs of this process (devices[i], or 0..n_devices-1 when devices is
+ * NULL) — SURVEY 8(b),(e): one process drives all GPUs of the box.  Every ttn_evaluate* call on such a plan
+ * splits its points into n_devices contiguous blocks (GPU g takes [g*ceil(n/G), ...)), each GPU copies its
+ * block in and its values out on its own streams (host buffers: straight into / out of the caller's arrays;
+ * device buffers on another GPU: peer copies over NVLink), there is no exchange step, and for reduce_sum != 0
+ * the per-GPU sums are added on the host in device order (deterministic).  `device` of ttn_info is devices[0]. */
+int ttn_plan_create_multi(const ttn_desc* desc, int32_t n_devices, const int32_t* devices, ttn_plan** out);
 void ttn_plan_destroy(ttn_plan* plan);
 int ttn_plan_info(const ttn_plan* plan, ttn_info* info);
 
@@ -223,6 +257,11 @@ int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coo
 /* FP64 roofline denominators measured on the plan's device: a dependent-free DFMA loop
  * (vector pipe) and an mma.sync m8n8k4 f64 loop (DMMA pipe); TFLOP/s. */
 int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);
+
+/* Pin / unpin a caller-owned host range (cudaHostRegister, portable) so that ttn_evaluate uses it in place at
+ * the full PCIe rate.  The caller must unregister before freeing the memory. */
+int ttn_host_register(void* ptr, uint64_t bytes);
+int ttn_host_unregister(void* ptr);
 
 const char* ttn_last_error(void);
 int ttn_device_count(void);

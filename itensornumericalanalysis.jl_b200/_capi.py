@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libttneval.so")
 
-TTN_ABI_VERSION = 2
+TTN_ABI_VERSION = 3
 TTN_OK, TTN_ERR_INVALID, TTN_ERR_DOMAIN, TTN_ERR_CUDA, TTN_ERR_UNSUPPORTED, TTN_ERR_NOMEM = range(6)
 TTN_LAYOUT_AOS, TTN_LAYOUT_SOA = 0, 1
 TTN_MEM_HOST, TTN_MEM_DEVICE = 0, 1
@@ -17,6 +17,9 @@ KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm", 5: "t
 KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 TTN_REDUCE_NONE, TTN_REDUCE_SUM, TTN_REDUCE_ABS2, TTN_REDUCE_WEIGHTED = range(4)
 REDUCE_IDS = {None: 0, False: 0, "none": 0, True: 1, "sum": 1, "abs2": 2, "weighted": 3}
+TTN_STAGE_AUTO, TTN_STAGE_OFF = 0, 1
+TTN_ACCURACY_FP64, TTN_ACCURACY_REFINED = 0, 1
+ACCURACY_IDS = {None: 0, "fp64": 0, "refined": 1}
 
 
 class ttn_desc(C.Structure):
@@ -56,6 +59,12 @@ class ttn_opts(C.Structure):
         ("weights_mem", C.c_int32),
         ("reserved_", C.c_int32),
         ("flops_executed", C.c_double),
+        ("host_staging", C.c_int32),
+        ("accuracy", C.c_int32),
+        ("refine_tau", C.c_double),
+        ("n_devices_used", C.c_int32),
+        ("staged", C.c_int32),
+        ("n_refined", C.c_int64),
     ]
 
 
@@ -80,7 +89,7 @@ class ttn_info(C.Structure):
         ("auto_kernel", C.c_int32),
         ("device", C.c_int32),
         ("kernels_available", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("n_devices", C.c_int32),
         ("flops_per_point", C.c_double),
         ("bytes_per_point", C.c_double),
         ("tensor_bytes", C.c_int64),
@@ -88,7 +97,7 @@ class ttn_info(C.Structure):
 
 
 EXPORTS = [
-    "ttn_plan_create", "ttn_plan_destroy", "ttn_plan_info", "ttn_evaluate", "ttn_evaluate_grid",
+    "ttn_plan_create", "ttn_plan_create_multi", "ttn_host_register", "ttn_host_unregister", "ttn_plan_destroy", "ttn_plan_info", "ttn_evaluate", "ttn_evaluate_grid",
     "ttn_evaluate_indices",
     "ttn_digits", "ttn_measure_fp64_peak", "ttn_last_error", "ttn_device_count",
     "ttn_abi_version",
@@ -116,6 +125,12 @@ def lib():
     vp = C.c_void_p
     L.ttn_plan_create.argtypes = [C.POINTER(ttn_desc), C.c_int32, C.POINTER(vp)]
     L.ttn_plan_create.restype = C.c_int
+    L.ttn_plan_create_multi.argtypes = [C.POINTER(ttn_desc), C.c_int32, C.POINTER(C.c_int32), C.POINTER(vp)]
+    L.ttn_plan_create_multi.restype = C.c_int
+    L.ttn_host_register.argtypes = [vp, C.c_uint64]
+    L.ttn_host_register.restype = C.c_int
+    L.ttn_host_unregister.argtypes = [vp]
+    L.ttn_host_unregister.restype = C.c_int
     L.ttn_plan_destroy.argtypes = [vp]
     L.ttn_plan_destroy.restype = None
     L.ttn_plan_info.argtypes = [vp, C.POINTER(ttn_info)]

@@ -212,6 +212,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // group merging (merge_groups): k vertices per stream position when the slice indices are bit
   // fields, the merged position has <= 16 slices and one position's matrices stay <= 32 KB (one
   // ring stage).  TTN_MMA_MERGE caps k (0 or 1: one vertex per position).
+  p->v6_teams = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
   int kmerge = 1;
   {
     // measured on B200 (scripts/merge_probe.py): 4 > 3 > 2 > 1 for binary chains; TTN_MMA_MERGE=k
@@ -223,7 +224,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     }
     // the team-sorted kernel (v6) reads site matrices straight from L2 into registers: no ring-stage
     // limit and up to 32 slices per position; the ring kernels take <= 16 slices and <= 32 KB per position
-    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && p->all_base2;
+    const bool v6_on = p->v6_teams != 0 && p->all_base2;
     if (NSL0 == 2 || NSL0 == 4)
       for (int kk : cand) {
         const int sb = bits0 * kk;
@@ -240,7 +241,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // (<= 128 MB each); a point gathers one row of each and runs only the middle groups as rounds.
   int kL = kmerge, kR = kmerge;
   {
-    const bool v6_on = !(getenv("TTN_MMA_V6") && atoi(getenv("TTN_MMA_V6")) == 0) && p->all_base2;
+    const bool v6_on = p->v6_teams != 0 && p->all_base2;
     // default: only when the two tables absorb the WHOLE chain with <= 2^16 rows each (L2-resident,
     // built in a fraction of a second): the evaluation is then two row gathers and a dot product.
     // TTN_MMA_DEEP=b sets the budget to 2^b rows of 16 doubles for any chain (0 disables); measured

@@ -424,14 +424,11 @@ static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
 
 // Applies to merged binary chains (build_chain_mma) of width 8, 16 or 32.  TTN_MMA_V6=0 switches the
 // kernel off (the ring kernels then run the merged image), =2 runs two teams per CTA (experiments).
-static int team_count() {
-  static const int v6 = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
-  return v6;
-}
+// The team count is a plan-time knob (ttn_plan::v6_teams, read from TTN_MMA_V6 by ttn_plan_create).
 
 bool chain_team_applicable(const ttn_plan* p) {
   const ChainMmaDev& c = p->cmma;
-  if (!team_count() || !c.merged || !p->all_base2 || c.spr != 1) return false;
+  if (!p->v6_teams || !c.merged || !p->all_base2 || c.spr != 1) return false;
   if (c.chi == 8 || c.chi == 16) return c.nsl == 4 || c.nsl == 8 || c.nsl == 16 || c.nsl == 32;
   return c.chi == 32 && (c.nsl == 4 || c.nsl == 8 || c.nsl == 16);
 }
@@ -439,7 +436,7 @@ bool chain_team_applicable(const ttn_plan* p) {
 int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                       cudaStream_t s) {
   const ChainMmaDev& c = p->cmma;
-  const int v6 = team_count();
+  const int v6 = p->v6_teams;
   if (v6 && c.merged && p->all_base2 && c.spr == 1) {
 #define TTN_V6_CASE(W, N)                                                                                   \
   if (c.chi == W && c.nsl == N)                                                                             \

@@ -1,11 +1,18 @@
 // C ABI of libttneval.so (include/ttneval.h): plan construction, chunked/pipelined evaluation,
 // error reporting.  Everything here is host code around the kernels in k_*.cu.
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <new>
 #include <numeric>
+#include <thread>
 
 #include "ttn_internal.h"
 
@@ -212,9 +219,28 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   return TTN_OK;
 }
 
+// Every entry point runs on the plan's device and restores the caller's current device on exit (a GC-driven
+// ttn_plan_destroy must not move a torch / CUDA.jl caller to another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static void destroy_plan(ttn_plan* p) {
   if (!p) return;
-  cudaSetDevice(p->device);
+  for (ttn_plan* r : p->replicas) destroy_plan(r);
+  p->replicas.clear();
+  DeviceGuard guard(p->device);
   for (auto& st : p->streams) {
     if (st.s) cudaStreamSynchronize(st.s);
     if (st.d_coords) cudaFree(st.d_coords);
@@ -225,11 +251,20 @@ static void destroy_plan(ttn_plan* p) {
     if (st.d_partial) cudaFree(st.d_partial);
     if (st.d_gemm) cudaFree(st.d_gemm);
     if (st.d_partial2) cudaFree(st.d_partial2);
+    if (st.d_sel) cudaFree(st.d_sel);
+    if (st.d_refine) cudaFree(st.d_refine);
+    if (st.h_coords) cudaFreeHost(st.h_coords);
+    if (st.h_out) cudaFreeHost(st.h_out);
+    if (st.h_weights) cudaFreeHost(st.h_weights);
+    if (st.h_digits) cudaFreeHost(st.h_digits);
     if (st.k0) cudaEventDestroy(st.k0);
     if (st.k1) cudaEventDestroy(st.k1);
+    if (st.ev_h2d) cudaEventDestroy(st.ev_h2d);
+    if (st.ev_d2h) cudaEventDestroy(st.ev_d2h);
     if (st.s) cudaStreamDestroy(st.s);
   }
   for (void* a : p->allocs) cudaFree(a);
+  if (p->d_grid_out) cudaFree(p->d_grid_out);
   if (p->d_err) cudaFree(p->d_err);
   if (p->d_sum) cudaFree(p->d_sum);
   if (p->t0) cudaEventDestroy(p->t0);
@@ -263,6 +298,113 @@ static int run_kernel(ttn_plan* p, int kernel, Stream& st, const CoordSource& sr
 
 constexpr int kMaxChunks = 4096;
 
+// ---- host staging pool ------------------------------------------------------------------------------------
+// cudaMemcpyAsync on PAGEABLE memory (a Julia Array, a numpy array) is staged by the driver on the calling
+// thread at 10-20 GB/s and serialises the H2D / kernel / D2H pipeline.  Pageable chunks are therefore copied
+// to / from a pinned ring (Stream::h_*) by a small pool of host threads, slice by slice.  The pool is a
+// process-wide leaked singleton (worker threads must not be joined from a library destructor).
+class CopyPool {
+ public:
+  static CopyPool& get() {
+    static CopyPool* pool = new CopyPool();
+    return *pool;
+  }
+  // dst[0:bytes) = src[0:bytes), in parallel; returns when done.  The caller takes slices too.
+  void copy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kSlice = (size_t)1 << 20;
+    if (bytes <= 2 * kSlice || workers_ == 0) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    auto job = std::make_shared<Job>();
+    job->dst = static_cast<char*>(dst);
+    job->src = static_cast<const char*>(src);
+    job->bytes = bytes;
+    job->n_slices = (bytes + kSlice - 1) / kSlice;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      jobs_.push_back(job);
+    }
+    cv_.notify_all();
+    work_on(*job);
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->cv.wait(lk, [&] { return job->done.load() == job->n_slices; });
+  }
+  int threads() const { return workers_ + 1; }
+
+ private:
+  struct Job {
+    char* dst;
+    const char* src;
+    size_t bytes, n_slices;
+    std::atomic<size_t> next{0}, done{0};
+    std::mutex mu;
+    std::condition_variable cv;
+  };
+  CopyPool() {
+    int n = 8;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(8, std::max(1, CPU_COUNT(&set)));
+    if (const char* e = getenv("TTN_HOST_THREADS")) n = std::max(1, std::min(atoi(e), 64));
+    workers_ = n - 1;
+    for (int i = 0; i < workers_; ++i) std::thread([this] { worker(); }).detach();
+  }
+  static void work_on(Job& j) {
+    constexpr size_t kSlice = (size_t)1 << 20;
+    for (;;) {
+      const size_t i = j.next.fetch_add(1);
+      if (i >= j.n_slices) return;
+      const size_t off = i * kSlice, len = std::min(kSlice, j.bytes - off);
+      memcpy(j.dst + off, j.src + off, len);
+      if (j.done.fetch_add(1) + 1 == j.n_slices) {
+        std::lock_guard<std::mutex> lk(j.mu);
+        j.cv.notify_all();
+      }
+    }
+  }
+  void worker() {
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] {
+          while (!jobs_.empty() && jobs_.front()->next.load() >= jobs_.front()->n_slices) jobs_.pop_front();
+          return !jobs_.empty();
+        });
+        job = jobs_.front();
+      }
+      work_on(*job);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::shared_ptr<Job>> jobs_;
+  int workers_ = 0;
+};
+
+// How a caller buffer is reached from the plan's device.
+enum Space {
+  SPACE_NONE = 0,
+  SPACE_DIRECT,   // device memory of the plan's device (or managed): kernels use the pointer
+  SPACE_ASYNC,    // pinned host memory or another GPU's memory: cudaMemcpyAsync in place (PCIe / NVLink peer copy)
+  SPACE_PAGEABLE  // pageable host memory: through the pinned staging ring
+};
+
+static Space classify(const void* ptr, int declared_mem, int device, int host_staging, size_t bytes) {
+  if (!ptr) return SPACE_NONE;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return declared_mem == TTN_MEM_DEVICE ? SPACE_DIRECT : SPACE_ASYNC;
+  }
+  if (a.type == cudaMemoryTypeDevice) return a.device == device ? SPACE_DIRECT : SPACE_ASYNC;
+  if (a.type == cudaMemoryTypeManaged) return SPACE_DIRECT;
+  if (a.type == cudaMemoryTypeHost) return SPACE_ASYNC;
+  // unregistered host memory; small buffers are not worth the ring
+  if (host_staging == TTN_STAGE_OFF || bytes < ((size_t)4 << 20)) return SPACE_ASYNC;
+  return SPACE_PAGEABLE;
+}
+
 static int ensure_stream_buffers(ttn_plan* p, Stream& st, int64_t chunk, bool need_coords, bool need_out) {
   const int NC = p->info.is_complex ? 2 : 1;
   if (st.cap_points < chunk || (need_coords && !st.d_coords) || (need_out && !st.d_out)) {
@@ -277,111 +419,185 @@ static int ensure_stream_buffers(ttn_plan* p, Stream& st, int64_t chunk, bool ne
     TTN_CUDA(cudaMalloc(&st.d_weights, sizeof(double) * (size_t)chunk));
     st.cap_points = chunk;
   }
-  const size_t pc = (size_t)2 * (p->sm_count * 8 + 8);
+  const size_t pc = (size_t)3 * (p->sm_count * 8 + 8);
   if (st.partial_cap < pc) {
     if (st.d_partial) cudaFree(st.d_partial);
+    st.d_partial = nullptr;
+    st.partial_cap = 0;
     TTN_CUDA(cudaMalloc(&st.d_partial, pc * sizeof(double)));
     st.partial_cap = pc;
   }
   return TTN_OK;
 }
 
-// Shared driver of ttn_evaluate / ttn_evaluate_grid.
+// pinned staging ring of one stream (allocated on the first pageable call, at chunk capacity)
+static int ensure_host_ring(ttn_plan* p, Stream& st, int64_t chunk, bool coords, bool out, bool weights) {
+  const int NC = p->info.is_complex ? 2 : 1;
+  if (st.h_cap_points < chunk) {
+    if (st.h_coords) cudaFreeHost(st.h_coords);
+    if (st.h_out) cudaFreeHost(st.h_out);
+    if (st.h_weights) cudaFreeHost(st.h_weights);
+    st.h_coords = st.h_out = st.h_weights = nullptr;
+    st.h_cap_points = chunk;
+  }
+  if (coords && !st.h_coords)
+    TTN_CUDA(cudaHostAlloc(&st.h_coords, sizeof(double) * (size_t)st.h_cap_points * std::max(p->info.n_coords, 1), cudaHostAllocPortable));
+  if (out && !st.h_out) TTN_CUDA(cudaHostAlloc(&st.h_out, sizeof(double) * (size_t)st.h_cap_points * NC, cudaHostAllocPortable));
+  if (weights && !st.h_weights) TTN_CUDA(cudaHostAlloc(&st.h_weights, sizeof(double) * (size_t)st.h_cap_points, cudaHostAllocPortable));
+  if (!st.ev_h2d) TTN_CUDA(cudaEventCreateWithFlags(&st.ev_h2d, cudaEventDisableTiming));
+  if (!st.ev_d2h) TTN_CUDA(cudaEventCreateWithFlags(&st.ev_d2h, cudaEventDisableTiming));
+  return TTN_OK;
+}
+
+static int validate_opts(const ttn_opts* opts, const void* out) {
+  if (opts->reduce_sum < 0 || opts->reduce_sum > TTN_REDUCE_WEIGHTED) return fail(TTN_ERR_INVALID, "bad reduce mode");
+  if (opts->reduce_sum == TTN_REDUCE_WEIGHTED && !opts->weights) return fail(TTN_ERR_INVALID, "TTN_REDUCE_WEIGHTED needs opts->weights");
+  if (!out && opts->reduce_sum == TTN_REDUCE_NONE) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
+  if (opts->accuracy != TTN_ACCURACY_FP64 && opts->accuracy != TTN_ACCURACY_REFINED) return fail(TTN_ERR_INVALID, "bad accuracy mode");
+  if (opts->host_staging != TTN_STAGE_AUTO && opts->host_staging != TTN_STAGE_OFF) return fail(TTN_ERR_INVALID, "bad host_staging mode");
+  if (!(opts->refine_tau >= 0.0) || opts->refine_tau > 1e3) return fail(TTN_ERR_INVALID, "refine_tau must be in [0, 1000]");
+  return TTN_OK;
+}
+
+// Shared driver of ttn_evaluate / ttn_evaluate_grid / ttn_evaluate_indices on ONE device.
+// soa_stride: distance (in points) between two coordinate slots of a host / peer SOA array (the whole call's
+// npts; a multi-device block is a sub-range of it).
 static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, void* out, ttn_opts* opts,
-                         const uint8_t* digits = nullptr) {
+                         const uint8_t* digits = nullptr, int64_t soa_stride = 0) {
   std::lock_guard<std::mutex> lock(p->mu);
-  TTN_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(TTN_ERR_CUDA, "cudaSetDevice failed");
   const auto wall0 = std::chrono::steady_clock::now();
   const int NC = p->info.is_complex ? 2 : 1;
   const int64_t npts = base.npts;
+  if (soa_stride == 0) soa_stride = npts;
+  opts->sum_out[0] = opts->sum_out[1] = 0.0;
+  opts->kernel_ms = opts->total_ms = 0.f;
+  opts->n_launches = 0;
+  opts->n_devices_used = 1;
+  opts->staged = 0;
+  opts->n_refined = 0;
+  opts->flops_executed = 0.0;
+  int rc = validate_opts(opts, out);
+  if (rc) return rc;
+  if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
+  const bool refine = opts->accuracy == TTN_ACCURACY_REFINED;
+  const double tau = opts->refine_tau > 0.0 ? opts->refine_tau : 0.02;
+  const bool do_sum = opts->reduce_sum != TTN_REDUCE_NONE;
+  const int n_sites = std::max(p->info.n_sites, 1);
+
+  const Space sp_out = classify(out, opts->out_mem, p->device, opts->host_staging, sizeof(double) * (size_t)npts * NC);
+  const Space sp_w = opts->reduce_sum == TTN_REDUCE_WEIGHTED
+                         ? classify(opts->weights, opts->weights_mem, p->device, opts->host_staging, sizeof(double) * (size_t)npts)
+                         : SPACE_NONE;
+
   // full dyadic grid of a binary chain: prefix-shared expansion (one pass over the whole grid)
-  if (base.grid && (opts->kernel == TTN_KERNEL_AUTO || opts->kernel == TTN_KERNEL_GRID) && grid_share_applicable(p, base) &&
-      !(opts->reduce_sum == TTN_REDUCE_WEIGHTED && opts->weights_mem == TTN_MEM_HOST)) {
-    opts->sum_out[0] = opts->sum_out[1] = 0.0;
+  if (base.grid && !refine && (opts->kernel == TTN_KERNEL_AUTO || opts->kernel == TTN_KERNEL_GRID) && grid_share_applicable(p, base) &&
+      (sp_w == SPACE_NONE || sp_w == SPACE_DIRECT)) {
     opts->kernel_used = TTN_KERNEL_GRID;
-    opts->n_launches = 0;
-    const bool do_sum_g = opts->reduce_sum != TTN_REDUCE_NONE;
-    if (!out && !do_sum_g) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
+    if (npts == 0) return TTN_OK;
     Stream& st = p->streams[0];
-    int rc = ensure_stream_buffers(p, st, 1, false, false);
+    rc = ensure_stream_buffers(p, st, 1, false, false);
     if (rc) return rc;
     double* d_out = reinterpret_cast<double*>(out);
-    double* tmp = nullptr;
-    const bool out_host_g = out && opts->out_mem == TTN_MEM_HOST;
-    if (out_host_g) {
-      TTN_CUDA(cudaMalloc(&tmp, sizeof(double) * (size_t)base.npts * NC));
-      d_out = tmp;
-    }
-    CoordSource src = base;
-    src.reduce_mode = opts->reduce_sum;
-    src.weights = opts->reduce_sum == TTN_REDUCE_WEIGHTED ? opts->weights : nullptr;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, st.s);
-    int n_partial = 0;
-    double flops = 0.0;
-    rc = launch_grid_share(p, st, src, d_out, do_sum_g ? st.d_partial : nullptr, &n_partial, st.s, &opts->n_launches, &flops);
-    if (rc == TTN_OK && do_sum_g) {
-      rc = launch_sum_partials(p, st.d_partial, n_partial, NC, p->d_sum, st.s);
-      opts->n_launches += 1;
-    }
-    cudaEventRecord(e1, st.s);
-    if (rc == TTN_OK && out_host_g)
-      cudaMemcpyAsync(out, tmp, sizeof(double) * (size_t)base.npts * NC, cudaMemcpyDeviceToHost, st.s);
-    const cudaError_t e = cudaStreamSynchronize(st.s);
-    if (rc == TTN_OK && e != cudaSuccess) rc = fail(TTN_ERR_CUDA, std::string("grid kernel: ") + cudaGetErrorString(e));
-    if (rc == TTN_OK) {
-      cudaEventElapsedTime(&opts->kernel_ms, e0, e1);
-      opts->flops_executed = flops;
-      if (do_sum_g) {
-        double hs[2];
-        cudaMemcpy(hs, p->d_sum, sizeof(hs), cudaMemcpyDeviceToHost);
-        opts->sum_out[0] = hs[0];
-        opts->sum_out[1] = hs[1];
+    bool scratch_ok = true;
+    if (out && sp_out != SPACE_DIRECT) {
+      // grow-only scratch for the whole grid (the kernel writes every level-L row once); when the device cannot
+      // hold it the per-point kernels below evaluate the grid chunk by chunk instead
+      const size_t need = sizeof(double) * (size_t)npts * NC;
+      if (p->grid_out_bytes < need) {
+        if (p->d_grid_out) cudaFree(p->d_grid_out);
+        p->d_grid_out = nullptr;
+        p->grid_out_bytes = 0;
+        if (cudaMalloc(&p->d_grid_out, need) == cudaSuccess) p->grid_out_bytes = need;
+        else {
+          cudaGetLastError();
+          scratch_ok = false;
+        }
       }
+      d_out = p->d_grid_out;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (tmp) cudaFree(tmp);
-    opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-    return rc;
+    if (scratch_ok) {
+      CoordSource src = base;
+      src.reduce_mode = opts->reduce_sum;
+      src.weights = opts->reduce_sum == TTN_REDUCE_WEIGHTED ? opts->weights : nullptr;
+      cudaEventRecord(st.k0, st.s);
+      int n_partial = 0;
+      double flops = 0.0;
+      rc = launch_grid_share(p, st, src, d_out, do_sum ? st.d_partial : nullptr, &n_partial, st.s, &opts->n_launches, &flops);
+      if (rc == TTN_OK && do_sum) {
+        rc = launch_sum_partials(p, st.d_partial, n_partial, NC, p->d_sum, st.s);
+        opts->n_launches += 1;
+      }
+      cudaEventRecord(st.k1, st.s);
+      if (rc == TTN_OK && out && sp_out != SPACE_DIRECT) {
+        // D2H in slices so that a pageable destination goes through the staging ring as well
+        const int64_t slice = (int64_t)1 << 22;
+        for (int64_t f0 = 0; f0 < npts && rc == TTN_OK; f0 += slice) {
+          const int64_t m = std::min(slice, npts - f0);
+          if (sp_out == SPACE_PAGEABLE) {
+            rc = ensure_host_ring(p, st, slice, false, true, false);
+            if (rc) break;
+            cudaMemcpyAsync(st.h_out, d_out + f0 * NC, sizeof(double) * m * NC, cudaMemcpyDeviceToHost, st.s);
+            cudaStreamSynchronize(st.s);
+            CopyPool::get().copy(reinterpret_cast<double*>(out) + f0 * NC, st.h_out, sizeof(double) * m * NC);
+            opts->staged |= 2;
+          } else {
+            cudaMemcpyAsync(reinterpret_cast<double*>(out) + f0 * NC, d_out + f0 * NC, sizeof(double) * m * NC, cudaMemcpyDefault, st.s);
+          }
+        }
+      }
+      const cudaError_t e = cudaStreamSynchronize(st.s);
+      if (rc == TTN_OK && e != cudaSuccess) rc = fail(TTN_ERR_CUDA, std::string("grid kernel: ") + cudaGetErrorString(e));
+      if (rc == TTN_OK) {
+        cudaEventElapsedTime(&opts->kernel_ms, st.k0, st.k1);
+        opts->flops_executed = flops;
+        if (do_sum) {
+          double hs[2];
+          cudaMemcpy(hs, p->d_sum, sizeof(hs), cudaMemcpyDeviceToHost);
+          opts->sum_out[0] = hs[0];
+          opts->sum_out[1] = hs[1];
+        }
+      }
+      opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+      return rc;
+    }
   }
   if (opts->kernel == TTN_KERNEL_GRID)
-    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GRID needs ttn_evaluate_grid on the FULL dyadic grid (count = 2^L, step = 2^-L, first = 0) of a chain with one binary site index per vertex and width <= 32");
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GRID needs ttn_evaluate_grid on the FULL dyadic grid (count = 2^L, step = 2^-L, first = 0) of a chain with one binary site index per vertex and width <= 32, in TTN_ACCURACY_FP64");
   int kernel = opts->kernel == TTN_KERNEL_AUTO ? p->info.auto_kernel : opts->kernel;
   if (kernel == TTN_KERNEL_CHAIN && !p->chain_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_CHAIN: network is not a chain with chi <= 32 (real) / 16 (complex) and <= 4 slices per vertex");
   if (kernel == TTN_KERNEL_TABLE && !p->ctab_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TABLE: network is not a chain of binary site indices with chi <= 4 (real) / 2 (complex), <= 2 site indices per vertex and <= 128 slice bits");
   if (kernel == TTN_KERNEL_TREE && !p->tgemm_ok)
-    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a real tree with <= 2 children per vertex, chi <= 64 and <= 8 slices per vertex");
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a tree the per-vertex GEMM kernel covers (<= 2 children per vertex, chi <= 64, <= 8 slices per vertex)");
   if (kernel == TTN_KERNEL_GEMM && !p->cgemm_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GEMM: network is not a chain with 32 < (real-embedded) width <= 256 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_DMMA: network is not a chain with chi <= 32 (real) / 16 (complex), <= 4 slices per vertex and <= 128 slice bits");
-  const bool coords_host = !base.grid && opts->coords_mem == TTN_MEM_HOST;
-  const int n_sites = std::max(p->info.n_sites, 1);
-  const bool out_host = out != nullptr && opts->out_mem == TTN_MEM_HOST;
-  const bool do_sum = opts->reduce_sum != TTN_REDUCE_NONE;
-  if (opts->reduce_sum < 0 || opts->reduce_sum > TTN_REDUCE_WEIGHTED) return fail(TTN_ERR_INVALID, "bad reduce mode");
-  if (opts->reduce_sum == TTN_REDUCE_WEIGHTED && !opts->weights) return fail(TTN_ERR_INVALID, "TTN_REDUCE_WEIGHTED needs opts->weights");
-  const bool weights_host = opts->reduce_sum == TTN_REDUCE_WEIGHTED && opts->weights_mem == TTN_MEM_HOST;
-  opts->sum_out[0] = opts->sum_out[1] = 0.0;
-  opts->kernel_ms = opts->total_ms = 0.f;
   opts->kernel_used = kernel;
-  opts->n_launches = 0;
-  if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
-  if (!out && !do_sum) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
   if (npts == 0) return TTN_OK;
   if (!base.grid && !coords && !digits) return fail(TTN_ERR_INVALID, "coords is NULL");
+
+  const void* in_ptr = digits ? static_cast<const void*>(digits) : static_cast<const void*>(coords);
+  const size_t in_bytes = digits ? (size_t)npts * n_sites : sizeof(double) * (size_t)npts * std::max(base.n_coords, 1);
+  Space sp_in = base.grid ? SPACE_NONE : classify(in_ptr, opts->coords_mem, p->device, opts->host_staging, in_bytes);
+  // a sub-range of an SOA array is strided: only the staged copies can address it
+  if (sp_in == SPACE_DIRECT && !digits && base.layout == TTN_LAYOUT_SOA && soa_stride != npts) sp_in = SPACE_ASYNC;
+  const bool in_staged = sp_in == SPACE_ASYNC || sp_in == SPACE_PAGEABLE;
+  const bool out_staged = sp_out == SPACE_ASYNC || sp_out == SPACE_PAGEABLE;
+  const bool w_staged = sp_w == SPACE_ASYNC || sp_w == SPACE_PAGEABLE;
+  // the refine pass and its functionals need the values of a chunk in device memory
+  const bool need_dout = out_staged || (refine && !out);
+  const bool chunked = in_staged || need_dout || w_staged;
 
   TTN_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->streams[0].s));
   TTN_CUDA(cudaStreamSynchronize(p->streams[0].s));
 
   int64_t chunk = npts;
   int n_chunks = 1;
-  if (coords_host || out_host || weights_host) {
+  if (chunked) {
     chunk = opts->chunk_points > 0 ? opts->chunk_points : (int64_t)1 << 21; // measured best on PCIe 5 x16 (scripts/e2e_probe.py)
     chunk = std::min(chunk, npts);
     n_chunks = (int)((npts + chunk - 1) / chunk);
@@ -390,87 +606,158 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       n_chunks = (int)((npts + chunk - 1) / chunk);
     }
   }
+  if (!chunked && npts > (int64_t)0x7fffff00 && refine) return fail(TTN_ERR_UNSUPPORTED, "TTN_ACCURACY_REFINED: more than 2^31 points in one un-chunked call");
+  if (sp_in == SPACE_DIRECT && !digits && base.layout == TTN_LAYOUT_SOA && n_chunks > 1)
+    return fail(TTN_ERR_UNSUPPORTED, "SOA device coordinates with a host output buffer are not supported; use AOS");
   std::vector<cudaEvent_t> ev(2 * (size_t)n_chunks, nullptr);
   auto cleanup_events = [&]() {
     for (auto e : ev)
       if (e) cudaEventDestroy(e);
   };
-  int rc = TTN_OK;
-  const int n_streams = (coords_host || out_host || weights_host) ? 3 : 1;
+  const int n_streams = chunked ? 3 : 1;
+  // pending D2H of a staged-pageable output: (destination, bytes) per stream, drained before the slot is reused
+  struct Pending {
+    double* dst = nullptr;
+    size_t bytes = 0;
+  } pend[3];
+  auto drain = [&](int si) {
+    if (!pend[si].dst) return;
+    cudaEventSynchronize(p->streams[si].ev_d2h);
+    CopyPool::get().copy(pend[si].dst, p->streams[si].h_out, pend[si].bytes);
+    pend[si].dst = nullptr;
+  };
+  const bool any_pageable = sp_in == SPACE_PAGEABLE || sp_out == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE;
   for (int ci = 0; ci < n_chunks && rc == TTN_OK; ++ci) {
-    Stream& st = p->streams[ci % n_streams];
+    const int si = ci % n_streams;
+    Stream& st = p->streams[si];
     const int64_t first = (int64_t)ci * chunk;
     const int64_t m = std::min(chunk, npts - first);
-    rc = ensure_stream_buffers(p, st, (coords_host || out_host || weights_host) ? chunk : 1, coords_host, out_host);
+    rc = ensure_stream_buffers(p, st, chunked ? chunk : 1, in_staged && !digits, need_dout);
     if (rc) break;
+    if (any_pageable) {
+      rc = ensure_host_ring(p, st, chunk, sp_in == SPACE_PAGEABLE && !digits, sp_out == SPACE_PAGEABLE, sp_w == SPACE_PAGEABLE);
+      if (rc) break;
+      drain(si);                                                  // values of chunk ci - 3 -> caller's array
+      if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE) cudaEventSynchronize(st.ev_h2d); // ring slot free again
+    }
     CoordSource src = base;
     src.npts = m;
     src.reduce_mode = opts->reduce_sum;
     src.weights = nullptr;
     if (opts->reduce_sum == TTN_REDUCE_WEIGHTED) {
-      if (weights_host) {
-        cudaMemcpyAsync(st.d_weights, opts->weights + first, sizeof(double) * m, cudaMemcpyHostToDevice, st.s);
+      if (sp_w == SPACE_PAGEABLE) {
+        CopyPool::get().copy(st.h_weights, opts->weights + first, sizeof(double) * m);
+        cudaMemcpyAsync(st.d_weights, st.h_weights, sizeof(double) * m, cudaMemcpyHostToDevice, st.s);
+        src.weights = st.d_weights;
+      } else if (sp_w == SPACE_ASYNC) {
+        cudaMemcpyAsync(st.d_weights, opts->weights + first, sizeof(double) * m, cudaMemcpyDefault, st.s);
         src.weights = st.d_weights;
       } else {
         src.weights = opts->weights + first;
       }
     }
     if (digits) {
-      if (coords_host) {
+      if (in_staged) {
         if (!st.d_digits || st.digits_cap < (size_t)chunk * n_sites) {
           if (st.d_digits) cudaFree(st.d_digits);
           st.d_digits = nullptr;
+          st.digits_cap = 0;
           TTN_CUDA(cudaMalloc(&st.d_digits, (size_t)chunk * n_sites));
           st.digits_cap = (size_t)chunk * n_sites;
         }
-        cudaMemcpyAsync(st.d_digits, digits + (size_t)first * p->info.n_sites, (size_t)m * p->info.n_sites,
-                        cudaMemcpyHostToDevice, st.s);
+        const uint8_t* hsrc = digits + (size_t)first * p->info.n_sites;
+        const size_t nbytes = (size_t)m * p->info.n_sites;
+        if (sp_in == SPACE_PAGEABLE) {
+          if (st.h_digits_cap < (size_t)chunk * n_sites) {
+            if (st.h_digits) cudaFreeHost(st.h_digits);
+            st.h_digits = nullptr;
+            st.h_digits_cap = 0;
+            TTN_CUDA(cudaHostAlloc(&st.h_digits, (size_t)chunk * n_sites, cudaHostAllocPortable));
+            st.h_digits_cap = (size_t)chunk * n_sites;
+          }
+          CopyPool::get().copy(st.h_digits, hsrc, nbytes);
+          hsrc = st.h_digits;
+          opts->staged |= 1;
+        }
+        cudaMemcpyAsync(st.d_digits, hsrc, nbytes, cudaMemcpyDefault, st.s);
         src.digits = st.d_digits;
       } else {
         src.digits = digits + (size_t)first * p->info.n_sites;
       }
     } else if (base.grid) {
       src.first = base.first + first;
-    } else if (coords_host) {
+    } else if (in_staged) {
+      const size_t row = sizeof(double) * (size_t)m;
       if (base.layout == TTN_LAYOUT_AOS) {
-        cudaMemcpyAsync(st.d_coords, coords + first * base.n_coords, sizeof(double) * m * base.n_coords,
-                        cudaMemcpyHostToDevice, st.s);
+        const double* hsrc = coords + first * base.n_coords;
+        if (sp_in == SPACE_PAGEABLE) {
+          CopyPool::get().copy(st.h_coords, hsrc, row * base.n_coords);
+          hsrc = st.h_coords;
+          opts->staged |= 1;
+        }
+        cudaMemcpyAsync(st.d_coords, hsrc, row * base.n_coords, cudaMemcpyDefault, st.s);
       } else {
-        for (int c = 0; c < base.n_coords; ++c)
-          cudaMemcpyAsync(st.d_coords + (int64_t)c * m, coords + (int64_t)c * npts + first, sizeof(double) * m,
-                          cudaMemcpyHostToDevice, st.s);
+        for (int c = 0; c < base.n_coords; ++c) {
+          const double* hsrc = coords + (int64_t)c * soa_stride + first;
+          if (sp_in == SPACE_PAGEABLE) {
+            CopyPool::get().copy(st.h_coords + (int64_t)c * m, hsrc, row);
+            hsrc = st.h_coords + (int64_t)c * m;
+            opts->staged |= 1;
+          }
+          cudaMemcpyAsync(st.d_coords + (int64_t)c * m, hsrc, row, cudaMemcpyDefault, st.s);
+        }
       }
       src.coords = st.d_coords;
     } else {
       // device coordinates: a chunk is a sub-range of the caller's array
-      if (base.layout == TTN_LAYOUT_AOS) {
-        src.coords = coords + first * base.n_coords;
-      } else if (n_chunks == 1) {
-        src.coords = coords;
-      } else {
-        cleanup_events();
-        return fail(TTN_ERR_UNSUPPORTED, "SOA device coordinates with a host output buffer are not supported; use AOS");
-      }
+      src.coords = base.layout == TTN_LAYOUT_AOS ? coords + first * base.n_coords : coords;
     }
+    if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE) cudaEventRecord(st.ev_h2d, st.s);
     double* d_out = nullptr;
-    if (out) d_out = out_host ? st.d_out : reinterpret_cast<double*>(out) + first * NC;
+    if (need_dout) d_out = st.d_out;
+    else if (out) d_out = reinterpret_cast<double*>(out) + first * NC;
     cudaEventCreate(&ev[2 * ci]);
     cudaEventCreate(&ev[2 * ci + 1]);
     cudaEventRecord(ev[2 * ci], st.s);
     int n_partial = 0;
-    rc = run_kernel(p, kernel, st, src, d_out, do_sum ? st.d_partial : nullptr, &n_partial, &opts->n_launches);
+    rc = run_kernel(p, kernel, st, src, d_out, (do_sum && !refine) ? st.d_partial : nullptr, &n_partial, &opts->n_launches);
     if (rc) break;
     opts->n_launches += 1;
+    if (refine) {
+      if (st.sel_cap < (size_t)(chunked ? chunk : npts)) {
+        if (st.d_sel) cudaFree(st.d_sel);
+        st.d_sel = nullptr;
+        st.sel_cap = 0;
+        const size_t cap = (size_t)(chunked ? chunk : npts);
+        TTN_CUDA(cudaMalloc(&st.d_sel, sizeof(int32_t) * (cap + 1)));
+        st.sel_cap = cap;
+      }
+      rc = launch_refine(p, st, src, d_out, tau, st.d_sel, do_sum ? st.d_partial : nullptr, &n_partial, st.s, &opts->n_launches);
+      if (rc) break;
+      // the count of this chunk, summed on the host after the streams have drained
+      cudaMemcpyAsync(p->d_nsel + ci, st.d_sel, sizeof(int32_t), cudaMemcpyDeviceToDevice, st.s);
+    }
     if (do_sum) {
       rc = launch_sum_partials(p, st.d_partial, n_partial, NC, p->d_sum + 2 * ci, st.s);
       if (rc) break;
       opts->n_launches += 1;
     }
     cudaEventRecord(ev[2 * ci + 1], st.s);
-    if (out_host)
-      cudaMemcpyAsync(reinterpret_cast<double*>(out) + first * NC, st.d_out, sizeof(double) * m * NC,
-                      cudaMemcpyDeviceToHost, st.s);
+    if (out && need_dout) {
+      double* dst = reinterpret_cast<double*>(out) + first * NC;
+      const size_t nbytes = sizeof(double) * (size_t)m * NC;
+      if (sp_out == SPACE_PAGEABLE) {
+        cudaMemcpyAsync(st.h_out, st.d_out, nbytes, cudaMemcpyDeviceToHost, st.s);
+        cudaEventRecord(st.ev_d2h, st.s);
+        pend[si].dst = dst;
+        pend[si].bytes = nbytes;
+        opts->staged |= 2;
+      } else {
+        cudaMemcpyAsync(dst, st.d_out, nbytes, cudaMemcpyDefault, st.s);
+      }
+    }
   }
+  for (int s = 0; s < n_streams; ++s) drain((n_chunks + s) % n_streams); // oldest first
   cudaError_t e = cudaSuccess;
   for (int s = 0; s < n_streams; ++s) {
     cudaError_t es = cudaStreamSynchronize(p->streams[s].s);
@@ -508,8 +795,90 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       opts->sum_out[0] = a;
       opts->sum_out[1] = b;
     }
+    if (refine && rc == TTN_OK) {
+      std::vector<int32_t> hn((size_t)n_chunks);
+      cudaMemcpy(hn.data(), p->d_nsel, sizeof(int32_t) * hn.size(), cudaMemcpyDeviceToHost);
+      for (int32_t v : hn) opts->n_refined += v;
+    }
   }
   cleanup_events();
+  opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  return rc;
+}
+
+// Contiguous block of device g: [g * ceil(n / G), min(n, (g + 1) * ceil(n / G)))  (SURVEY 8 e)
+static void shard_bounds(int64_t n, int g, int G, int64_t* lo, int64_t* hi) {
+  const int64_t per = (n + G - 1) / G;
+  *lo = std::min(n, (int64_t)g * per);
+  *hi = std::min(n, *lo + per);
+}
+
+// Multi-device plans: every replica evaluates its block on its own host thread (own streams, own pipeline)
+// straight from / into the caller's arrays; sums are added in device order.
+static int evaluate_any(ttn_plan* p, CoordSource base, const double* coords, void* out, ttn_opts* opts,
+                        const uint8_t* digits = nullptr) {
+  if (p->replicas.empty()) return evaluate_impl(p, base, coords, out, opts, digits);
+  const int G = (int)p->replicas.size();
+  const int NC = p->info.is_complex ? 2 : 1;
+  const int64_t npts = base.npts;
+  int rc = validate_opts(opts, out);
+  if (rc) return rc;
+  if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
+  const auto wall0 = std::chrono::steady_clock::now();
+  std::vector<ttn_opts> ro((size_t)G, *opts);
+  std::vector<int> rrc((size_t)G, TTN_OK);
+  std::vector<std::string> rerr((size_t)G);
+  auto work = [&](int g) {
+    int64_t lo, hi;
+    shard_bounds(npts, g, G, &lo, &hi);
+    CoordSource b = base;
+    b.npts = hi - lo;
+    if (base.grid) b.first = base.first + lo;
+    ttn_opts& o = ro[g];
+    if (o.weights) o.weights = o.weights + lo;
+    const double* c = coords;
+    if (c) c = base.layout == TTN_LAYOUT_AOS ? c + lo * base.n_coords : c + lo;
+    const uint8_t* dgt = digits ? digits + (size_t)lo * p->info.n_sites : nullptr;
+    void* o_ptr = out ? static_cast<void*>(reinterpret_cast<double*>(out) + lo * NC) : nullptr;
+    if (hi == lo) {
+      o.kernel_used = p->replicas[g]->info.auto_kernel;
+      o.kernel_ms = o.total_ms = 0.f;
+      o.n_launches = 0;
+      o.n_refined = 0;
+      o.staged = 0;
+      o.flops_executed = 0.0;
+      o.sum_out[0] = o.sum_out[1] = 0.0;
+      return;
+    }
+    rrc[g] = evaluate_impl(p->replicas[g], b, c, o_ptr, &o, dgt, npts);
+    if (rrc[g] != TTN_OK) rerr[g] = g_err;
+  };
+  std::vector<std::thread> th;
+  for (int g = 1; g < G; ++g) th.emplace_back(work, g);
+  work(0);
+  for (auto& t : th) t.join();
+  opts->sum_out[0] = opts->sum_out[1] = 0.0;
+  opts->kernel_ms = 0.f;
+  opts->n_launches = 0;
+  opts->n_devices_used = 0;
+  opts->staged = 0;
+  opts->n_refined = 0;
+  opts->flops_executed = 0.0;
+  opts->kernel_used = ro[0].kernel_used;
+  for (int g = 0; g < G; ++g) {
+    if (rrc[g] != TTN_OK && rc == TTN_OK) {
+      rc = rrc[g];
+      set_error("device " + std::to_string(p->replicas[g]->device) + ": " + rerr[g]);
+    }
+    opts->sum_out[0] += ro[g].sum_out[0]; // device order => deterministic
+    opts->sum_out[1] += ro[g].sum_out[1];
+    opts->kernel_ms = std::max(opts->kernel_ms, ro[g].kernel_ms); // the devices run concurrently
+    opts->n_launches += ro[g].n_launches;
+    opts->n_devices_used += ro[g].n_launches > 0 ? 1 : 0;
+    opts->staged |= ro[g].staged;
+    opts->n_refined += ro[g].n_refined;
+    opts->flops_executed += ro[g].flops_executed;
+  }
   opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   return rc;
 }
@@ -536,8 +905,7 @@ int ttn_device_count(void) {
   return n;
 }
 
-int ttn_plan_create(const ttn_desc* desc, int32_t device, ttn_plan** out) {
-  if (!desc || !out) return fail(TTN_ERR_INVALID, "null argument");
+static int create_single(const ttn_desc* desc, int32_t device, ttn_plan** out) {
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -549,30 +917,98 @@ int ttn_plan_create(const ttn_desc* desc, int32_t device, ttn_plan** out) {
   if (!p) return fail(TTN_ERR_NOMEM, "out of host memory");
   p->device = device;
   int rc = TTN_OK;
-  do {
-    if (cudaSetDevice(device) != cudaSuccess) { rc = fail(TTN_ERR_CUDA, "cudaSetDevice failed"); break; }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = fail(TTN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
-    if (prop.major != 10) { rc = fail(TTN_ERR_CUDA, std::string("libttneval is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor)); break; }
-    p->sm_count = prop.multiProcessorCount;
-    bool ok = true;
-    for (auto& st : p->streams) {
-      ok = ok && cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking) == cudaSuccess;
-      ok = ok && cudaEventCreate(&st.k0) == cudaSuccess && cudaEventCreate(&st.k1) == cudaSuccess;
-    }
-    ok = ok && cudaMalloc(&p->d_err, sizeof(int)) == cudaSuccess;
-    ok = ok && cudaMalloc(&p->d_sum, sizeof(double) * 2 * kMaxChunks) == cudaSuccess;
-    ok = ok && cudaEventCreate(&p->t0) == cudaSuccess && cudaEventCreate(&p->t1) == cudaSuccess;
-    if (!ok) { rc = fail(TTN_ERR_CUDA, std::string("plan resources: ") + cudaGetErrorString(cudaGetLastError())); break; }
-    rc = build_plan(p, desc);
-  } while (0);
+  {
+    DeviceGuard guard(device);
+    do {
+      if (!guard.ok) { rc = fail(TTN_ERR_CUDA, "cudaSetDevice failed"); break; }
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = fail(TTN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
+      if (prop.major != 10) { rc = fail(TTN_ERR_CUDA, std::string("libttneval is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor)); break; }
+      p->sm_count = prop.multiProcessorCount;
+      bool ok = true;
+      for (auto& st : p->streams) {
+        ok = ok && cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreate(&st.k0) == cudaSuccess && cudaEventCreate(&st.k1) == cudaSuccess;
+      }
+      ok = ok && cudaMalloc(&p->d_err, sizeof(int)) == cudaSuccess;
+      ok = ok && cudaMalloc(&p->d_sum, sizeof(double) * 2 * kMaxChunks) == cudaSuccess;
+      ok = ok && cudaMalloc(&p->d_nsel, sizeof(int32_t) * kMaxChunks) == cudaSuccess;
+      ok = ok && cudaEventCreate(&p->t0) == cudaSuccess && cudaEventCreate(&p->t1) == cudaSuccess;
+      if (!ok) { rc = fail(TTN_ERR_CUDA, std::string("plan resources: ") + cudaGetErrorString(cudaGetLastError())); break; }
+      rc = build_plan(p, desc);
+    } while (0);
+  }
   if (rc != TTN_OK) {
     const std::string keep = g_err;
     destroy_plan(p);
     g_err = keep;
     return rc;
   }
+  p->info.n_devices = 1;
   *out = p;
+  return TTN_OK;
+}
+
+int ttn_plan_create(const ttn_desc* desc, int32_t device, ttn_plan** out) {
+  if (!desc || !out) return fail(TTN_ERR_INVALID, "null argument");
+  return create_single(desc, device, out);
+}
+
+int ttn_plan_create_multi(const ttn_desc* desc, int32_t n_devices, const int32_t* devices, ttn_plan** out) {
+  if (!desc || !out) return fail(TTN_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(TTN_ERR_CUDA, "no CUDA device available (libttneval has no CPU fallback)");
+  }
+  if (n_devices < 1 || n_devices > ndev) return fail(TTN_ERR_INVALID, "n_devices must be in [1, ttn_device_count()]");
+  std::vector<int> devs((size_t)n_devices);
+  for (int g = 0; g < n_devices; ++g) {
+    devs[g] = devices ? devices[g] : g;
+    if (devs[g] < 0 || devs[g] >= ndev) return fail(TTN_ERR_INVALID, "device index out of range");
+    for (int h = 0; h < g; ++h)
+      if (devs[h] == devs[g]) return fail(TTN_ERR_INVALID, "devices[] lists a device twice");
+  }
+  ttn_plan* mp = new (std::nothrow) ttn_plan();
+  if (!mp) return fail(TTN_ERR_NOMEM, "out of host memory");
+  mp->device = devs[0];
+  mp->replicas.assign((size_t)n_devices, nullptr);
+  // the replicas are built concurrently (a plan with tables takes up to ~1.5 s per device)
+  std::vector<int> rrc((size_t)n_devices, TTN_OK);
+  std::vector<std::string> rerr((size_t)n_devices);
+  auto build = [&](int g) {
+    rrc[g] = create_single(desc, devs[g], &mp->replicas[g]);
+    if (rrc[g] != TTN_OK) rerr[g] = g_err;
+  };
+  {
+    std::vector<std::thread> th;
+    for (int g = 1; g < n_devices; ++g) th.emplace_back(build, g);
+    build(0);
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < n_devices; ++g)
+    if (rrc[g] != TTN_OK) {
+      const int rc = rrc[g];
+      const std::string msg = "device " + std::to_string(devs[g]) + ": " + rerr[g];
+      destroy_plan(mp);
+      return fail(rc, msg);
+    }
+  // peer access both ways, so that blocks of a device-resident array on another GPU move over NVLink
+  for (int g = 0; g < n_devices; ++g) {
+    DeviceGuard guard(devs[g]);
+    for (int h = 0; h < n_devices; ++h) {
+      int can = 0;
+      if (h != g && cudaDeviceCanAccessPeer(&can, devs[g], devs[h]) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devs[h], 0);
+        if (e != cudaSuccess) cudaGetLastError(); // already enabled (by the caller's framework) is fine
+      }
+    }
+  }
+  mp->info = mp->replicas[0]->info;
+  mp->info.n_devices = n_devices;
+  mp->sm_count = mp->replicas[0]->sm_count;
+  *out = mp;
   return TTN_OK;
 }
 
@@ -596,7 +1032,7 @@ int ttn_evaluate(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_c
   src.n_coords = n_coords;
   src.layout = layout;
   src.grid = 0;
-  return evaluate_impl(plan, src, coords, out, opts);
+  return evaluate_any(plan, src, coords, out, opts);
 }
 
 int ttn_evaluate_grid(ttn_plan* plan, const ttn_grid* grid, void* out_or_null, ttn_opts* opts) {
@@ -618,7 +1054,7 @@ int ttn_evaluate_grid(ttn_plan* plan, const ttn_grid* grid, void* out_or_null, t
   }
   if (grid->first < 0 || grid->npts < 0 || grid->first + grid->npts > total)
     return fail(TTN_ERR_INVALID, "grid range exceeds the number of grid points");
-  return evaluate_impl(plan, src, nullptr, out_or_null, opts);
+  return evaluate_any(plan, src, nullptr, out_or_null, opts);
 }
 
 int ttn_evaluate_indices(ttn_plan* plan, const uint8_t* index_values, int64_t npts, void* out, ttn_opts* opts) {
@@ -629,45 +1065,96 @@ int ttn_evaluate_indices(ttn_plan* plan, const uint8_t* index_values, int64_t np
   src.npts = npts;
   src.n_coords = plan->info.n_coords;
   src.layout = TTN_LAYOUT_AOS;
-  return evaluate_impl(plan, src, nullptr, out, opts, index_values);
+  return evaluate_any(plan, src, nullptr, out, opts, index_values);
 }
 
 int ttn_digits(ttn_plan* plan, const double* coords, int64_t npts, int32_t n_coords, int32_t layout,
                uint8_t* digits_out, ttn_opts* opts) {
   if (!plan || !opts || !digits_out) return fail(TTN_ERR_INVALID, "null argument");
+  if (!plan->replicas.empty()) plan = plan->replicas[0]; // integer work of a few bytes per point: one device
   if (n_coords != plan->info.n_coords) return fail(TTN_ERR_INVALID, "n_coords does not match the plan");
+  if (layout != TTN_LAYOUT_AOS && layout != TTN_LAYOUT_SOA) return fail(TTN_ERR_INVALID, "bad layout");
+  if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
+  opts->n_launches = 0;
   if (npts == 0) return TTN_OK;
   if (!coords) return fail(TTN_ERR_INVALID, "coords is NULL");
   std::lock_guard<std::mutex> lock(plan->mu);
-  TTN_CUDA(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(TTN_ERR_CUDA, "cudaSetDevice failed");
   Stream& st = plan->streams[0];
   const int ns = std::max(plan->info.n_sites, 1);
-  const bool host_c = opts->coords_mem == TTN_MEM_HOST, host_o = opts->out_mem == TTN_MEM_HOST;
-  double* d_c = nullptr;
-  uint8_t* d_o = nullptr;
+  const bool direct_c = classify(coords, opts->coords_mem, plan->device, TTN_STAGE_OFF, 0) == SPACE_DIRECT;
+  const bool direct_o = classify(digits_out, opts->out_mem, plan->device, TTN_STAGE_OFF, 0) == SPACE_DIRECT;
   TTN_CUDA(cudaMemsetAsync(plan->d_err, 0, sizeof(int), st.s));
-  if (host_c) {
-    TTN_CUDA(cudaMalloc(&d_c, sizeof(double) * (size_t)npts * std::max(n_coords, 1)));
-    TTN_CUDA(cudaMemcpyAsync(d_c, coords, sizeof(double) * (size_t)npts * n_coords, cudaMemcpyHostToDevice, st.s));
+  // chunks through the stream's grow-only buffers (no per-call allocation once warm)
+  const int64_t chunk = (direct_c && direct_o) ? npts : std::min<int64_t>(npts, (int64_t)1 << 21);
+  if (direct_c && layout == TTN_LAYOUT_SOA && chunk != npts)
+    return fail(TTN_ERR_UNSUPPORTED, "SOA device coordinates with a host digit buffer are not supported; use AOS");
+  int rc = TTN_OK;
+  if (!direct_c) rc = ensure_stream_buffers(plan, st, chunk, true, false);
+  if (rc == TTN_OK && !direct_o && st.digits_cap < (size_t)chunk * ns) {
+    if (st.d_digits) cudaFree(st.d_digits);
+    st.d_digits = nullptr;
+    st.digits_cap = 0;
+    if (cudaMalloc(&st.d_digits, (size_t)chunk * ns) != cudaSuccess) rc = fail(TTN_ERR_NOMEM, "out of device memory (digit buffer)");
+    else st.digits_cap = (size_t)chunk * ns;
   }
-  if (host_o) TTN_CUDA(cudaMalloc(&d_o, (size_t)npts * ns));
-  CoordSource src{};
-  src.coords = host_c ? d_c : coords;
-  src.npts = npts;
-  src.n_coords = n_coords;
-  src.layout = layout;
-  int rc = launch_digits(plan, src, host_o ? d_o : digits_out, st.s);
-  opts->n_launches = 1;
-  if (rc == TTN_OK && host_o)
-    cudaMemcpyAsync(digits_out, d_o, (size_t)npts * plan->info.n_sites, cudaMemcpyDeviceToHost, st.s);
-  cudaError_t e = cudaStreamSynchronize(st.s);
+  for (int64_t first = 0; first < npts && rc == TTN_OK; first += chunk) {
+    const int64_t m = std::min(chunk, npts - first);
+    CoordSource src{};
+    src.npts = m;
+    src.n_coords = n_coords;
+    src.layout = layout;
+    if (direct_c) {
+      src.coords = layout == TTN_LAYOUT_AOS ? coords + first * n_coords : coords;
+    } else {
+      if (layout == TTN_LAYOUT_AOS) {
+        cudaMemcpyAsync(st.d_coords, coords + first * n_coords, sizeof(double) * (size_t)m * n_coords, cudaMemcpyDefault, st.s);
+      } else {
+        for (int c = 0; c < n_coords; ++c)
+          cudaMemcpyAsync(st.d_coords + (int64_t)c * m, coords + (int64_t)c * npts + first, sizeof(double) * (size_t)m,
+                          cudaMemcpyDefault, st.s);
+      }
+      src.coords = st.d_coords;
+    }
+    uint8_t* d_o = direct_o ? digits_out + (size_t)first * plan->info.n_sites : st.d_digits;
+    rc = launch_digits(plan, src, d_o, st.s);
+    opts->n_launches += 1;
+    if (rc == TTN_OK && !direct_o)
+      cudaMemcpyAsync(digits_out + (size_t)first * plan->info.n_sites, st.d_digits, (size_t)m * plan->info.n_sites,
+                      cudaMemcpyDefault, st.s);
+    if (!direct_c || !direct_o) cudaStreamSynchronize(st.s); // the single buffer pair is reused by the next chunk
+  }
+  const cudaError_t e = cudaStreamSynchronize(st.s);
   int herr = 0;
   cudaMemcpy(&herr, plan->d_err, sizeof(int), cudaMemcpyDeviceToHost);
-  if (d_c) cudaFree(d_c);
-  if (d_o) cudaFree(d_o);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(TTN_ERR_CUDA, std::string("digits kernel: ") + cudaGetErrorString(e));
   if (herr) return fail(TTN_ERR_DOMAIN, "a coordinate is negative or NaN");
+  return TTN_OK;
+}
+
+int ttn_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return fail(TTN_ERR_INVALID, "null / empty range");
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return TTN_OK;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TTN_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  }
+  return TTN_OK;
+}
+
+int ttn_host_unregister(void* ptr) {
+  if (!ptr) return fail(TTN_ERR_INVALID, "null pointer");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(TTN_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+  }
   return TTN_OK;
 }
 

@@ -174,6 +174,19 @@ struct Stream {
   size_t gemm_bytes = 0;
   double* d_partial2 = nullptr;
   size_t partial2_bytes = 0;
+  // pinned staging ring for PAGEABLE caller buffers (allocated on first use, chunk capacity)
+  double* h_coords = nullptr;
+  double* h_out = nullptr;
+  double* h_weights = nullptr;
+  uint8_t* h_digits = nullptr;
+  int64_t h_cap_points = 0;
+  size_t h_digits_cap = 0;
+  cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;
+  // refine pass (TTN_ACCURACY_REFINED): compacted point list + values
+  int32_t* d_sel = nullptr;   // [1 + points]: count, then the selected point indices
+  size_t sel_cap = 0;         // in points
+  void* d_refine = nullptr;   // double-double workspace
+  size_t refine_bytes = 0;
 };
 
 } // namespace ttn
@@ -219,8 +232,13 @@ struct ttn_plan {
   double tgemm_flops_exec = 0.0;
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
+  int v6_teams = 3;        // teams per CTA of the team-sorted kernel (TTN_MMA_V6 at ttn_plan_create; 0 = ring kernels)
+  double* d_grid_out = nullptr; // grow-only scratch of the grid kernel's host-output path
+  size_t grid_out_bytes = 0;
+  std::vector<ttn_plan*> replicas; // non-empty: a multi-device plan (ttn_plan_create_multi); this object owns them
   int* d_err = nullptr;    // domain-error flag
-  double* d_sum = nullptr; // (re, im)
+  double* d_sum = nullptr; // (re, im) per chunk
+  int32_t* d_nsel = nullptr; // refined points per chunk
   ttn::Stream streams[3];
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   std::mutex mu;
@@ -263,4 +281,7 @@ int debug_table_image(const ttn_desc* d, int32_t budget_kb, int32_t* meta, doubl
                       int32_t* site_bitpos);
 bool chain_supported(int chi, int nsl, bool cplx);
 int measure_fp64_peak(int device, double* dfma, double* dmma);
+// TTN_ACCURACY_REFINED (k_refine.cu): select the points with |f| < thr, re-evaluate them in double-double
+int launch_refine(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double tau, int32_t* d_sel,
+                  double* d_partial, int* n_partial, cudaStream_t s, int* n_launches);
 } // namespace ttn

@@ -123,12 +123,43 @@ def complex_digit_siteinds(g, real_dimension_vertices=None, imag_dimension_verti
     return s
 
 
+def _fma(a, b, c):
+    """Correctly rounded a*b + c (Python 3.12 has no math.fma): exact rational arithmetic, one rounding."""
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
 def _inv_pow(base, digit):
-    """float(base)^-digit (realindexmap.jl:14).  Exact for powers of two; for other bases the
-    correctly rounded value of base^-digit (Julia's compensated pow_body is correctly rounded
-    except in rare half-ulp cases; the Julia wrapper computes thresholds with the reference's
-    own function, so on the Julia side thresholds are bit-identical by construction)."""
-    return float(Fraction(1, int(base) ** int(digit)))
+    """float(base)^-digit exactly as Julia computes it at realindexmap.jl:14 / complexindexmap.jl:27:
+    `^(x::Float64, n::Integer)` -> Base.Math.pow_body (Julia >= 1.8; base/math.jl), restated operation by
+    operation with fused muladd / two_mul (x86-64 with FMA, what Julia emits on every current host):
+      n == -2 is the uncompensated inv(x)*inv(x)   (1 ulp off the correctly rounded value for bases 5 and 10),
+      n == -1 and n <= -3 run the compensated square-and-multiply loop on inv(x).
+    Powers of two are exact either way.  The Julia wrapper computes the thresholds with the reference's own
+    index_value_to_scalar, so on the Julia side they are bit-identical by construction; this restatement makes
+    the Python mirror (packer thresholds, test inputs) choose the same digits for every base."""
+    x, n = float(base), -int(digit)
+    if n == 0:
+        return 1.0
+    y, xnlo, ynlo = 1.0, 0.0, 0.0
+    if n == 3:
+        return x * x * x
+    if n < 0:
+        rx = 1.0 / x
+        if n == -2:
+            return rx * rx
+        xnlo = -_fma(x, rx, -1.0) * rx
+        x, n = rx, -n
+    while n > 1:
+        if n & 1:
+            err = _fma(y, xnlo, x * ynlo)
+            y, ynlo = x * y, _fma(x, y, -(x * y))
+            ynlo += err
+        err = x * 2 * xnlo
+        x, xnlo = x * x, _fma(x, x, -(x * x))
+        xnlo += err
+        n >>= 1
+    err = _fma(y, xnlo, x * ynlo)
+    return _fma(x, y, err)
 
 
 # --------------------------------------------------------------------------- index maps

@@ -32,12 +32,22 @@ def default_contraction_alg():
 class Plan:
     """Owns one `ttn_plan*` (device memory, streams) for one packed network."""
 
-    def __init__(self, packed, device=0):
+    def __init__(self, packed, device=0, ngpus=1, devices=None):
+        """device: the GPU of a single-device plan.  ngpus > 1 (or an explicit `devices` list): the plan is
+        replicated on those GPUs of this process and every call shards its points over them
+        (ttn_plan_create_multi; SURVEY 8(b),(e))."""
         self.packed = packed
-        self.device = int(device)
         self._h = C.c_void_p()
         L = _capi.lib()
-        _capi.check(L.ttn_plan_create(C.byref(packed.desc()), self.device, C.byref(self._h)))
+        if devices is None and int(ngpus) <= 1:
+            self.device = int(device)
+            self.devices = [self.device]
+            _capi.check(L.ttn_plan_create(C.byref(packed.desc()), self.device, C.byref(self._h)))
+        else:
+            self.devices = [int(d) for d in devices] if devices is not None else list(range(int(ngpus)))
+            self.device = self.devices[0]
+            arr = (C.c_int32 * len(self.devices))(*self.devices)
+            _capi.check(L.ttn_plan_create_multi(C.byref(packed.desc()), len(self.devices), arr, C.byref(self._h)))
 
     def close(self):
         h = getattr(self, "_h", None)
@@ -56,8 +66,12 @@ class Plan:
         return {f: getattr(info, f) for f, _ in _capi.ttn_info._fields_}
 
     @staticmethod
-    def _opts(kernel, reduce_sum, coords_mem=0, out_mem=0, chunk_points=0):
+    def _opts(kernel, reduce_sum, coords_mem=0, out_mem=0, chunk_points=0, accuracy=None, refine_tau=0.0,
+              host_staging=0):
         o = _capi.ttn_opts()
+        o.accuracy = _capi.ACCURACY_IDS[accuracy] if not isinstance(accuracy, (int, np.integer)) else int(accuracy)
+        o.refine_tau = float(refine_tau)
+        o.host_staging = int(host_staging)
         o.coords_mem, o.out_mem = coords_mem, out_mem
         o.kernel = _capi.KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel or 0)
         o.reduce_sum = _capi.REDUCE_IDS[reduce_sum] if not isinstance(reduce_sum, (int, np.integer)) or isinstance(reduce_sum, bool) else int(reduce_sum)
@@ -65,8 +79,10 @@ class Plan:
         return o
 
     def evaluate_host(self, coords, layout=_capi.TTN_LAYOUT_AOS, kernel="auto", reduce_sum=False,
-                      want_values=True, chunk_points=0, out=None, weights=None):
-        """coords: float64 array, (npts, n_coords) for AOS or (n_coords, npts) for SOA."""
+                      want_values=True, chunk_points=0, out=None, weights=None, accuracy=None, refine_tau=0.0,
+                      host_staging=0):
+        """coords: float64 array, (npts, n_coords) for AOS or (n_coords, npts) for SOA.  Pageable arrays
+        (plain numpy) go through the library's pinned staging ring; pinned ones are used in place."""
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         nc = self.packed.n_coords
         npts = coords.shape[0] if layout == _capi.TTN_LAYOUT_AOS else coords.shape[1]
@@ -78,7 +94,8 @@ class Plan:
                 raise ValueError("out must be a contiguous array of npts values of the network's eltype")
         elif want_values:
             out = np.empty(npts, dtype=dt)
-        o = self._opts(kernel, reduce_sum, chunk_points=chunk_points)
+        o = self._opts(kernel, reduce_sum, chunk_points=chunk_points, accuracy=accuracy, refine_tau=refine_tau,
+                       host_staging=host_staging)
         if weights is not None:
             weights = np.ascontiguousarray(weights, dtype=np.float64)
             if weights.size != npts:
@@ -91,9 +108,11 @@ class Plan:
         return out, o
 
     def evaluate_device(self, coords_ptr, npts, out_ptr, layout=_capi.TTN_LAYOUT_AOS,
-                        kernel="auto", reduce_sum=False):
-        """Raw device pointers (e.g. torch tensors' data_ptr()) on the plan's device."""
-        o = self._opts(kernel, reduce_sum, _capi.TTN_MEM_DEVICE, _capi.TTN_MEM_DEVICE)
+                        kernel="auto", reduce_sum=False, accuracy=None, refine_tau=0.0):
+        """Raw device pointers (e.g. torch tensors' data_ptr()).  On a multi-GPU plan the arrays may live on any
+        one GPU: the other GPUs move their blocks with peer copies."""
+        o = self._opts(kernel, reduce_sum, _capi.TTN_MEM_DEVICE, _capi.TTN_MEM_DEVICE, accuracy=accuracy,
+                       refine_tau=refine_tau)
         rc = _capi.lib().ttn_evaluate(self._h, C.c_void_p(coords_ptr), int(npts),
                                       self.packed.n_coords, layout,
                                       C.c_void_p(out_ptr) if out_ptr else None, C.byref(o))
@@ -101,7 +120,7 @@ class Plan:
         return o
 
     def evaluate_grid(self, steps, counts, first=0, npts=None, kernel="auto", reduce_sum=True,
-                      want_values=False, out_ptr=None):
+                      want_values=False, out_ptr=None, accuracy=None):
         steps = np.ascontiguousarray(steps, dtype=np.float64)
         counts = np.ascontiguousarray(counts, dtype=np.int64)
         total = int(np.prod(counts.astype(object)))
@@ -113,7 +132,7 @@ class Plan:
         g.count = counts.ctypes.data_as(C.POINTER(C.c_int64))
         g.first, g.npts = int(first), int(npts)
         out = None
-        o = self._opts(kernel, reduce_sum)
+        o = self._opts(kernel, reduce_sum, accuracy=accuracy)
         ptr = None
         if out_ptr is not None:
             o.out_mem = _capi.TTN_MEM_DEVICE
@@ -126,10 +145,15 @@ class Plan:
 
     def evaluate_indices_host(self, index_values, kernel="auto", reduce_sum=False, want_values=True):
         """index_values: uint8 array (npts, n_sites), columns in the order of packed.site_inds."""
-        iv = np.ascontiguousarray(index_values, dtype=np.uint8)
+        iv = np.asarray(index_values)
         ns = len(self.packed.site_dim)
         if iv.ndim != 2 or iv.shape[1] != ns:
             raise ValueError(f"index_values must have {ns} columns (one per site index)")
+        if iv.dtype != np.uint8:
+            # range-check BEFORE the cast: 256 would wrap to a valid-looking 0
+            if iv.size and (iv.min() < 0 or (iv >= np.asarray(self.packed.site_dim)[None, :]).any()):
+                raise _capi.TTNError(_capi.TTN_ERR_INVALID, "an index value is out of range for its site index")
+        iv = np.ascontiguousarray(iv, dtype=np.uint8)
         npts = iv.shape[0]
         out = np.empty(npts, dtype=np.complex128 if self.packed.is_complex else np.float64) if want_values else None
         o = self._opts(kernel, reduce_sum)
@@ -141,7 +165,11 @@ class Plan:
     def digits_host(self, coords, layout=_capi.TTN_LAYOUT_AOS):
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         nc = self.packed.n_coords
+        if coords.ndim != 2:
+            raise ValueError(f"coords must be a 2-D array holding {nc} coordinate slots per point")
         npts = coords.shape[0] if layout == _capi.TTN_LAYOUT_AOS else coords.shape[1]
+        if coords.size != npts * nc:
+            raise ValueError(f"coords must hold {nc} coordinate slots per point")
         out = np.empty((npts, len(self.packed.site_dim)), dtype=np.uint8)
         o = self._opts("auto", False)
         _capi.check(_capi.lib().ttn_digits(self._h, coords.ctypes.data_as(C.c_void_p), npts, nc,
@@ -175,7 +203,12 @@ class ITensorNetworkFunction:
         return self.itensornetwork[v]
 
     def __setitem__(self, v, t):
-        self.itensornetwork[v] = t
+        self.itensornetwork[v] = t  # bumps the network's version: cached plans of the old tensors are dropped
+
+    def invalidate_plans(self):
+        """Drop the cached GPU plans.  Needed only after mutating a tensor's ARRAY in place
+        (`fitn[v].array[...] = x`); assigning a vertex (`fitn[v] = t`, `fitn.itensornetwork[v] = t`, the
+        reference's `psi[v] = ...` / `psi[v] *= c`) is tracked through the network's version counter."""
         self._plans.clear()
 
     def is_tree(self):
@@ -211,12 +244,19 @@ class ITensorNetworkFunction:
     __rmul__ = __mul__
 
     # ---- plans --------------------------------------------------------------------
-    def plan(self, dims=None, device=0) -> Plan:
+    def plan(self, dims=None, device=0, ngpus=1) -> Plan:
+        """The cached GPU plan of (dims, device / ngpus) for the network's CURRENT tensors.  Plans built for an
+        older version of the network (any `psi[v] = t` since) are dropped first, so a mutated network is never
+        evaluated with stale packed tensors; see invalidate_plans() for in-place array edits."""
         if dims is None:
             dims = self.indexmap.dimensions()
-        key = (tuple(int(d) for d in dims), int(device))
+        ver = self.itensornetwork.version
+        if getattr(self, "_plans_version", ver) != ver:
+            self._plans.clear()
+        self._plans_version = ver
+        key = (tuple(int(d) for d in dims), int(device), int(ngpus))
         if key not in self._plans:
-            self._plans[key] = Plan(pack(self, list(key[0])), device=device)
+            self._plans[key] = Plan(pack(self, list(key[0])), device=device, ngpus=ngpus)
         return self._plans[key]
 
 
@@ -257,19 +297,21 @@ def _points_to_coords(fitn, xs, dims):
     return coords, dims, single
 
 
-def evaluate(fitn: ITensorNetworkFunction, xs, dims=None, *, alg=None, device=0, kernel="auto",
-             reduce=None, weights=None, return_opts=False):
+def evaluate(fitn: ITensorNetworkFunction, xs, dims=None, *, alg=None, device=0, ngpus=1, kernel="auto",
+             reduce=None, weights=None, accuracy=None, return_opts=False):
     """Evaluate `fitn` at one point or at a batch of points (see module docstring).
 
     reduce=None  -> values;  reduce="sum" -> the sum over all points (grid quadrature,
     cf. integrate(...; take_sum=true), src/integration.jl:6-17); reduce="abs2" -> sum |f|^2;
     reduce="weighted" -> sum_p weights[p] * f(p) (fused quadrature functionals).
     `alg` is accepted for signature compatibility ("bp" and "exact" coincide on trees).
+    ngpus=G shards the points over G GPUs of this process (contiguous blocks, network replicated; SURVEY 8 e).
+    accuracy="refined" re-evaluates the points that cancel (|f| << rms) in double-double (TTN_ACCURACY_REFINED).
     """
     coords, dims, single = _points_to_coords(fitn, xs, dims)
-    plan = fitn.plan(dims, device=device)
+    plan = fitn.plan(dims, device=device, ngpus=ngpus)
     out, o = plan.evaluate_host(coords, kernel=kernel, reduce_sum=reduce, want_values=(reduce is None),
-                                weights=weights)
+                                weights=weights, accuracy=accuracy)
     if reduce == "abs2":
         res = o.sum_out[0]
     elif reduce is not None:

@@ -23,7 +23,7 @@ using NamedGraphs.GraphsExtensions: is_tree, leaf_vertices
 
 const LIBTTNEVAL = get(ENV, "LIBTTNEVAL", "libttneval.so")
 
-const TTN_ABI_VERSION = Int32(2)
+const TTN_ABI_VERSION = Int32(3)
 const TTN_LAYOUT_AOS = Int32(0)   # coords[c + n_coords*p]: a Julia (n_coords x npts) Matrix
 const TTN_MEM_HOST = Int32(0)
 
@@ -64,11 +64,19 @@ mutable struct TTNOpts
   weights_mem::Int32
   reserved_::Int32
   flops_executed::Float64
+  host_staging::Int32   # 0 = pageable Julia arrays go through the library's pinned staging ring
+  accuracy::Int32       # 0 = FP64, 1 = refined (double-double re-evaluation of the points that cancel)
+  refine_tau::Float64
+  n_devices_used::Int32
+  staged::Int32
+  n_refined::Int64
 end
 # reduce: TTN_REDUCE_NONE = 0, _SUM = 1 (sum f), _ABS2 = 2 (sum |f|^2), _WEIGHTED = 3 (sum w f)
 const REDUCE_MODES = Dict(:none => Int32(0), :sum => Int32(1), :abs2 => Int32(2), :weighted => Int32(3))
-TTNOpts(; reduce::Symbol=:none, weights::Ptr{Float64}=Ptr{Float64}(C_NULL)) =
-  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, REDUCE_MODES[reduce], 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, weights, TTN_MEM_HOST, 0, 0.0)
+const ACCURACY_MODES = Dict(:fp64 => Int32(0), :refined => Int32(1))
+TTNOpts(; reduce::Symbol=:none, weights::Ptr{Float64}=Ptr{Float64}(C_NULL), accuracy::Symbol=:fp64) =
+  TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, REDUCE_MODES[reduce], 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, weights, TTN_MEM_HOST, 0, 0.0,
+    0, ACCURACY_MODES[accuracy], 0.0, 0, 0, 0)
 
 "Flat arrays of one packed network; keeps everything the C side points at alive."
 struct PackedNetwork
@@ -92,7 +100,9 @@ end
 mutable struct TTNPlan
   handle::Ptr{Cvoid}
   packed::PackedNetwork
-  function TTNPlan(packed::PackedNetwork; device::Integer=0)
+  # ngpus > 1: the plan is replicated on GPUs 0..ngpus-1 of this process and every call shards its points over
+  # them (ttn_plan_create_multi): contiguous blocks, each GPU copies its block in and its values out itself
+  function TTNPlan(packed::PackedNetwork; device::Integer=0, ngpus::Integer=1)
     desc = TTNDesc(
       TTN_ABI_VERSION, length(packed.parent), packed.n_coords, packed.is_complex ? 1 : 0,
       packed.root, length(packed.site_dim),
@@ -103,8 +113,13 @@ mutable struct TTNPlan
     )
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve packed begin
-      rc = ccall((:ttn_plan_create, LIBTTNEVAL), Cint, (Ref{TTNDesc}, Int32, Ref{Ptr{Cvoid}}),
-        desc, Int32(device), h)
+      rc = if ngpus > 1
+        ccall((:ttn_plan_create_multi, LIBTTNEVAL), Cint, (Ref{TTNDesc}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+          desc, Int32(ngpus), C_NULL, h)
+      else
+        ccall((:ttn_plan_create, LIBTTNEVAL), Cint, (Ref{TTNDesc}, Int32, Ref{Ptr{Cvoid}}),
+          desc, Int32(device), h)
+      end
     end
     rc == 0 || error("ttn_plan_create: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
     plan = new(h[], packed)
@@ -166,8 +181,15 @@ Runs once per (network, dims).  Replaces the per-point `copy(fitn)`
 `index_value_to_scalar`, so digit selection is bit-identical for every base.
 """
 function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn))
-  @assert is_tree(fitn) "the batched evaluator needs a tree (cf. truncate, src/itensornetworkfunction.jl:115)"
   tn = itensornetwork(fitn)
+  # Loopy graphs: the reference only evaluates them with link dimension 1 (const_itn on named_grid((3,3)),
+  # test/test_realitensorfunction.jl:39-57) or alg="exact".  A dimension-1 link carries no sum, so the links
+  # outside a spanning tree are dropped exactly (their axes have length 1); anything else stays on the
+  # reference's per-point path.
+  if !is_tree(fitn)
+    all(e -> dim(only(commoninds(tn[Graphs.src(e)], tn[Graphs.dst(e)]))) == 1, edges(tn)) ||
+      error("the batched evaluator needs a tree, or a loopy network whose link dimensions are all 1 (cf. truncate, src/itensornetworkfunction.jl:115)")
+  end
   s = indsnetwork(indsnetworkmap(fitn))
   imap = indexmap(fitn)
   cmap = imap isa ComplexIndexMap
@@ -196,6 +218,9 @@ function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn)
     i = vid[v]
     sites = collect(s[v])
     children = sort(filter(u -> parent[vid[u] + 1] == i, collect(neighbors(tn, v))); by=u -> vid[u])
+    # neighbours that are neither children nor the parent: dimension-1 links outside the BFS spanning tree
+    extra = Index[only(commoninds(tn[v], tn[u])) for u in neighbors(tn, v)
+                  if parent[vid[u] + 1] != i && parent[i + 1] != vid[u]]
     # C order [site..., child..., parent] (last fastest) == Julia column-major with reversed axes
     axes = Index[]
     append!(axes, sites)
@@ -207,7 +232,7 @@ function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn)
       push!(axes, pl)
       link_dim[i + 1] = dim(pl)
     end
-    arr = isempty(axes) ? T[tn[v][]] : vec(array(permute(tn[v], reverse(axes)...)))
+    arr = (isempty(axes) && isempty(extra)) ? T[tn[v][]] : vec(array(permute(tn[v], reverse(axes)..., extra...)))
     append!(tensors, T.(arr))
     push!(tensor_ptr, length(tensors))
     for ind in sites
@@ -224,10 +249,45 @@ function pack(fitn::ITensorNetworkFunction, dims::Vector{<:Int}=dimensions(fitn)
     tensor_ptr, tensors, vid[root], (cmap ? 2 : 1) * length(dims), eltype_c, cmap, site_inds)
 end
 
-const _plan_cache = IdDict{Any,Any}()
-function plan(fitn::ITensorNetworkFunction, dims; device=0)
-  get!(() -> TTNPlan(pack(fitn, dims); device), get!(() -> Dict(), _plan_cache, fitn), (dims, device))
+# ---- plan cache -------------------------------------------------------------------------------------------
+# Keyed on the ITensorNetwork OBJECT (a mutable struct) in a WeakKeyDict, so a network that is garbage collected
+# takes its plans (up to ~0.5 GB of device memory each) with it: their finalizers run ttn_plan_destroy.  The
+# reference mutates networks in place (`psi[v] = t`, `psi[v] *= c`), and both create a NEW ITensor — a new storage
+# object — at that vertex: every entry therefore carries a fingerprint of the tensors it was packed from (the
+# objectid of every vertex tensor's storage plus one sampled element), and a plan whose fingerprint no longer
+# matches is rebuilt.  Not covered: writing single ELEMENTS into a tensor's storage (`psi[v][i, j] = x`) other
+# than the sampled one — call `invalidate_plans!(fitn)` after that, or pass an explicit plan:
+#     pl = TTNPlan(pack(fitn, dims)); evaluate(pl, points)
+const _plan_cache = WeakKeyDict{Any,Any}()
+const _plan_cache_lock = ReentrantLock()
+
+function network_fingerprint(fitn::ITensorNetworkFunction)
+  tn = itensornetwork(fitn)
+  h = UInt(0x7474)
+  for v in vertices(tn)
+    t = tn[v]
+    st = ITensors.storage(t)
+    h = hash((objectid(st), inds(t), isempty(ITensors.data(st)) ? 0.0 : first(ITensors.data(st))), h)
+  end
+  return h
 end
+
+function plan(fitn::ITensorNetworkFunction, dims; device=0, ngpus=1)
+  fp = network_fingerprint(fitn)
+  lock(_plan_cache_lock) do
+    entry = get!(() -> Dict{Any,Any}(), _plan_cache, itensornetwork(fitn))
+    key = (collect(dims), device, ngpus)
+    hit = get(entry, key, nothing)
+    if hit === nothing || hit[1] != fp
+      entry[key] = (fp, TTNPlan(pack(fitn, dims); device, ngpus))
+    end
+    return entry[key][2]
+  end
+end
+
+"Drop every cached plan of `fitn` (needed only after element-wise writes into a tensor's storage)."
+invalidate_plans!(fitn::ITensorNetworkFunction) =
+  lock(() -> (delete!(_plan_cache, itensornetwork(fitn)); nothing), _plan_cache_lock)
 
 "coords as the (n_coords x npts) Float64 matrix the C side reads in AOS layout"
 function coords_matrix(packed::PackedNetwork, points::AbstractMatrix)
@@ -241,28 +301,37 @@ function coords_matrix(packed::PackedNetwork, points::AbstractMatrix)
 end
 
 """
-    evaluate(fitn, points::AbstractMatrix, dims; reduce=:none, weights=nothing, device=0)
+    evaluate(fitn, points::AbstractMatrix, dims; reduce=:none, weights=nothing, device=0, ngpus=1, accuracy=:fp64)
     evaluate(fitn, points::Vector{<:Vector}, dims; ...)
+    evaluate(plan::TTNPlan, points::AbstractMatrix; ...)        # explicit plan, no cache lookup
 
 Batched `evaluate`: column `j` of `points` (or `points[j]`) holds the coordinates of point `j`
 along `dims`.  Returns `Vector{Float64}` for real networks and `Vector{ComplexF64}` for complex
 ones.  `reduce = :sum` returns the sum over all points, `:abs2` the sum of |f|^2, `:weighted` (with
 `weights`, one real weight per point) the weighted sum — the fused quadrature functionals, computed in
 the kernels' epilogues without writing the values.  Negative or NaN coordinates raise an error (the
-reference's digit loop does not terminate on them).
+reference's digit loop does not terminate on them).  `ngpus = G` shards the points over GPUs 0..G-1 of this
+process (contiguous blocks, the network replicated, every GPU copies its own block in and its values out;
+the per-GPU sums of a `reduce` are added in device order).  `accuracy = :refined` re-evaluates the points whose
+value is small against the RMS of the batch (cancellation) in double-double arithmetic, so that the relative
+error bound 1e-12 holds at the maximum and not only at the 99.9th percentile.  `points` may be any Julia
+array: pageable memory is staged through the library's pinned ring by several host threads.
 """
 function evaluate(fitn::ITensorNetworkFunction, points::AbstractMatrix,
-  dims::Vector{<:Int}=dimensions(fitn); alg=default_contraction_alg(), reduce::Symbol=:none,
-  weights::Union{Nothing,Vector{Float64}}=nothing, device=0)
+  dims::Vector{<:Int}=dimensions(fitn); alg=default_contraction_alg(), device=0, ngpus=1, kwargs...)
   @assert size(points, 1) == length(dims)
-  pl = plan(fitn, dims; device)
+  return evaluate(plan(fitn, dims; device, ngpus), points; kwargs...)
+end
+
+function evaluate(pl::TTNPlan, points::AbstractMatrix; reduce::Symbol=:none,
+  weights::Union{Nothing,Vector{Float64}}=nothing, accuracy::Symbol=:fp64)
   coords = coords_matrix(pl.packed, points)
   npts = size(coords, 2)
   T = pl.packed.is_complex ? ComplexF64 : Float64
   out = reduce == :none ? Vector{T}(undef, npts) : T[]
   w = weights === nothing ? Float64[] : weights
   reduce == :weighted && @assert length(w) == npts
-  opts = TTNOpts(; reduce, weights=(reduce == :weighted ? pointer(w) : Ptr{Float64}(C_NULL)))
+  opts = TTNOpts(; reduce, weights=(reduce == :weighted ? pointer(w) : Ptr{Float64}(C_NULL)), accuracy)
   GC.@preserve coords out pl w begin
     rc = ccall((:ttn_evaluate, LIBTTNEVAL), Cint,
       (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Int32, Ptr{Cvoid}, Ref{TTNOpts}),
@@ -299,10 +368,10 @@ The loop it replaces: examples/2d_laplace_solver.jl:46-53.  On the full dyadic g
 library shares the common digit prefixes of neighbouring grid points.
 """
 function evaluate_grid(fitn::ITensorNetworkFunction, N::Int, dims::Vector{<:Int}=dimensions(fitn);
-  reduce::Symbol=:sum, values::Bool=false, device=0)
+  reduce::Symbol=:sum, values::Bool=false, device=0, ngpus=1)
   imap = indexmap(fitn)
   @assert imap isa RealIndexMap "grid evaluation is defined for real index maps (grid_points)"
-  pl = plan(fitn, dims; device)
+  pl = plan(fitn, dims; device, ngpus)
   grids = [grid_points(imap, N, d) for d in dims]
   steps = Float64[length(g) > 1 ? g[2] : 0.0 for g in grids]
   counts = Int64[length(g) for g in grids]

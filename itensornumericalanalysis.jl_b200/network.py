@@ -75,6 +75,7 @@ class TensorNetwork:
         self.graph = graph
         self.tensors = tensors  # vertex -> Tensor
         self.links = links      # frozenset({a, b}) -> Index
+        self.version = 0        # bumped by every vertex assignment; plan caches key on it
 
     def vertices(self):
         return self.graph.vertices()
@@ -87,6 +88,7 @@ class TensorNetwork:
 
     def __setitem__(self, v, t):
         self.tensors[v] = t
+        self.version += 1
 
     def copy(self):
         return TensorNetwork(self.graph, {v: t.copy() for v, t in self.tensors.items()},
