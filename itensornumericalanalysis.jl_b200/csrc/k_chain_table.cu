@@ -266,6 +266,17 @@ __global__ void __launch_bounds__(NT, MINB)
       }
     }
 
+    if (src.dbg_stream) { // test hook: the fused K1's digits, compared as integers by the tests
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) {
+        const int64_t p = p0 + (int64_t)k * NT;
+        if (p < src.npts) {
+          src.dbg_stream[2 * p] = w0[k];
+          src.dbg_stream[2 * p + 1] = W2 ? w1[k] : 0ull;
+        }
+      }
+    }
+
     // slice index of the group at stream offset `off` (lb bits): one funnel shift + mask on a one-word
     // stream; the two-word stream is consumed by shifting (groups are visited in stream order)
     auto take = [&](int k, int off, int lb) -> uint32_t {

@@ -195,6 +195,16 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     {
       uint64_t w0[PPL];
       compute_words(tile, w0, w1);
+      if (src.dbg_stream) { // test hook: the fused K1's digits, compared as integers by the tests
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int64_t p = p0 + k * 32 + lane;
+          if (p < src.npts) {
+            src.dbg_stream[2 * p] = w0[k];
+            src.dbg_stream[2 * p + 1] = w1[k];
+          }
+        }
+      }
       // ---- leaf rows
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {

@@ -1170,6 +1170,57 @@ int ttn_debug_table_image(const ttn_desc* desc, int32_t budget_kb, int32_t* meta
   return debug_table_image(desc, budget_kb, meta, image, image_cap, site_bitpos);
 }
 
+/* Test hook, not part of include/ttneval.h: the packed slice stream — i.e. the DIGITS — that the kernels with a
+ * fused K1 really use (team-sorted DMMA kernel: run fast path floor(x 2^L); table kernel: 32-bit saturating
+ * conversion, bit-deposit network).  One launch of `kernel` (TTN_KERNEL_DMMA / TTN_KERNEL_TABLE) over npts AoS host
+ * points; words_out[2p], [2p+1] = the 128-bit stream of point p; site_bit[s] = stream bit of site index s of the
+ * description (its digit = that bit).  tests/test_gpu_round2.py compares these integers with the CPU greedy loop. */
+int ttn_debug_slice_stream(ttn_plan* plan, const double* coords, int64_t npts, int32_t kernel, uint64_t* words_out,
+                           int32_t* site_bit) {
+  if (!plan || !coords || !words_out || !site_bit || npts <= 0) return fail(TTN_ERR_INVALID, "null / empty argument");
+  if (!plan->replicas.empty()) plan = plan->replicas[0];
+  if (!plan->all_base2) return fail(TTN_ERR_UNSUPPORTED, "slice-stream dump: binary site indices only");
+  const DigitTable* dt = nullptr;
+  if (kernel == TTN_KERNEL_DMMA && plan->cmma_ok && chain_team_applicable(plan)) dt = &plan->digits_mma;
+  if (kernel == TTN_KERNEL_TABLE && plan->ctab_ok) dt = &plan->digits_tab;
+  if (!dt) return fail(TTN_ERR_UNSUPPORTED, "slice-stream dump: the team-sorted DMMA kernel or the table kernel must apply");
+  std::lock_guard<std::mutex> lock(plan->mu);
+  DeviceGuard guard(plan->device);
+  if (!guard.ok) return fail(TTN_ERR_CUDA, "cudaSetDevice failed");
+  const int nc = plan->info.n_coords, ns = plan->info.n_sites, NC = plan->info.is_complex ? 2 : 1;
+  Stream& st = plan->streams[0];
+  int rc = ensure_stream_buffers(plan, st, npts, true, true);
+  if (rc) return rc;
+  unsigned long long* d_words = nullptr;
+  TTN_CUDA(cudaMalloc(&d_words, sizeof(unsigned long long) * 2 * (size_t)npts));
+  cudaMemsetAsync(plan->d_err, 0, sizeof(int), st.s);
+  cudaMemcpyAsync(st.d_coords, coords, sizeof(double) * (size_t)npts * nc, cudaMemcpyHostToDevice, st.s);
+  CoordSource src{};
+  src.coords = st.d_coords;
+  src.npts = npts;
+  src.n_coords = nc;
+  src.layout = TTN_LAYOUT_AOS;
+  src.dbg_stream = d_words;
+  int n_partial = 0, extra = 0;
+  rc = run_kernel(plan, kernel, st, src, st.d_out, nullptr, &n_partial, &extra);
+  (void)NC;
+  if (rc == TTN_OK) {
+    cudaMemcpyAsync(words_out, d_words, sizeof(unsigned long long) * 2 * (size_t)npts, cudaMemcpyDeviceToHost, st.s);
+    const cudaError_t e = cudaStreamSynchronize(st.s);
+    if (e != cudaSuccess) rc = fail(TTN_ERR_CUDA, std::string("slice-stream dump: ") + cudaGetErrorString(e));
+  }
+  cudaFree(d_words);
+  if (rc) return rc;
+  std::vector<DigitEntry> ent((size_t)std::max(ns, 1));
+  TTN_CUDA(cudaMemcpy(ent.data(), dt->entries, sizeof(DigitEntry) * (size_t)ns, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < ns; ++i) {
+    int lg = 0;
+    while ((1 << lg) < ent[i].stride) ++lg;
+    site_bit[ent[i].site] = ent[i].word * 64 + ent[i].shift + lg;
+  }
+  return TTN_OK;
+}
+
 int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops) {
   if (!dfma_tflops || !dmma_tflops) return fail(TTN_ERR_INVALID, "null argument");
   return measure_fp64_peak(device, dfma_tflops, dmma_tflops);

@@ -58,6 +58,9 @@ struct CoordSource {
   const uint8_t* digits; // index-setting mode (ttn_evaluate_indices): digits[p * n_sites + site], else nullptr
   int32_t reduce_mode;   // TTN_REDUCE_* (what the kernels accumulate per point)
   const double* weights; // TTN_REDUCE_WEIGHTED: device pointer, one weight per point of this launch
+  unsigned long long* dbg_stream; // test hook (ttn_debug_slice_stream): the kernels with a FUSED K1 (team-sorted DMMA
+                                  // kernel, table kernel) store the packed slice stream of point p — the digits they
+                                  // really use — at dbg_stream[2p], [2p + 1]; nullptr in every product call
 };
 
 // ---- generic tree program (device) ---------------------------------------------------
