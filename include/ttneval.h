@@ -63,7 +63,7 @@ enum {
 
 /* ---- pageable host buffers (ABI 3).  cudaMemcpyAsync from pageable memory is staged by the driver on one thread
  * and collapses the H2D / kernel / D2H pipeline, so ttn_evaluate copies pageable buffers through an internal
- * pinned ring with several host threads (TTN_HOST_THREADS, default min(8, cores)).  Buffers the caller pinned
+ * pinned ring with several host threads (TTN_HOST_THREADS, default min(16, cores)).  Buffers the caller pinned
  * (cudaHostAlloc / ttn_host_register) are used in place.  A registration is never cached across calls: a stale
  * one would outlive a freed Julia / numpy array. */
 enum {

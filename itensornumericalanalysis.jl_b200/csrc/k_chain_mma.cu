@@ -56,7 +56,7 @@ struct ChainImage {
 // exactly the same packed bit stream read k*bits0 bits at a time — so K1 and the run fast path are
 // untouched while a point needs 1/k as many matrix-vector products.  Products are accumulated in
 // long double and rounded once.  Needs (#positions) % k == 0 and >= 2k positions.
-static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0, int kL, int kR) {
+static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0, int kL, int kR, int kLh, int kRh) {
   // positions: leaf group = leaf + steps[0, kL-1), middle groups of k steps, root group =
   // steps[T-(kR-1), T) + root.  kL and kR may be much larger than k ("deep" leaf / root tables of
   // 2^(bits0 kL) vectors, kept in global memory): those are built with vector products only, one
@@ -71,7 +71,7 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
     std::vector<double> cur((size_t)S0 * CHI);
     for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.leaf[i];
     size_t n_cur = (size_t)1 << bits0;
-    for (int i = 1; i < kL; ++i) {
+    for (int i = 1; i < kLh; ++i) { // levels kLh .. kL - 1 are added on the device (extend_deep_tables)
       std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
       const std::vector<double>& E = a.steps[i - 1];
       for (int bsl = 0; bsl < S0; ++bsl) {
@@ -129,13 +129,13 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
   // ---- root table, built from the root backwards (the member nearest the leaf owns the LOW bits):
   // R_j[s + (idx << bits0)][i] = sum_l E_j[s][i][l] R_{j+1}[idx][l]
   {
-    const size_t SR = (size_t)1 << (bits0 * kR);
+    const size_t SR = (size_t)1 << (bits0 * kRh); // members kR - kRh - 1 .. 0 are added on the device
     m.root.assign((size_t)nout * SR * CHI, 0.0);
     for (int o = 0; o < nout; ++o) {
       std::vector<double> cur((size_t)S0 * CHI);
       for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.root[(size_t)o * S0 * CHI + i];
       size_t n_cur = (size_t)1 << bits0;
-      for (int j = kR - 2; j >= 0; --j) { // step index T - (kR - 1) + j
+      for (int j = kR - 2; j >= kR - kRh; --j) { // step index T - (kR - 1) + j
         const std::vector<double>& E = a.steps[T - (kR - 1) + j];
         std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
         for (int sl = 0; sl < S0; ++sl) {
@@ -192,6 +192,126 @@ static int upload_chain_image(ttn_plan* p, const ChainImage& im, int CHI, ChainM
   return TTN_OK;
 }
 
+// ---- deep leaf / root tables, upper levels on the device.  The host (merge_groups) builds the tables of the
+// first kLh / last kRh vertices; every further member doubles (x 2^bits0) the table with one vector-matrix
+// product per row.  Dot products are accumulated in double-double (error-free two_prod via FMA + two_sum) and
+// rounded once per member — the same "long accumulation, one rounding per member" the host loop does in long
+// double, at a few ms for 2^20 rows instead of seconds.
+struct dd2 {
+  double hi, lo;
+};
+__device__ __forceinline__ void dd2_mac(dd2& acc, double a, double b) {
+  const double pr = __dmul_rn(a, b);
+  const double e = __fma_rn(a, b, -pr);
+  const double t = __dadd_rn(acc.hi, pr);
+  const double bb = __dsub_rn(t, acc.hi);
+  const double err = __dadd_rn(__dsub_rn(acc.hi, __dsub_rn(t, bb)), __dsub_rn(pr, bb));
+  acc.lo = __dadd_rn(acc.lo, __dadd_rn(err, e));
+  acc.hi = t;
+}
+// nxt[s + (b << shift)][j] = sum_k cur[s][k] E[b][k][j]
+__global__ void deep_leaf_extend_kernel(const double* __restrict__ cur, size_t n_cur, const double* __restrict__ E, int S0,
+                                        int shift, int CHI, double* __restrict__ nxt) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cur * S0 * CHI) return;
+  const int j = (int)(idx % CHI), b = (int)((idx / CHI) % S0);
+  const size_t sidx = idx / ((size_t)CHI * S0);
+  const double* A = cur + sidx * CHI;
+  const double* B = E + (size_t)b * CHI * CHI + j;
+  dd2 acc{0.0, 0.0};
+  for (int k = 0; k < CHI; ++k) dd2_mac(acc, A[k], __ldg(B + (size_t)k * CHI));
+  nxt[(sidx + ((size_t)b << shift)) * CHI + j] = __dadd_rn(acc.hi, acc.lo);
+}
+// nxt[sl + (idx << bits0)][i] = sum_l E[sl][i][l] cur[idx][l]
+__global__ void deep_root_extend_kernel(const double* __restrict__ cur, size_t n_cur, const double* __restrict__ E, int S0,
+                                        int bits0, int CHI, double* __restrict__ nxt) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_cur * S0 * CHI) return;
+  const int i = (int)(idx % CHI), sl = (int)((idx / CHI) % S0);
+  const size_t ridx = idx / ((size_t)CHI * S0);
+  const double* A = E + ((size_t)sl * CHI + i) * CHI;
+  const double* Rv = cur + ridx * CHI;
+  dd2 acc{0.0, 0.0};
+  for (int l = 0; l < CHI; ++l) dd2_mac(acc, __ldg(A + l), Rv[l]);
+  nxt[((size_t)sl + (ridx << bits0)) * CHI + i] = __dadd_rn(acc.hi, acc.lo);
+}
+
+static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nout, int bits0, int kLh, int kL, int kRh,
+                              int kR, ChainMmaDev& c) {
+  const int S0 = a.nsl, T = (int)a.steps.size();
+  const size_t M = (size_t)CHI * CHI;
+  double* d_E = nullptr;
+  TTN_CUDA(cudaMalloc(&d_E, (size_t)S0 * M * 8));
+  int rc = TTN_OK;
+  auto run = [&](bool leaf, const double* start, size_t n_start, int lv0, int lv1, double** result) -> int {
+    // levels lv0 .. lv1 - 1; ping-pong between two buffers of the final size, the last level lands in `fin`
+    const size_t rows_fin = n_start << (bits0 * (lv1 - lv0));
+    double *fin = nullptr, *tmp = nullptr;
+    TTN_CUDA(cudaMalloc(&fin, rows_fin * CHI * 8));
+    p->allocs.push_back(fin);
+    if (cudaMalloc(&tmp, std::max<size_t>(rows_fin / S0, 1) * CHI * 8) != cudaSuccess) {
+      set_error("deep tables: out of device memory");
+      return TTN_ERR_NOMEM;
+    }
+    const int nlev = lv1 - lv0;
+    const double* cur = start;
+    size_t n_cur = n_start;
+    for (int q = 0; q < nlev; ++q) {
+      double* dst = ((nlev - 1 - q) % 2 == 0) ? fin : tmp;
+      // leaf level i uses step i - 1; root member j (descending) uses step T - (kR - 1) + j
+      const int step = leaf ? (lv0 + q) - 1 : T - (kR - 1) + (kR - 1 - (lv0 + q));
+      cudaMemcpy(d_E, a.steps[step].data(), (size_t)S0 * M * 8, cudaMemcpyHostToDevice);
+      const size_t total = n_cur * S0 * CHI;
+      const unsigned grid = (unsigned)((total + 255) / 256);
+      if (leaf) deep_leaf_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, bits0 * (lv0 + q), CHI, dst);
+      else deep_root_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, bits0, CHI, dst);
+      cudaDeviceSynchronize(); // d_E is reused by the next level
+      cur = dst;
+      n_cur <<= bits0;
+    }
+    cudaFree(tmp);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error(std::string("deep tables: ") + cudaGetErrorString(e));
+      return TTN_ERR_CUDA;
+    }
+    *result = fin;
+    return TTN_OK;
+  };
+  if (kL > kLh) {
+    double* fin = nullptr;
+    rc = run(true, c.leaf, (size_t)1 << (bits0 * kLh), kLh, kL, &fin);
+    if (rc == TTN_OK) c.leaf = fin;
+  }
+  if (rc == TTN_OK && kR > kRh) {
+    // nout tables back to back: [o][2^(bits0 kR)][CHI]
+    const size_t rows_h = (size_t)1 << (bits0 * kRh), rows_f = (size_t)1 << (bits0 * kR);
+    double* all = nullptr;
+    if (nout == 1) {
+      rc = run(false, c.root, rows_h, kRh, kR, &all);
+    } else {
+      if (cudaMalloc(&all, (size_t)nout * rows_f * CHI * 8) != cudaSuccess) {
+        set_error("deep tables: out of device memory");
+        rc = TTN_ERR_NOMEM;
+      } else {
+        p->allocs.push_back(all);
+        for (int o = 0; o < nout && rc == TTN_OK; ++o) {
+          double* one = nullptr;
+          rc = run(false, c.root + (size_t)o * rows_h * CHI, rows_h, kRh, kR, &one);
+          if (rc == TTN_OK) cudaMemcpy(all + (size_t)o * rows_f * CHI, one, rows_f * CHI * 8, cudaMemcpyDeviceToDevice);
+          if (rc == TTN_OK) { // `one` was pushed to p->allocs by run(): release it now
+            p->allocs.pop_back();
+            cudaFree(one);
+          }
+        }
+      }
+    }
+    if (rc == TTN_OK) c.root = all;
+  }
+  cudaFree(d_E);
+  return rc;
+}
+
 int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   p->cmma_ok = false;
   p->cmma_plain_ok = false;
@@ -242,12 +362,13 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   int kL = kmerge, kR = kmerge;
   {
     const bool v6_on = p->v6_teams != 0 && p->all_base2;
-    // default: only when the two tables absorb the WHOLE chain with <= 2^16 rows each (L2-resident,
-    // built in a fraction of a second): the evaluation is then two row gathers and a dot product.
-    // TTN_MMA_DEEP=b sets the budget to 2^b rows of 16 doubles for any chain (0 disables); measured
-    // on config 2 with b = 20: 5.7 G points/s device-resident instead of 3.6 G, 2 x 128 MB of
-    // tables, 2 s of plan time, the kernel then bound by random 128-byte HBM gathers
-    int deep_bits = (n * bits0 <= 32) ? 16 : 0;
+    // default budget: 2^16 rows of 16 doubles when the two tables then absorb the WHOLE chain (L2-resident:
+    // the evaluation is two row gathers and a dot product), else 2^20 rows (2 x 128 MB).  Measured on config 2
+    // (scripts/deep_bits_sweep.py, 1e8 points, G points/s device-resident): no deep tables 3.58, 2^12 4.37,
+    // 2^16 5.20, 2^18 5.55, 2^20 5.98 — fewer DMMA rounds per point (13 -> 5) against two random 128-byte row
+    // gathers.  The upper table levels are built on the device (extend_deep_tables: 2^20 rows in milliseconds;
+    // the host loop took 2 s).  TTN_MMA_DEEP=b overrides (0 disables).
+    int deep_bits = (n * bits0 <= 32) ? 16 : 20;
     if (const char* e = getenv("TTN_MMA_DEEP")) deep_bits = std::min(atoi(e), 22);
     if (merge && v6_on && deep_bits > 0) {
       const int lb = deep_bits - (CHI >= 32 ? 1 : 0) + (CHI <= 8 ? 1 : 0), rb = lb - (cplx ? 1 : 0);
@@ -402,8 +523,11 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   }
   int NSL = NSL0, bits = bits0;
   if (merge) {
-    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0, kL, kR);
+    // host levels: up to 2^10 rows per table; the rest of a deep table is built on the device
+    const int kLh = std::min(kL, std::max(kmerge, 10 / bits0)), kRh = std::min(kR, std::max(kmerge, 10 / bits0));
+    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0, kL, kR, kLh, kRh);
     if ((rc = upload_chain_image(p, mg, CHI, c))) return rc;
+    if ((kL > kLh || kR > kRh) && (rc = extend_deep_tables(p, im, CHI, nout, bits0, kLh, kL, kRh, kR, c))) return rc;
     NSL = mg.nsl;
     bits = bits0 * kmerge;
     spr = 1;

@@ -1,5 +1,6 @@
 // C ABI of libttneval.so (include/ttneval.h): plan construction, chunked/pipelined evaluation,
 // error reporting.  Everything here is host code around the kernels in k_*.cu.
+#include <immintrin.h>
 #include <sched.h>
 
 #include <algorithm>
@@ -303,6 +304,34 @@ constexpr int kMaxChunks = 4096;
 // thread at 10-20 GB/s and serialises the H2D / kernel / D2H pipeline.  Pageable chunks are therefore copied
 // to / from a pinned ring (Stream::h_*) by a small pool of host threads, slice by slice.  The pool is a
 // process-wide leaked singleton (worker threads must not be joined from a library destructor).
+// Streaming copy for the staging ring: the destination (the pinned ring on the way in, the caller's array on the
+// way out) is not read by the CPU soon, so non-temporal stores skip the read-for-ownership of every destination
+// line — a third less DRAM traffic than memcpy, on a path whose host side is memory-bound (the DMA engines read /
+// write the same DRAM at PCIe rate meanwhile).
+__attribute__((target("avx2"))) static void stream_copy_avx2(char* dst, const char* src, size_t n) {
+  const size_t head = std::min(n, (size_t)((32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31));
+  if (head) memcpy(dst, src, head);
+  dst += head, src += head, n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+    const __m256i a1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+    const __m256i a2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+    const __m256i a3 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a0);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), a1);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), a2);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), a3);
+  }
+  _mm_sfence();
+  if (i < n) memcpy(dst + i, src + i, n - i);
+}
+static void stream_copy(void* dst, const void* src, size_t n) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && n >= 4096) stream_copy_avx2(static_cast<char*>(dst), static_cast<const char*>(src), n);
+  else memcpy(dst, src, n);
+}
+
 class CopyPool {
  public:
   static CopyPool& get() {
@@ -313,7 +342,7 @@ class CopyPool {
   void copy(void* dst, const void* src, size_t bytes) {
     constexpr size_t kSlice = (size_t)1 << 20;
     if (bytes <= 2 * kSlice || workers_ == 0) {
-      memcpy(dst, src, bytes);
+      stream_copy(dst, src, bytes);
       return;
     }
     auto job = std::make_shared<Job>();
@@ -344,7 +373,7 @@ class CopyPool {
   CopyPool() {
     int n = 8;
     cpu_set_t set;
-    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(8, std::max(1, CPU_COUNT(&set)));
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(16, std::max(1, CPU_COUNT(&set)));
     if (const char* e = getenv("TTN_HOST_THREADS")) n = std::max(1, std::min(atoi(e), 64));
     workers_ = n - 1;
     for (int i = 0; i < workers_; ++i) std::thread([this] { worker(); }).detach();
@@ -355,7 +384,7 @@ class CopyPool {
       const size_t i = j.next.fetch_add(1);
       if (i >= j.n_slices) return;
       const size_t off = i * kSlice, len = std::min(kSlice, j.bytes - off);
-      memcpy(j.dst + off, j.src + off, len);
+      stream_copy(j.dst + off, j.src + off, len);
       if (j.done.fetch_add(1) + 1 == j.n_slices) {
         std::lock_guard<std::mutex> lk(j.mu);
         j.cv.notify_all();
