@@ -32,6 +32,24 @@ struct __align__(16) Digit2 {
 constexpr int kFeMaxSites = 160; // static shared-memory copies of the digit tables (within the 12 KB the
 constexpr int kFeMaxThr = 640;   // launchers reserve); larger networks take the chain / generic kernels
 
+// K1 of one site index for NP points of a thread when the network has non-binary site indices (base 3 / 4,
+// test/test_realitensorfunction.jl:89-104): the tabulated greedy loop of k_digits.cuh on the global-memory digit
+// table (warp-uniform addresses: one broadcast load per entry), digit value v placed as v * stride at the site's
+// stream position.  step = distance between two points of the thread.
+template <int NP>
+__device__ __forceinline__ void k1_generic_site(const DigitTable& dg, const CoordSource& src, int e_i, int64_t p0, int64_t step,
+                                                double (&x)[NP], uint64_t (&w0)[NP], uint64_t (&w1)[NP], int* err) {
+  const DigitEntry e = dg.entries[e_i];
+  const double* thr = dg.thr + e.thr_off;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const int v = src.digits ? given_digit(src, p0 + k * step, dg.n_sites, e.site, e.base, err) : greedy_digit(x[k], thr, e.base);
+    const uint64_t bb = (uint64_t)(uint32_t)(v * e.stride) << e.shift;
+    if (e.word) w1[k] += bb;
+    else w0[k] += bb;
+  }
+}
+
 __device__ __forceinline__ int greedy_digit_smem(double& x, const double* thr, int base) {
   int v = base - 1;
   double t = thr[v];

@@ -327,7 +327,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   const int CHI = cplx ? mma_width(2 * maxchi) : mma_width(maxchi);
   const int H = CHI / 2; // complex: row = [re(H) | im(H)]
   if (CHI == 0 || maxsl > 4) return TTN_OK;
-  const int NSL0 = maxsl; // slices per vertex of the network as given
+  const int NSL0 = maxsl == 3 ? 4 : maxsl; // slices per vertex; a base-3 index takes a 2-bit field (slice 3: zero matrix, never selected)
   const int bits0 = NSL0 <= 1 ? 0 : (NSL0 <= 2 ? 1 : 2); // stream bits per VERTEX
   // group merging (merge_groups): k vertices per stream position when the slice indices are bit
   // fields, the merged position has <= 16 slices and one position's matrices stay <= 32 KB (one
@@ -344,7 +344,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     }
     // the team-sorted kernel (v6) reads site matrices straight from L2 into registers: no ring-stage
     // limit and up to 32 slices per position; the ring kernels take <= 16 slices and <= 32 KB per position
-    const bool v6_on = p->v6_teams != 0 && p->all_base2;
+    const bool v6_on = p->v6_teams != 0;
     if (NSL0 == 2 || NSL0 == 4)
       for (int kk : cand) {
         const int sb = bits0 * kk;
@@ -361,7 +361,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // (<= 128 MB each); a point gathers one row of each and runs only the middle groups as rounds.
   int kL = kmerge, kR = kmerge;
   {
-    const bool v6_on = p->v6_teams != 0 && p->all_base2;
+    const bool v6_on = p->v6_teams != 0;
     // default budget: 2^16 rows of 16 doubles when the two tables then absorb the WHOLE chain (L2-resident:
     // the evaluation is two row gathers and a dot product), else 2^20 rows (2 x 128 MB).  Measured on config 2
     // (scripts/deep_bits_sweep.py, 1e8 points, G points/s device-resident): no deep tables 3.58, 2^12 4.37,
@@ -542,6 +542,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     c.n_steps = n_steps_p;
   }
   c.merged = merge ? kmerge : 0;
+  c.k1_generic = p->all_base2 ? 0 : 1;
   c.leaf_bits = merge ? bits0 * kL : bits0; // stream bits the leaf / root group consumes
   c.root_bits = merge ? bits0 * kR : bits0;
   c.nsl = NSL;

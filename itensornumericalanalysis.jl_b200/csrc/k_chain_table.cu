@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
         for (int k = 0; k < PPT; ++k) w1[k] += q[k] << (plow - 64);
       }
+    } else if (ct.k1_generic) {
+      for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_generic_site<PPT>(dg, src, e_i, p0, NT, x, w0, w1, err);
     } else {
       for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
         const Digit2 e = s_d2[e_i];
@@ -463,9 +465,13 @@ static bool make_table_image(const ttn_desc* d, size_t budget_bytes, bool allow_
   }
   int maxchi = 1, maxsl = 1;
   for (int v = 0; v < n; ++v) {
+    // slice indices are bit fields of the stream: binary site indices (1 or 2 per vertex), or ONE site index of
+    // dimension 3 or 4 (base 3 / 4 digits) in a 2-bit field (slice 3 of a base-3 vertex is an all-zero matrix that
+    // no point selects)
     for (int si = d->site_ptr[v]; si < d->site_ptr[v + 1]; ++si) {
-      if (d->site_dim[si] != 2) return false; // binary digits only (bit-field slice indices)
-      nsl[v] *= 2;
+      if (d->site_dim[si] < 2 || d->site_dim[si] > 4) return false;
+      if (d->site_dim[si] > 2 && d->site_ptr[v + 1] - d->site_ptr[v] != 1) return false;
+      nsl[v] *= d->site_dim[si];
     }
     maxchi = std::max(maxchi, d->link_dim[v]);
     maxsl = std::max(maxsl, nsl[v]);
@@ -707,7 +713,7 @@ static size_t table_budget_bytes() {
 
 int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   p->ctab_ok = false;
-  if (!p->is_chain || !p->all_base2) return TTN_OK;
+  if (!p->is_chain) return TTN_OK;
   TableImage im;
   const bool allow_rep = !(getenv("TTN_TABLE_REP") && atoi(getenv("TTN_TABLE_REP")) == 0);
   if (!make_table_image(d, table_budget_bytes(), allow_rep, &im)) return TTN_OK;
@@ -717,6 +723,7 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   c.H = im.H;
   c.cplx = im.cplx;
   c.rep = im.rep;
+  c.k1_generic = p->all_base2 ? 0 : 1;
   c.total_doubles = (int)im.image.size();
   for (int g = 0; g < c.n_groups; ++g) {
     c.gbits[g] = im.gbits[g];

@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
             w1[k] += q << (plow - 64);
           }
         }
+      } else if (ch.k1_generic) {
+        for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_generic_site<PPL>(dg, src, e_i, p0 + lane, 32, x, w0, w1, err);
       } else {
         for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) {
           const Digit2 e = s_d2[e_i];
@@ -438,7 +440,7 @@ static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, 
 
 bool chain_team_applicable(const ttn_plan* p) {
   const ChainMmaDev& c = p->cmma;
-  if (!p->v6_teams || !c.merged || !p->all_base2 || c.spr != 1) return false;
+  if (!p->v6_teams || !c.merged || c.spr != 1) return false;
   if (c.chi == 8 || c.chi == 16) return c.nsl == 4 || c.nsl == 8 || c.nsl == 16 || c.nsl == 32;
   return c.chi == 32 && (c.nsl == 4 || c.nsl == 8 || c.nsl == 16);
 }
@@ -447,7 +449,7 @@ int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double
                       cudaStream_t s) {
   const ChainMmaDev& c = p->cmma;
   const int v6 = p->v6_teams;
-  if (v6 && c.merged && p->all_base2 && c.spr == 1) {
+  if (v6 && c.merged && c.spr == 1) {
 #define TTN_V6_CASE(W, N)                                                                                   \
   if (c.chi == W && c.nsl == N)                                                                             \
     return v6 == 2 ? launch_mma6_inst<W, N, 2, 128>(p, src, d_out, d_partial, n_partial, s)                 \

@@ -140,6 +140,156 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+// ---- classification of the evaluation path: only the vertices that run as GEMMs need row lists, a vertex may
+// be a MERGED run of up to 4 single-child vertices (class = their slice bits side by side, <= 16 classes), and
+// the chunk is split over many blocks (count -> offsets -> scatter); one block per vertex walking the chunk alone
+// took a third of a narrow tree's time (profiles/r01_launches_tree_comb_summary.txt).
+constexpr int TCLS = 16, TOFF = TCLS + 1, TSEG = 4096;
+struct TgClass {
+  int32_t v;       // list / offset slot (the top vertex of a merged run)
+  int32_t nsl;     // classes
+  int32_t n_mem;   // member vertices
+  int32_t mem_v[4], mem_shift[4];
+};
+
+__device__ __forceinline__ int tg_class_of(const uint8_t* __restrict__ slices, int pc, const TgClass& g, int i) {
+  int c = 0;
+  for (int m = 0; m < g.n_mem; ++m) c |= (int)slices[(size_t)g.mem_v[m] * pc + i] << g.mem_shift[m];
+  return c;
+}
+
+__global__ void __launch_bounds__(256) tree_count_kernel(const uint8_t* __restrict__ slices, int pc, const TgClass* __restrict__ gv,
+                                                         int* __restrict__ counts) {
+  const TgClass g = gv[blockIdx.y];
+  __shared__ int cnt[TCLS];
+  if (threadIdx.x < TCLS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int i_end = min(pc, (int)(blockIdx.x + 1) * TSEG);
+  int local = 0; // lane c keeps the warp's count of class c
+  for (int i0 = blockIdx.x * TSEG + (threadIdx.x - lane); i0 < i_end; i0 += 256) {
+    const int i = i0 + lane;
+    const int c = i < i_end ? tg_class_of(slices, pc, g, i) : -1;
+    for (int k = 0; k < g.nsl; ++k) {
+      const int n = __popc(__ballot_sync(0xffffffffu, c == k));
+      if (lane == k) local += n;
+    }
+  }
+  if (lane < g.nsl && local) atomicAdd(&cnt[lane], local);
+  __syncthreads();
+  if (threadIdx.x < g.nsl && cnt[threadIdx.x]) atomicAdd(&counts[blockIdx.y * TOFF + threadIdx.x], cnt[threadIdx.x]);
+}
+
+__global__ void tree_offsets_kernel(const TgClass* __restrict__ gv, int nv, const int* __restrict__ counts,
+                                    int* __restrict__ cls_off, int* __restrict__ tile_off, int* __restrict__ cursor) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= nv) return;
+  const TgClass g = gv[y];
+  int run = 0, trun = 0;
+  for (int c = 0; c <= TCLS; ++c) {
+    cls_off[g.v * TOFF + c] = run;
+    tile_off[g.v * TOFF + c] = trun;
+    if (c < TCLS) cursor[y * TOFF + c] = run;
+    const int n = c < g.nsl ? counts[y * TOFF + c] : 0;
+    run += n;
+    trun += (n + TBM - 1) / TBM;
+  }
+}
+
+__global__ void __launch_bounds__(256) tree_scatter_kernel(const uint8_t* __restrict__ slices, int pc, const TgClass* __restrict__ gv,
+                                                           int* __restrict__ cursor, uint32_t* __restrict__ lists) {
+  const TgClass g = gv[blockIdx.y];
+  uint32_t* list = lists + (size_t)g.v * pc;
+  __shared__ int cnt[TCLS], base[TCLS];
+  if (threadIdx.x < TCLS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int i_beg = blockIdx.x * TSEG, i_end = min(pc, i_beg + TSEG);
+  if (g.nsl == 1) {
+    for (int i = i_beg + threadIdx.x; i < i_end; i += 256) list[i] = (uint32_t)i;
+    return;
+  }
+  int local = 0;
+  for (int i0 = i_beg + (threadIdx.x - lane); i0 < i_end; i0 += 256) {
+    const int i = i0 + lane;
+    const int c = i < i_end ? tg_class_of(slices, pc, g, i) : -1;
+    for (int k = 0; k < g.nsl; ++k) {
+      const int n = __popc(__ballot_sync(0xffffffffu, c == k));
+      if (lane == k) local += n;
+    }
+  }
+  if (lane < g.nsl && local) atomicAdd(&cnt[lane], local);
+  __syncthreads();
+  if (threadIdx.x < g.nsl) {
+    base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[blockIdx.y * TOFF + threadIdx.x], cnt[threadIdx.x]) : 0;
+    cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  for (int i0 = i_beg + (threadIdx.x - lane); i0 < i_end; i0 += 256) {
+    const int i = i0 + lane;
+    const int c = i < i_end ? tg_class_of(slices, pc, g, i) : -1;
+    for (int k = 0; k < g.nsl; ++k) {
+      const uint32_t m = __ballot_sync(0xffffffffu, c == k);
+      if (m) { // warp-uniform
+        int b = 0;
+        if (lane == 0) b = atomicAdd(&cnt[k], __popc(m));
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (c == k) list[base[k] + b + __popc(m & lt)] = (uint32_t)i;
+      }
+    }
+  }
+}
+
+// root with two children and W <= 32: one THREAD per point, the root tensor of every slice in shared memory
+// (value = sum_a M_a[a] sum_b T_d[a][b] M_b[b]); the warp-per-point kernel below spent a quarter of a narrow
+// tree's time here.
+template <int W>
+__global__ void __launch_bounds__(128) tree_root2_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb,
+                                                         const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
+                                                         const double* __restrict__ T, int nsl, double* __restrict__ out,
+                                                         double* __restrict__ partial, int do_sum, CoordSource src) {
+  extern __shared__ __align__(16) double sT[]; // [nsl][W][W]
+  for (int i = threadIdx.x; i < nsl * W * W; i += 128) sT[i] = T[i];
+  __syncthreads();
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const bool live = i < pc && p0 + i < npts;
+  double v = 0.0;
+  if (live) {
+    double mb[W];
+    const double2* rb = reinterpret_cast<const double2*>(Mb + (size_t)i * W);
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) {
+      const double2 t = rb[j];
+      mb[2 * j] = t.x;
+      mb[2 * j + 1] = t.y;
+    }
+    const double* Td = sT + (size_t)sl[i] * W * W;
+    const double* ra = Ma + (size_t)i * W;
+#pragma unroll 4
+    for (int a = 0; a < W; ++a) {
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < W; ++b) s = fma(Td[a * W + b], mb[b], s);
+      v = fma(ra[a], s, v);
+    }
+    if (out) out[p0 + i] = v;
+  }
+  if (do_sum) {
+    __shared__ double sh[128];
+    double a0 = 0.0, a1 = 0.0;
+    if (live) accumulate_point(src, p0 + i, v, 0.0, a0, a1);
+    sh[threadIdx.x] = a0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (int k = 0; k < 128; ++k) a += sh[k]; // fixed order: deterministic
+      partial[2 * blockIdx.x] = a;
+      partial[2 * blockIdx.x + 1] = 0.0;
+    }
+  }
+}
+
 __global__ void tree_leaf_kernel(const uint8_t* __restrict__ sl, int pc, const double* __restrict__ T, int W,
                                  double* __restrict__ M) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // one double2 per thread
@@ -348,6 +498,7 @@ __global__ void tree_table_kernel(const uint8_t* __restrict__ slices, int pc, co
 // ------------------------------------------------------------------------------ host side
 
 static int build_tree_tables(ttn_plan* p, const ttn_desc* d);
+static int build_tree_merge(ttn_plan* p, const ttn_desc* d);
 
 int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   p->tgemm_ok = false;
@@ -430,7 +581,8 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   TTN_CUDA(cudaMemcpy(d_ns, p->nslices.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
   g.nslices = d_ns;
   p->tgemm_ok = true;
-  return build_tree_tables(p, d);
+  if (int rc = build_tree_tables(p, d)) return rc;
+  return build_tree_merge(p, d);
 }
 
 template <int W, int NCH>
@@ -473,7 +625,7 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   const size_t msg_b = (size_t)PC * W * 8;
   const size_t slices_b = ((size_t)n * PC + 255) / 256 * 256;
   const size_t lists_b = (size_t)n * PC * 4;
-  const size_t offs_b = (size_t)n * 9 * 4 * 2 + 256;
+  const size_t offs_b = (size_t)n * TOFF * 4 * 4 + 256; // cls_off, tile_off, counts, cursor
   const size_t need = (size_t)n * msg_b + slices_b + lists_b + offs_b;
   if (st.gemm_bytes < need) {
     if (st.d_gemm) cudaFree(st.d_gemm);
@@ -487,10 +639,14 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   uint8_t* slices = base + (size_t)n * msg_b;
   uint32_t* lists = reinterpret_cast<uint32_t*>(slices + slices_b);
   int* cls_off = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(lists) + lists_b);
-  int* tile_off = cls_off + (size_t)n * 9 + 16;
+  int* tile_off = cls_off + (size_t)n * TOFF;
+  int* counts = tile_off + (size_t)n * TOFF;
+  int* cursor = counts + (size_t)n * TOFF;
   const int do_sum = d_partial != nullptr;
   const int64_t n_chunks = (src.npts + PC - 1) / PC;
-  const int root_blocks = (PC * 32 + 255) / 256;
+  const int root_nch = p->child_ptr[g.root + 1] - p->child_ptr[g.root];
+  const bool fast_root = root_nch == 2 && W <= 32 && (size_t)p->nslices[g.root] * W * W * 8 <= 96 * 1024;
+  const int root_blocks = fast_root ? (PC + 127) / 128 : (PC * 32 + 255) / 256;
   double* big_partial = nullptr;
   if (do_sum) {
     const size_t needp = sizeof(double) * 2 * (size_t)n_chunks * root_blocks;
@@ -504,11 +660,20 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     big_partial = st.d_partial2;
   }
   auto M = [&](int v) { return msgs + (size_t)v * PC * W; };
+  const TgClass* gv = reinterpret_cast<const TgClass*>(p->tg_gv);
+  const int ngv = p->tg_ngv;
+  const int nseg = (PC + TSEG - 1) / TSEG;
   for (int64_t ck = 0; ck < n_chunks; ++ck) {
     const int64_t p0 = ck * PC;
     tree_digits_kernel<<<(PC + 255) / 256, 256, 0, s>>>(p->digits, src, p0, PC, n, slices, p->d_err);
-    tree_classify_kernel<<<n, 1024, 0, s>>>(slices, PC, g.nslices, lists, cls_off, tile_off);
-    *n_launches += 2;
+    *n_launches += 1;
+    if (ngv > 0) {
+      TTN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)ngv * TOFF, s));
+      tree_count_kernel<<<dim3(nseg, ngv), 256, 0, s>>>(slices, PC, gv, counts);
+      tree_offsets_kernel<<<(ngv + 63) / 64, 64, 0, s>>>(gv, ngv, counts, cls_off, tile_off, cursor);
+      tree_scatter_kernel<<<dim3(nseg, ngv), 256, 0, s>>>(slices, PC, gv, cursor, lists);
+      *n_launches += 3;
+    }
     for (int oi = 0; oi < n; ++oi) {
       const int v = p->post[oi];
       const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
@@ -523,19 +688,37 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
         *n_launches += 1;
         continue;
       }
+      const int role = p->tg_role[v];
+      if (role == 1) continue; // absorbed into the merged run that ends higher up
       if (v == g.root) {
-        tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
-                                                     slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out,
-                                                     do_sum ? big_partial + 2 * ck * root_blocks : nullptr, do_sum, src);
+        double* part = do_sum ? big_partial + 2 * ck * root_blocks : nullptr;
+        if (fast_root) {
+          const size_t sm = (size_t)p->nslices[v] * W * W * 8;
+          if (W == 16) {
+            TTN_CUDA(cudaFuncSetAttribute(tree_root2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            tree_root2_kernel<16><<<root_blocks, 128, sm, s>>>(M(ca), M(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
+                                                               p->nslices[v], d_out, part, do_sum, src);
+          } else {
+            TTN_CUDA(cudaFuncSetAttribute(tree_root2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            tree_root2_kernel<32><<<root_blocks, 128, sm, s>>>(M(ca), M(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
+                                                               p->nslices[v], d_out, part, do_sum, src);
+          }
+        } else {
+          tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
+                                                       slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out, part, do_sum, src);
+        }
       } else if (nch == 0) {
         tree_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices + (size_t)v * PC, PC, blob, W, M(v));
       } else {
+        // role 2: a merged run of single-child vertices — one GEMM with the run's class matrices, fed by the message below it
         const double* Ma = nch == 2 ? M(ca) : nullptr;
-        const double* Mb = nch == 2 ? M(cb) : M(ca);
+        const double* Mb = role == 2 ? M(p->tg_in[v]) : (nch == 2 ? M(cb) : M(ca));
+        const double* fr = role == 2 ? p->tg_mblob + p->tg_mfrag_off[v] : blob;
+        const int nsl = role == 2 ? p->tg_mnsl[v] : p->nslices[v];
         int rc;
-        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
-        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
-        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * 9, tile_off + v * 9, blob, p->nslices[v], PC, s);
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
         if (rc) return rc;
       }
       *n_launches += 1;
@@ -551,6 +734,123 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   return TTN_OK;
 }
 
+// Evaluation plan: which vertices run as GEMMs, and which runs of single-child vertices are merged.  A run of k
+// consecutive single-child vertices (a tooth of a comb above its subtree table, the backbone of a chain-like tree)
+// acts on the message below it as ONE of 2^(bits) W x W matrices, bits = the slice bits of its members: the products
+// are formed here once (long double, rounded once) and the run costs one GEMM launch and 2 W^2 flops per point
+// instead of k of each — the tree kernel's version of the chain kernels' group merging (k_chain_mma.cu).
+static int build_tree_merge(ttn_plan* p, const ttn_desc* d) {
+  const int n = d->n_vertices;
+  const TreeGemmDev& g = p->tgemm;
+  const int W = g.W;
+  p->tg_role.assign(n, 0);
+  p->tg_in.assign(n, -1);
+  p->tg_mnsl.assign(n, 0);
+  p->tg_mfrag_off.assign(n, 0);
+  auto nchild = [&](int v) { return p->child_ptr[v + 1] - p->child_ptr[v]; };
+  auto tab_of = [&](int v) { return p->tg_tab_of.empty() ? -1 : p->tg_tab_of[v]; };
+  auto bits_of = [&](int v) {
+    int b = 0;
+    while ((1 << b) < p->nslices[v]) ++b;
+    return b;
+  };
+  auto mergeable = [&](int v) {
+    const int ns = p->nslices[v];
+    return v != d->root && nchild(v) == 1 && tab_of(v) == -1 && (ns & (ns - 1)) == 0;
+  };
+  const bool merge_on = !(getenv("TTN_TREE_MERGE") && atoi(getenv("TTN_TREE_MERGE")) == 0);
+  const double* T = reinterpret_cast<const double*>(d->tensors);
+  std::vector<double> mblob;
+  typedef long double ld;
+  for (int oi = 0; oi < n && merge_on; ++oi) { // post order: a run is met at its bottom member first
+    const int b0 = p->post[oi];
+    if (!mergeable(b0) || p->tg_role[b0] != 0) continue;
+    std::vector<int> mem{b0};
+    int bits = bits_of(b0);
+    for (int u = d->parent[b0]; u >= 0 && mergeable(u) && (int)mem.size() < 4 && bits + bits_of(u) <= 4; u = d->parent[u]) {
+      mem.push_back(u);
+      bits += bits_of(u);
+    }
+    if (mem.size() < 2) continue;
+    const int top = mem.back(), ncls = 1 << bits;
+    const int in_v = p->child[p->child_ptr[b0]];
+    // class matrices: row vector (child dim of the bottom member) x E_m0[s0] x E_m1[s1] ... (parent dim of the top)
+    std::vector<double> F((size_t)ncls * W * W, 0.0);
+    for (int c = 0; c < ncls; ++c) {
+      std::vector<ld> cur((size_t)W * W, 0.0L);
+      int rows = d->link_dim[in_v], cols = rows;
+      for (int i = 0; i < rows; ++i) cur[(size_t)i * W + i] = 1.0L;
+      int shift = 0;
+      for (int m : mem) {
+        const int bm = bits_of(m), sm = (c >> shift) & ((1 << bm) - 1);
+        shift += bm;
+        const int ca = cols, pd = d->link_dim[m];
+        const double* Tm = T + d->tensor_ptr[m] + (size_t)sm * ca * pd;
+        std::vector<ld> nxt((size_t)W * W, 0.0L);
+        for (int i = 0; i < rows; ++i)
+          for (int k = 0; k < ca; ++k) {
+            const ld a = cur[(size_t)i * W + k];
+            if (a == 0.0L) continue;
+            for (int q = 0; q < pd; ++q) nxt[(size_t)i * W + q] += a * (ld)Tm[(size_t)k * pd + q];
+          }
+        cur.swap(nxt);
+        cols = pd;
+      }
+      double* Fs = F.data() + (size_t)c * W * W;
+      for (int kb = 0; kb < W / 4; ++kb)
+        for (int nb = 0; nb < W / 8; ++nb)
+          for (int ln = 0; ln < 32; ++ln)
+            Fs[((size_t)kb * (W / 8) + nb) * 32 + ln] = (double)cur[(size_t)(4 * kb + (ln & 3)) * W + 8 * nb + (ln >> 2)];
+    }
+    for (size_t i = 0; i + 1 < mem.size(); ++i) p->tg_role[mem[i]] = 1;
+    p->tg_role[top] = 2;
+    p->tg_in[top] = in_v;
+    p->tg_mnsl[top] = ncls;
+    p->tg_mfrag_off[top] = (int64_t)mblob.size();
+    mblob.insert(mblob.end(), F.begin(), F.end());
+    for (int m : mem) p->tgemm_flops_exec -= 2.0 * d->link_dim[p->child[p->child_ptr[m]]] * d->link_dim[m];
+    p->tgemm_flops_exec += 2.0 * d->link_dim[in_v] * d->link_dim[top];
+  }
+  if (!mblob.empty()) {
+    TTN_CUDA(cudaMalloc(&p->tg_mblob, mblob.size() * 8));
+    p->allocs.push_back(p->tg_mblob);
+    TTN_CUDA(cudaMemcpy(p->tg_mblob, mblob.data(), mblob.size() * 8, cudaMemcpyHostToDevice));
+  }
+  // the vertices that run as GEMMs (row lists needed): merged tops with their members, other inner vertices as is
+  std::vector<TgClass> gv;
+  for (int v = 0; v < n; ++v) {
+    if (v == d->root || nchild(v) == 0 || tab_of(v) != -1 || p->tg_role[v] == 1) continue;
+    TgClass c{};
+    c.v = v;
+    if (p->tg_role[v] == 2) {
+      std::vector<int> mem; // walk down from the top to the bottom member
+      for (int u = v; u != p->tg_in[v]; u = p->child[p->child_ptr[u]]) mem.push_back(u);
+      std::reverse(mem.begin(), mem.end());
+      int shift = 0;
+      for (int m : mem) {
+        c.mem_v[c.n_mem] = m;
+        c.mem_shift[c.n_mem] = shift;
+        c.n_mem++;
+        shift += bits_of(m);
+      }
+      c.nsl = p->tg_mnsl[v];
+    } else {
+      c.nsl = p->nslices[v];
+      c.n_mem = 1;
+      c.mem_v[0] = v;
+      c.mem_shift[0] = 0;
+    }
+    gv.push_back(c);
+  }
+  p->tg_ngv = (int)gv.size();
+  if (!gv.empty()) {
+    TTN_CUDA(cudaMalloc(&p->tg_gv, gv.size() * sizeof(TgClass)));
+    p->allocs.push_back(p->tg_gv);
+    TTN_CUDA(cudaMemcpy(p->tg_gv, gv.data(), gv.size() * sizeof(TgClass), cudaMemcpyHostToDevice));
+  }
+  return TTN_OK;
+}
+
 // Subtree message tables.  sub_bits(v) = sum of log2(nslices) over v's subtree; every non-root vertex
 // whose subtree has >= 2 vertices, only power-of-two slice counts and sub_bits <= the budget (2^bits
 // rows of W doubles <= 32 MB, bits <= 16; TTN_TREE_TABLE_BITS overrides, 0 disables) and whose parent
@@ -561,7 +861,7 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
   const int n = d->n_vertices;
   const TreeGemmDev& g = p->tgemm;
   const int W = g.W;
-  int budget = 16;
+  int budget = 18; // W = 16: 2^18 rows, W = 32: 2^17, W = 64: 2^16 — 32 MB per table
   while (budget > 0 && ((size_t)1 << budget) * W * 8 > ((size_t)32 << 20)) --budget;
   if (const char* e = getenv("TTN_TREE_TABLE_BITS")) budget = std::min(atoi(e), 20);
   p->tg_tab_of.assign(n, -1);

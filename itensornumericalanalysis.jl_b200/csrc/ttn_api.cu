@@ -802,7 +802,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     opts->kernel_ms = total;
     opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? p->cmma_flops_exec
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
-                            : (kernel == TTN_KERNEL_TREE && !p->tg_tab.empty()) ? p->tgemm_flops_exec
+                            : kernel == TTN_KERNEL_TREE ? p->tgemm_flops_exec
                             : kernel == TTN_KERNEL_TABLE ? p->ctab_flops_exec
                                                                              : p->info.flops_per_point) *
                            (double)npts;
@@ -1203,12 +1203,12 @@ int ttn_debug_table_image(const ttn_desc* desc, int32_t budget_kb, int32_t* meta
  * fused K1 really use (team-sorted DMMA kernel: run fast path floor(x 2^L); table kernel: 32-bit saturating
  * conversion, bit-deposit network).  One launch of `kernel` (TTN_KERNEL_DMMA / TTN_KERNEL_TABLE) over npts AoS host
  * points; words_out[2p], [2p+1] = the 128-bit stream of point p; site_bit[s] = stream bit of site index s of the
- * description (its digit = that bit).  tests/test_gpu_round2.py compares these integers with the CPU greedy loop. */
+
+ * description (its digit = the field of ceil(log2(dim)) bits starting there).  tests/test_gpu_round2.py compares these integers with the CPU greedy loop. */
 int ttn_debug_slice_stream(ttn_plan* plan, const double* coords, int64_t npts, int32_t kernel, uint64_t* words_out,
                            int32_t* site_bit) {
   if (!plan || !coords || !words_out || !site_bit || npts <= 0) return fail(TTN_ERR_INVALID, "null / empty argument");
   if (!plan->replicas.empty()) plan = plan->replicas[0];
-  if (!plan->all_base2) return fail(TTN_ERR_UNSUPPORTED, "slice-stream dump: binary site indices only");
   const DigitTable* dt = nullptr;
   if (kernel == TTN_KERNEL_DMMA && plan->cmma_ok && chain_team_applicable(plan)) dt = &plan->digits_mma;
   if (kernel == TTN_KERNEL_TABLE && plan->ctab_ok) dt = &plan->digits_tab;

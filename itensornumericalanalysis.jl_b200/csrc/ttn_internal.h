@@ -104,6 +104,7 @@ struct ChainMmaDev {
   int32_t root_pos; // position of the root in the packed slice stream (after identity padding)
   int32_t merged;   // k > 0: k vertices pre-contracted into one stream position (build_chain_mma)
   int32_t leaf_bits, root_bits; // stream bits of the leaf / root group (deep tables: up to 21)
+  int32_t k1_generic;           // 1: some site index is not binary -> K1 runs the tabulated greedy loop (base 3 / 4)
   // per coordinate slot: "run" fast path of K1 (see build_chain_mma): L == 0 -> use the table loop
   int32_t run_L[TTN_MAX_COORDS];     // number of binary digits
   int32_t run_plow[TTN_MAX_COORDS];  // lowest stream position of the run
@@ -138,6 +139,7 @@ struct ChainTabDev {
   int32_t H;             // padded bond dimension (a complex entry counts once): 1, 2 or 4
   int32_t cplx;
   int32_t rep;           // 1: chi = 1 tables replicated per lane (one 128-byte line per entry; conflict-free)
+  int32_t k1_generic;    // 1: some site index is not binary (base 3 / 4): tabulated greedy loop in K1
   int32_t total_doubles; // image size (even)
   int32_t gbits[kTabMaxGroups]; // stream bits consumed by the group (<= 16)
   int32_t goff[kTabMaxGroups];  // offset of the group's table in the image, in doubles (even)
@@ -233,6 +235,13 @@ struct ttn_plan {
   std::vector<double*> tg_tab;
   std::vector<int32_t*> tg_tab_vs;
   double tgemm_flops_exec = 0.0;
+  // evaluation plan of the tree kernel (build_tree_merge): runs of single-child vertices merged into one GEMM
+  std::vector<int32_t> tg_role;       // per vertex: 0 = as is, 1 = absorbed into a merged run, 2 = top of a merged run
+  std::vector<int32_t> tg_in, tg_mnsl; // merged top: vertex whose message feeds the run; number of classes
+  std::vector<int64_t> tg_mfrag_off;  // merged top: offset of its class matrices in tg_mblob
+  double* tg_mblob = nullptr;         // (in allocs)
+  void* tg_gv = nullptr;              // device array of TgClass: the vertices that run as GEMMs (in allocs)
+  int tg_ngv = 0;
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int v6_teams = 3;        // teams per CTA of the team-sorted kernel (TTN_MMA_V6 at ttn_plan_create; 0 = ring kernels)

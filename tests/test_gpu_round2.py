@@ -132,7 +132,8 @@ def _slice_stream_digits(plan, coords, kernel):
                    site_bit.ctypes.data_as(C.c_void_p)))
     out = np.empty((npts, ns), dtype=np.uint8)
     for s_, b in enumerate(site_bit):
-        out[:, s_] = (words[:, b // 64] >> np.uint64(b % 64)) & np.uint64(1)
+        mask = 1 if plan.packed.site_dim[s_] <= 2 else 3      # base 3 / 4 digits sit in 2-bit fields
+        out[:, s_] = (words[:, b // 64] >> np.uint64(b % 64)) & np.uint64(mask)
     return out
 
 
@@ -180,6 +181,98 @@ def test_fused_k1_digits_are_bit_exact(which):
     assert bad.size == 0, (which, bad[:5], pts[bad[:5, 0]])
     # and the separate digits kernel agrees (ttn_digits)
     assert (plan.digits_host(pts) == ref).all()
+
+
+# ------------------------------------------------------------------ base 3 / base 4 digits
+
+def _base_b_networks():
+    out = {}
+    for base in (3, 4):
+        s = t.continuous_siteinds(t.named_grid((30, 1)), base=base)
+        out[f"base{base}_mps30_chi16"] = (t.rand_itn(s, link_space=16, rng=base, normalise=True), _capi.TTN_KERNEL_DMMA)
+        s = t.continuous_siteinds(t.named_grid((24, 1)), base=base, map_dimension=2)
+        out[f"base{base}_mps2d_chi32"] = (t.rand_itn(s, link_space=32, rng=10 + base, normalise=True), _capi.TTN_KERNEL_DMMA)
+        out[f"base{base}_mps2d_chi2"] = (t.rand_itn(s, link_space=2, rng=20 + base, normalise=True), _capi.TTN_KERNEL_TABLE)
+        s = t.continuous_siteinds(t.named_grid((20, 1)), base=base)
+        out[f"base{base}_exp_chi1"] = (t.exp_itn(s, k=0.7, a=0.2, c=1.1, dim=1), _capi.TTN_KERNEL_TABLE)
+        out[f"base{base}_cos_cplx_chi2"] = (t.cos_itn(s, k=2.5, a=0.1, c=0.9, dim=1), _capi.TTN_KERNEL_TABLE)
+    s = t.complex_continuous_siteinds(t.named_grid((16, 1)), [[(i, 1) for i in range(1, 17, 2)]],
+                                      [[(i, 1) for i in range(2, 17, 2)]], base=3)
+    out["base3_cplx_alt_chi8"] = (t.rand_itn(s, link_space=8, rng=31, eltype=complex, normalise=True), _capi.TTN_KERNEL_DMMA)
+    return out
+
+
+@pytest.mark.parametrize("which", list(_base_b_networks()))
+def test_base3_base4_fast_paths(which):
+    """test/test_realitensorfunction.jl:89-104, test_complexitensorfunction.jl:91-110 use base-3 digits.  Chains with
+    ONE base-3 / base-4 site index per vertex run on the merged team-sorted DMMA kernel (2-bit fields, 16 classes per
+    round) and, at chi <= 4, on the table kernel; K1 is the tabulated greedy loop with the caller's thresholds
+    (float(3)^-k is inexact: only the threshold table is bit-exact).  Digits are compared as integers through the
+    slice-stream dump, values against the 80-bit oracle on random points plus every threshold and its neighbours."""
+    f, kernel = _base_b_networks()[which]
+    plan = f.plan()
+    packed = plan.packed
+    assert plan.info()["auto_kernel"] == kernel, plan.info()
+    nc = packed.n_coords
+    rng = np.random.default_rng(5)
+    thr = np.unique(np.asarray(packed.thr))
+    thr = thr[thr > 0]
+    edge = np.concatenate([thr, np.nextafter(thr, 0), np.nextafter(thr, 1), 2 * thr[thr < 0.5], [0.0, 1.0, 1.5, 1 - 2.0 ** -53]])
+    pts = np.concatenate([rng.random((20_000, nc)), np.stack([np.roll(edge, 5 * c) for c in range(nc)], axis=1)])
+    ref_digits = orc.digits(packed, pts)
+    assert (_slice_stream_digits(plan, pts, kernel) == ref_digits).all()
+    assert (plan.digits_host(pts) == ref_digits).all()
+    got, o = plan.evaluate_host(pts)
+    assert o.kernel_used == kernel
+    ref = orc.evaluate(packed, pts, orc.ORACLE_LD, nthreads=orc.max_threads())
+    err = orc.error_metric(got, ref)
+    assert np.quantile(err, 0.999) < TOL and err.max() < 5e-12, (which, err.max())
+    # index-setting mode and the fused functionals go through the same K1 branch
+    iv, _ = plan.evaluate_indices_host(ref_digits)
+    assert (iv == got).all()
+    _, osum = plan.evaluate_host(pts, reduce_sum="sum", want_values=False)
+    assert abs(complex(osum.sum_out[0], osum.sum_out[1]) - got.sum()) <= 1e-11 * np.abs(got).sum()
+
+
+# ------------------------------------------------------------------ narrow trees: merged runs, multi-block classification
+
+def _comb(nx, ny, chi, rng, two_site=False):
+    g = t.named_comb_tree((nx, ny))
+    dv = [[(j, i) for i in range(1, ny + 1)] for j in range(1, nx + 1)]
+    s = t.continuous_siteinds(g, dv)
+    return t.rand_itn(s, link_space=chi, rng=rng, normalise=True)
+
+
+@pytest.mark.parametrize("which", ["comb3x20_chi16", "comb3x22_chi8", "comb4x9_chi24", "comb3x7_chi40"])
+def test_tree_kernel_merged_runs(which, monkeypatch):
+    """Comb trees (examples/construct_multi_dimensional_function.jl:15-22 topology) through the per-vertex GEMM tree
+    kernel: subtree tables at the tooth ends, the single-child vertices above them merged into one GEMM per run
+    (build_tree_merge), multi-block classification, thread-per-point root.  Against the 80-bit oracle, and against the
+    same kernel with merging off."""
+    nx, ny, chi = {"comb3x20_chi16": (3, 20, 16), "comb3x22_chi8": (3, 22, 8), "comb4x9_chi24": (4, 9, 24),
+                   "comb3x7_chi40": (3, 7, 40)}[which]
+    f = _comb(nx, ny, chi, rng=chi + ny)
+    plan = f.plan()
+    assert plan.info()["auto_kernel"] == _capi.TTN_KERNEL_TREE
+    rng = np.random.default_rng(ny)
+    pts = cases.edge_points(ny, nx, rng, 700_000 if which == "comb3x20_chi16" else 30_000)   # several chunks for the first
+    got, o = plan.evaluate_host(pts, reduce_sum="sum", want_values=True)
+    assert o.kernel_used == _capi.TTN_KERNEL_TREE
+    assert o.flops_executed < plan.info()["flops_per_point"] * len(pts)      # tables and merged runs remove work
+    sub = np.concatenate([np.arange(20_000), np.arange(len(pts) - 15, len(pts))])
+    ref = orc.evaluate(plan.packed, pts[sub], orc.ORACLE_LD, nthreads=orc.max_threads())
+    err = orc.error_metric(got[sub], ref)
+    assert np.quantile(err, 0.999) < TOL and err.max() < 5e-12, (which, err.max())
+    assert abs(o.sum_out[0] - got.sum()) <= 1e-11 * np.abs(got).sum()
+    f.invalidate_plans()
+    monkeypatch.setenv("TTN_TREE_MERGE", "0")
+    monkeypatch.setenv("TTN_TREE_TABLE_BITS", "0")
+    m = min(len(pts), 50_000)
+    plain, o0 = f.plan().evaluate_host(pts[:m])
+    assert o0.flops_executed == f.plan().info()["flops_per_point"] * m
+    scale = np.maximum(np.abs(plain), 1e-3 * np.sqrt(np.mean(plain ** 2)))
+    assert (np.abs(plain - got[:m]) / scale).max() < 1e-11
+    f.invalidate_plans()
 
 
 # ------------------------------------------------------------------ pageable host buffers
