@@ -29,6 +29,45 @@ struct __align__(16) Digit2 {
   uint32_t wv;   // (site << 16) | (word << 8) | stride
 };
 
+// base 3 / 4 digit entry for the branch-free form of the greedy loop (32 bytes).  With strictly increasing
+// thresholds thr[1] < thr[2] < thr[3] the loop "largest v with x >= thr[v]" (abstractindexmap.jl:121-138) picks
+// v = (x >= thr[1]) + (x >= thr[2]) + (x >= thr[3]); thresholds a base does not have are +inf.
+struct __align__(16) Digit4 {
+  double t1, t2, t3;
+  uint32_t sh;   // shift inside the word
+  uint32_t wv;   // (base << 24) | (site << 16) | (word << 8) | stride
+};
+__device__ __forceinline__ Digit4 make_digit4(const DigitTable& dg, int i) {
+  const DigitEntry e = dg.entries[i];
+  Digit4 d4;
+  d4.t1 = e.base > 1 ? dg.thr[e.thr_off + 1] : __longlong_as_double(0x7ff0000000000000ll);
+  d4.t2 = e.base > 2 ? dg.thr[e.thr_off + 2] : __longlong_as_double(0x7ff0000000000000ll);
+  d4.t3 = e.base > 3 ? dg.thr[e.thr_off + 3] : __longlong_as_double(0x7ff0000000000000ll);
+  d4.sh = (uint32_t)e.shift;
+  d4.wv = ((uint32_t)e.base << 24) | ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+  return d4;
+}
+template <int NP>
+__device__ __forceinline__ void k1_digit4(const Digit4 e, const DigitTable& dg, const CoordSource& src, int64_t p0, int64_t step,
+                                          double (&x)[NP], uint64_t (&w0)[NP], uint64_t (&w1)[NP], int* err) {
+  const uint32_t stride = e.wv & 0xffu;
+  const bool hi = ((e.wv >> 8) & 0xffu) != 0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    uint32_t v;
+    if (src.digits) {
+      v = (uint32_t)given_digit(src, p0 + k * step, dg.n_sites, (int)((e.wv >> 16) & 0xffu), (int)(e.wv >> 24), err);
+    } else {
+      const bool g1 = x[k] >= e.t1, g2 = x[k] >= e.t2, g3 = x[k] >= e.t3;
+      v = (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3;
+      x[k] = __dsub_rn(x[k], g3 ? e.t3 : (g2 ? e.t2 : (g1 ? e.t1 : 0.0)));
+    }
+    const uint64_t bb = (uint64_t)(v * stride) << e.sh;
+    if (hi) w1[k] += bb;
+    else w0[k] += bb;
+  }
+}
+
 constexpr int kFeMaxSites = 160; // static shared-memory copies of the digit tables (within the 12 KB the
 constexpr int kFeMaxThr = 640;   // launchers reserve); larger networks take the chain / generic kernels
 
@@ -59,6 +98,19 @@ __device__ __forceinline__ int greedy_digit_smem(double& x, const double* thr, i
   }
   x = __dsub_rn(x, t);
   return v;
+}
+
+// K1 mode of the kernels with a fused K1 for a description with non-binary site indices: 1 = branch-free Digit4
+// form (every site index has dimension <= 4 and strictly increasing thresholds), 2 = tabulated greedy loop on
+// the global-memory digit table (any base), 0 = all binary.
+inline int k1_generic_mode(const ttn_desc* d) {
+  bool binary = true, fast = true;
+  for (int s = 0; s < d->n_sites; ++s) {
+    binary = binary && d->site_dim[s] == 2;
+    fast = fast && d->site_dim[s] <= 4;
+    for (int v = 1; v < d->site_dim[s]; ++v) fast = fast && d->thr[d->thr_ptr[s] + v] > d->thr[d->thr_ptr[s] + v - 1];
+  }
+  return binary ? 0 : (fast ? 1 : 2);
 }
 
 } // namespace ttn

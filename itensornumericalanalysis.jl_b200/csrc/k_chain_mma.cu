@@ -542,7 +542,7 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     c.n_steps = n_steps_p;
   }
   c.merged = merge ? kmerge : 0;
-  c.k1_generic = p->all_base2 ? 0 : 1;
+  c.k1_generic = k1_generic_mode(d);
   c.leaf_bits = merge ? bits0 * kL : bits0; // stream bits the leaf / root group consumes
   c.root_bits = merge ? bits0 * kR : bits0;
   c.nsl = NSL;

@@ -97,12 +97,15 @@ __global__ void __launch_bounds__(NT, MINB)
   constexpr int E = CPLX ? 2 : 1, HE = H * E, MM = H * H * E;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NT / 32];
-  __shared__ Digit2 s_d2[kFeMaxSites];
+  __shared__ __align__(16) unsigned char s_dig[kFeMaxSites * sizeof(Digit4)]; // Digit2[] (binary) or Digit4[] (base 3 / 4)
+  Digit2* s_d2 = reinterpret_cast<Digit2*>(s_dig);
+  Digit4* s_d4 = reinterpret_cast<Digit4*>(s_dig);
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
 
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
-  for (int i = tid; i < dg.n_sites; i += NT) {
+  for (int i = tid; i < (ct.k1_generic == 1 ? dg.n_sites : 0); i += NT) s_d4[i] = make_digit4(dg, i);
+  for (int i = tid; i < (ct.k1_generic == 0 ? dg.n_sites : 0); i += NT) {
     const DigitEntry e = dg.entries[i];
     Digit2 d2;
     d2.thr1 = dg.thr[e.thr_off + 1];
@@ -199,6 +202,8 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
         for (int k = 0; k < PPT; ++k) w1[k] += q[k] << (plow - 64);
       }
+    } else if (ct.k1_generic == 1) {
+      for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_digit4<PPT>(s_d4[e_i], dg, src, p0, NT, x, w0, w1, err);
     } else if (ct.k1_generic) {
       for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_generic_site<PPT>(dg, src, e_i, p0, NT, x, w0, w1, err);
     } else {
@@ -723,7 +728,7 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   c.H = im.H;
   c.cplx = im.cplx;
   c.rep = im.rep;
-  c.k1_generic = p->all_base2 ? 0 : 1;
+  c.k1_generic = k1_generic_mode(d);
   c.total_doubles = (int)im.image.size();
   for (int g = 0; g < c.n_groups; ++g) {
     c.gbits[g] = im.gbits[g];

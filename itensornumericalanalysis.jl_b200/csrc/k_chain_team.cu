@@ -76,14 +76,17 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NTEAM * TW];
-  __shared__ Digit2 s_d2[kFeMaxSites];
+  __shared__ __align__(16) unsigned char s_dig[kFeMaxSites * sizeof(Digit4)]; // Digit2[] (binary) or Digit4[] (base 3 / 4)
+  Digit2* s_d2 = reinterpret_cast<Digit2*>(s_dig);
+  Digit4* s_d4 = reinterpret_cast<Digit4*>(s_dig);
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int team = tid / (TW * 32), warp = (tid >> 5) % TW;
   const int g = lane >> 2, tq = lane & 3;
   for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
-  for (int i = tid; i < dg.n_sites; i += NT) {
+  for (int i = tid; i < (ch.k1_generic == 1 ? dg.n_sites : 0); i += NT) s_d4[i] = make_digit4(dg, i);
+  for (int i = tid; i < (ch.k1_generic == 0 ? dg.n_sites : 0); i += NT) {
     const DigitEntry e = dg.entries[i];
     Digit2 d2;
     d2.thr1 = dg.thr[e.thr_off + 1];
@@ -170,6 +173,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
             w1[k] += q << (plow - 64);
           }
         }
+      } else if (ch.k1_generic == 1) {
+        for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_digit4<PPL>(s_d4[e_i], dg, src, p0 + lane, 32, x, w0, w1, err);
       } else if (ch.k1_generic) {
         for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_generic_site<PPL>(dg, src, e_i, p0 + lane, 32, x, w0, w1, err);
       } else {

@@ -248,7 +248,8 @@ template <int W>
 __global__ void __launch_bounds__(128) tree_root2_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb,
                                                          const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
                                                          const double* __restrict__ T, int nsl, double* __restrict__ out,
-                                                         double* __restrict__ partial, int do_sum, CoordSource src) {
+                                                         double* __restrict__ partial, int do_sum, CoordSource src,
+                                                         const uint32_t* __restrict__ ta, const uint32_t* __restrict__ tb) {
   extern __shared__ __align__(16) double sT[]; // [nsl][W][W]
   for (int i = threadIdx.x; i < nsl * W * W; i += 128) sT[i] = T[i];
   __syncthreads();
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(128) tree_root2_kernel(const double* __restric
   double v = 0.0;
   if (live) {
     double mb[W];
-    const double2* rb = reinterpret_cast<const double2*>(Mb + (size_t)i * W);
+    const double2* rb = reinterpret_cast<const double2*>(Mb + (size_t)(tb ? tb[i] : (uint32_t)i) * W);
 #pragma unroll
     for (int j = 0; j < W / 2; ++j) {
       const double2 t = rb[j];
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(128) tree_root2_kernel(const double* __restric
       mb[2 * j + 1] = t.y;
     }
     const double* Td = sT + (size_t)sl[i] * W * W;
-    const double* ra = Ma + (size_t)i * W;
+    const double* ra = Ma + (size_t)(ta ? ta[i] : (uint32_t)i) * W;
 #pragma unroll 4
     for (int a = 0; a < W; ++a) {
       double s = 0.0;
@@ -305,7 +306,11 @@ template <int W, int NCH>
 __global__ void __launch_bounds__(256, 1)
     tree_vertex_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb, double* __restrict__ Mout,
                        const uint32_t* __restrict__ list, const int* __restrict__ cls_off,
-                       const int* __restrict__ tile_off, const double* __restrict__ frags, int nsl) {
+                       const int* __restrict__ tile_off, const double* __restrict__ frags, int nsl,
+                       const uint32_t* __restrict__ ta, const uint32_t* __restrict__ tb) {
+  // ta / tb != nullptr: child a / b is a TABULATED subtree — Ma / Mb is its message table and ta / tb holds the
+  // table row of every point of the chunk (tree_tabidx_kernel): the rows are gathered straight from the table
+  // instead of being copied into a message buffer first
   constexpr int RS = W + 4;            // row stride (doubles) of the child blocks in shared memory
   constexpr int NT = W / 16;           // 8-column tiles per warp (warp tile 32 x W/2)
   constexpr int KTOT = (NCH == 2) ? W * W : W;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(256, 1)
   double* Sa = reinterpret_cast<double*>(smem);          // [TBM][RS]  (NCH == 2 only)
   double* Sb = Sa + (NCH == 2 ? TBM * RS : 0);           // [TBM][RS]  second child, or the only child
   double* Bs = Sb + TBM * RS;                            // [TSTAGES][B_STAGE_D]
-  __shared__ uint32_t rowid[TBM];
+  __shared__ uint32_t rowid[TBM], rowa[TBM], rowb[TBM];
 
   const int tile = blockIdx.x;
   int c = -1;
@@ -326,7 +331,12 @@ __global__ void __launch_bounds__(256, 1)
   const int mblk = tile - tile_off[c];
   const int row0 = cls_off[c] + mblk * TBM, row_end = cls_off[c + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < TBM) rowid[tid] = list[min(row0 + tid, row_end - 1)];
+  if (tid < TBM) {
+    const uint32_t r = list[min(row0 + tid, row_end - 1)];
+    rowid[tid] = r;
+    rowb[tid] = tb ? tb[r] : r;
+    if (NCH == 2) rowa[tid] = ta ? ta[r] : r;
+  }
   __syncthreads();
 
   const double* E = frags + (size_t)c * KTOT * W;
@@ -344,8 +354,8 @@ __global__ void __launch_bounds__(256, 1)
     constexpr int CPR = W / 2; // 16-byte chunks per row
     for (int ch = tid; ch < TBM * CPR; ch += 256) {
       const int r = ch / CPR, cc = ch % CPR;
-      t_cp_async16(smem_u32(Sb) + (uint32_t)(r * RS + cc * 2) * 8u, Mb + (size_t)rowid[r] * W + cc * 2);
-      if (NCH == 2) t_cp_async16(smem_u32(Sa) + (uint32_t)(r * RS + cc * 2) * 8u, Ma + (size_t)rowid[r] * W + cc * 2);
+      t_cp_async16(smem_u32(Sb) + (uint32_t)(r * RS + cc * 2) * 8u, Mb + (size_t)rowb[r] * W + cc * 2);
+      if (NCH == 2) t_cp_async16(smem_u32(Sa) + (uint32_t)(r * RS + cc * 2) * 8u, Ma + (size_t)rowa[r] * W + cc * 2);
     }
     load_B(0, 0);
     t_cp_async_commit();
@@ -495,6 +505,21 @@ __global__ void tree_table_kernel(const uint8_t* __restrict__ slices, int pc, co
   reinterpret_cast<double2*>(M)[idx] = __ldg(reinterpret_cast<const double2*>(table + (size_t)t * W) + j);
 }
 
+// table row of every point of the chunk, for all tables of the plan at once: grid (chunk / 256, tables)
+struct TgTabRef {
+  const int32_t* vs;
+  int32_t ns;
+};
+__global__ void tree_tabidx_kernel(const uint8_t* __restrict__ slices, int pc, const TgTabRef* __restrict__ tabs,
+                                   uint32_t* __restrict__ tabidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pc) return;
+  const TgTabRef tr = tabs[blockIdx.y];
+  uint32_t t = 0;
+  for (int q = 0; q < tr.ns; ++q) t |= (uint32_t)slices[(size_t)tr.vs[3 * q] * pc + i] << tr.vs[3 * q + 1];
+  tabidx[(size_t)blockIdx.y * pc + i] = t;
+}
+
 // ------------------------------------------------------------------------------ host side
 
 static int build_tree_tables(ttn_plan* p, const ttn_desc* d);
@@ -587,21 +612,23 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
 
 template <int W, int NCH>
 static int launch_vertex(const double* Ma, const double* Mb, double* Mout, const uint32_t* list, const int* cls_off,
-                         const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s) {
+                         const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s,
+                         const uint32_t* ta = nullptr, const uint32_t* tb = nullptr) {
   constexpr size_t smem = ((size_t)(NCH == 2 ? 2 : 1) * TBM * (W + 4) + (size_t)TSTAGES * TBK * W) * 8;
   auto kern = tree_vertex_kernel<W, NCH>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = pc / TBM + nsl;
-  kern<<<grid, 256, smem, s>>>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl);
+  kern<<<grid, 256, smem, s>>>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, ta, tb);
   TTN_CUDA(cudaGetLastError());
   return TTN_OK;
 }
 
 template <int W>
 static int launch_vertex_w(int nch, const double* Ma, const double* Mb, double* Mout, const uint32_t* list,
-                           const int* cls_off, const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s) {
-  return nch == 2 ? launch_vertex<W, 2>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s)
-                  : launch_vertex<W, 1>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s);
+                           const int* cls_off, const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s,
+                           const uint32_t* ta = nullptr, const uint32_t* tb = nullptr) {
+  return nch == 2 ? launch_vertex<W, 2>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s, ta, tb)
+                  : launch_vertex<W, 1>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s, ta, tb);
 }
 
 int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_out, double* d_partial,
@@ -626,7 +653,9 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   const size_t slices_b = ((size_t)n * PC + 255) / 256 * 256;
   const size_t lists_b = (size_t)n * PC * 4;
   const size_t offs_b = (size_t)n * TOFF * 4 * 4 + 256; // cls_off, tile_off, counts, cursor
-  const size_t need = (size_t)n * msg_b + slices_b + lists_b + offs_b;
+  const int n_tab = (int)p->tg_tab.size();
+  const size_t tabidx_b = (size_t)n_tab * PC * 4;
+  const size_t need = (size_t)n * msg_b + slices_b + lists_b + offs_b + tabidx_b;
   if (st.gemm_bytes < need) {
     if (st.d_gemm) cudaFree(st.d_gemm);
     st.d_gemm = nullptr;
@@ -642,6 +671,7 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   int* tile_off = cls_off + (size_t)n * TOFF;
   int* counts = tile_off + (size_t)n * TOFF;
   int* cursor = counts + (size_t)n * TOFF;
+  uint32_t* tabidx = reinterpret_cast<uint32_t*>(base + (size_t)n * msg_b + slices_b + lists_b + offs_b);
   const int do_sum = d_partial != nullptr;
   const int64_t n_chunks = (src.npts + PC - 1) / PC;
   const int root_nch = p->child_ptr[g.root + 1] - p->child_ptr[g.root];
@@ -660,6 +690,13 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     big_partial = st.d_partial2;
   }
   auto M = [&](int v) { return msgs + (size_t)v * PC * W; };
+  // a tabulated child is read straight from its table through the per-point row index (no message copy), unless
+  // its consumer is the warp-per-point root kernel
+  auto tab_direct = [&](int c) {
+    return c >= 0 && !p->tg_tab_of.empty() && p->tg_tab_of[c] >= 0 && (p->parent[c] != g.root || fast_root);
+  };
+  auto msg_of = [&](int c) -> const double* { return tab_direct(c) ? p->tg_tab[p->tg_tab_of[c]] : M(c); };
+  auto idx_of = [&](int c) -> const uint32_t* { return tab_direct(c) ? tabidx + (size_t)p->tg_tab_of[c] * PC : nullptr; };
   const TgClass* gv = reinterpret_cast<const TgClass*>(p->tg_gv);
   const int ngv = p->tg_ngv;
   const int nseg = (PC + TSEG - 1) / TSEG;
@@ -667,6 +704,10 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
     const int64_t p0 = ck * PC;
     tree_digits_kernel<<<(PC + 255) / 256, 256, 0, s>>>(p->digits, src, p0, PC, n, slices, p->d_err);
     *n_launches += 1;
+    if (n_tab > 0) {
+      tree_tabidx_kernel<<<dim3((PC + 255) / 256, n_tab), 256, 0, s>>>(slices, PC, reinterpret_cast<const TgTabRef*>(p->tg_tabrefs), tabidx);
+      *n_launches += 1;
+    }
     if (ngv > 0) {
       TTN_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)ngv * TOFF, s));
       tree_count_kernel<<<dim3(nseg, ngv), 256, 0, s>>>(slices, PC, gv, counts);
@@ -683,9 +724,11 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
       const int tab = p->tg_tab_of.empty() ? -1 : p->tg_tab_of[v];
       if (tab == -2) continue; // inside a tabulated subtree
       if (tab >= 0) {
-        tree_table_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices, PC, p->tg_tab_vs[tab], p->tg_tab_ns[tab],
-                                                                                          p->tg_tab[tab], W, M(v));
-        *n_launches += 1;
+        if (!tab_direct(v)) {
+          tree_table_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices, PC, p->tg_tab_vs[tab], p->tg_tab_ns[tab],
+                                                                                            p->tg_tab[tab], W, M(v));
+          *n_launches += 1;
+        }
         continue;
       }
       const int role = p->tg_role[v];
@@ -696,12 +739,12 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
           const size_t sm = (size_t)p->nslices[v] * W * W * 8;
           if (W == 16) {
             TTN_CUDA(cudaFuncSetAttribute(tree_root2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            tree_root2_kernel<16><<<root_blocks, 128, sm, s>>>(M(ca), M(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
-                                                               p->nslices[v], d_out, part, do_sum, src);
+            tree_root2_kernel<16><<<root_blocks, 128, sm, s>>>(msg_of(ca), msg_of(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
+                                                               p->nslices[v], d_out, part, do_sum, src, idx_of(ca), idx_of(cb));
           } else {
             TTN_CUDA(cudaFuncSetAttribute(tree_root2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            tree_root2_kernel<32><<<root_blocks, 128, sm, s>>>(M(ca), M(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
-                                                               p->nslices[v], d_out, part, do_sum, src);
+            tree_root2_kernel<32><<<root_blocks, 128, sm, s>>>(msg_of(ca), msg_of(cb), slices + (size_t)v * PC, PC, p0, src.npts, blob,
+                                                               p->nslices[v], d_out, part, do_sum, src, idx_of(ca), idx_of(cb));
           }
         } else {
           tree_root_kernel<<<root_blocks, 256, 0, s>>>(nch, nch == 2 ? M(ca) : nullptr, nch == 2 ? M(cb) : (nch == 1 ? M(ca) : nullptr),
@@ -711,14 +754,17 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
         tree_leaf_kernel<<<(unsigned)(((int64_t)PC * (W / 2) + 255) / 256), 256, 0, s>>>(slices + (size_t)v * PC, PC, blob, W, M(v));
       } else {
         // role 2: a merged run of single-child vertices — one GEMM with the run's class matrices, fed by the message below it
-        const double* Ma = nch == 2 ? M(ca) : nullptr;
-        const double* Mb = role == 2 ? M(p->tg_in[v]) : (nch == 2 ? M(cb) : M(ca));
+        const int vb = role == 2 ? p->tg_in[v] : (nch == 2 ? cb : ca);
+        const double* Ma = nch == 2 ? msg_of(ca) : nullptr;
+        const uint32_t* ia = nch == 2 ? idx_of(ca) : nullptr;
+        const double* Mb = msg_of(vb);
+        const uint32_t* ib = idx_of(vb);
         const double* fr = role == 2 ? p->tg_mblob + p->tg_mfrag_off[v] : blob;
         const int nsl = role == 2 ? p->tg_mnsl[v] : p->nslices[v];
         int rc;
-        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
-        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
-        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s);
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
         if (rc) return rc;
       }
       *n_launches += 1;
@@ -841,6 +887,13 @@ static int build_tree_merge(ttn_plan* p, const ttn_desc* d) {
       c.mem_shift[0] = 0;
     }
     gv.push_back(c);
+  }
+  if (!p->tg_tab.empty()) {
+    std::vector<TgTabRef> refs(p->tg_tab.size());
+    for (size_t i = 0; i < refs.size(); ++i) refs[i] = TgTabRef{p->tg_tab_vs[i], p->tg_tab_ns[i]};
+    TTN_CUDA(cudaMalloc(&p->tg_tabrefs, refs.size() * sizeof(TgTabRef)));
+    p->allocs.push_back(p->tg_tabrefs);
+    TTN_CUDA(cudaMemcpy(p->tg_tabrefs, refs.data(), refs.size() * sizeof(TgTabRef), cudaMemcpyHostToDevice));
   }
   p->tg_ngv = (int)gv.size();
   if (!gv.empty()) {

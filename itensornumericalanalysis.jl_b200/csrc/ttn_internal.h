@@ -242,6 +242,7 @@ struct ttn_plan {
   double* tg_mblob = nullptr;         // (in allocs)
   void* tg_gv = nullptr;              // device array of TgClass: the vertices that run as GEMMs (in allocs)
   int tg_ngv = 0;
+  void* tg_tabrefs = nullptr;         // device array of (vs, ns) per subtree table (in allocs)
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int v6_teams = 3;        // teams per CTA of the team-sorted kernel (TTN_MMA_V6 at ttn_plan_create; 0 = ring kernels)
