@@ -381,8 +381,12 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
         lambda: plan.evaluate_device(b.x_dev.data_ptr(), npts, b.out_dev.data_ptr()))
     dt_e2e, _, _, o_e2e, clocks_e2e = timed(lambda: plan.evaluate_host(b.x_np, out=b.out_np)[1])
     # correctness guard inside the bench: device path == host path bit for bit on a slice
+    # (host-buffer calls of deep-table chains run the image without deep tables — PCIe-bound, k_chain_mma.cu "Light
+    # variant" — so the two paths may differ by the rounding of two FP64 evaluation orders)
     nchk = min(npts, 1 << 16) * nc_out
-    same = bool((b.out_dev[:nchk].cpu().numpy() == b.out_host[:nchk].numpy()).all())
+    dv, hv = b.out_dev[:nchk].cpu().numpy(), b.out_host[:nchk].numpy()
+    same = bool((dv == hv).all())
+    rel = float((np.abs(dv - hv) / np.maximum(np.abs(hv), 1e-3 * np.sqrt(np.mean(hv ** 2)) + 1e-300)).max())
 
     h2d, d2h = int(npts * ncol * 8), int(npts * nc_out * 8)
     e2e = {"value": npts * ctx.world / dt_e2e, "unit": "points/s", "h2d_bytes_per_step": h2d * ctx.world,
@@ -430,7 +434,7 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
         "data": "synthetic",
         "config": {"workload": desc, "points_per_gpu": npts, "kernel": _capi.KERNEL_NAMES[o_dev.kernel_used],
                    "flops_per_point": info["flops_per_point"], "l2": l2_note,
-                   "device_eq_host_bitwise": same, "rank0_numa_node": ctx.numa},
+                   "device_eq_host_bitwise": same, "device_vs_host_max_floored_rel": rel, "rank0_numa_node": ctx.numa},
         "kernel_ms_events": kernel_ms,
         "e2e": e2e,
         "gpu_launches": launches,

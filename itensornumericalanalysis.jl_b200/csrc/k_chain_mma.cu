@@ -603,6 +603,29 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       c.run_scale[cidx] = std::ldexp(1.0, L);
     }
   }
+  // Light variant for host-buffer calls: measured on config 2 (bench.py e2e, pinned buffers, 2 Mi-point chunks) the
+  // deep-table kernel — two random 128-byte row gathers per point at > 5 G points/s — slows the H2D / D2H copies
+  // that run beside it (e2e 2.79 G points/s for ANY table size, L2-resident ones included, against 3.19 = the
+  // copy ceiling with uniform groups): such calls are PCIe-bound, so they take the image without deep tables.
+  // Same packed stream (built only when both images pad the chain identically), same digits, same kernel instance.
+  p->cmma_light_ok = false;
+  const bool light_on = !(getenv("TTN_MMA_LIGHT") && atoi(getenv("TTN_MMA_LIGHT")) == 0); // 0: host-buffer calls run the deep image too
+  if (light_on && merge && (kL > kmerge || kR > kmerge)) {
+    const int n_steps_u = kmerge + kmerge + (n - 2 * kmerge + kmerge - 1) / kmerge * kmerge - 2;
+    if (n_steps_u == n_steps_p) {
+      ChainMmaDev& q = p->cmma_light;
+      q = c; // layout, run fast path, k1 mode are shared; (leaf, root, frags, rounds) replaced below
+      const ChainImage mu = merge_groups(im, CHI, nout, kmerge, bits0, kmerge, kmerge, kmerge, kmerge);
+      if ((rc = upload_chain_image(p, mu, CHI, q))) return rc;
+      q.n_steps = (int)mu.steps.size();
+      q.n_rounds = q.n_steps;
+      q.leaf_bits = q.root_bits = bits0 * kmerge;
+      double fm = 0.0;
+      for (int gI = 0; gI < q.n_steps; ++gI) fm += (cplx ? 8.0 : 2.0) * dim_in[kmerge - 1 + gI * kmerge] * dim_out[kmerge - 1 + gI * kmerge + kmerge - 1];
+      p->cmma_light_flops = fm + (cplx ? 8.0 : 2.0) * dim_in[n_steps_p - (kmerge - 1)];
+      p->cmma_light_ok = true;
+    }
+  }
   // both kernels keep the digit and threshold tables in static shared memory
   p->cmma_ok = p->digits.n_sites <= kFeMaxSites && d->n_sites <= kFeMaxSites && d->thr_ptr[d->n_sites] <= kFeMaxThr;
   return TTN_OK;

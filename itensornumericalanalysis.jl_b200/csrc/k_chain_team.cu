@@ -426,7 +426,7 @@ template <int CHI, int NCLS, int NTEAM, int PW_>
 static int launch_mma6_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                             cudaStream_t s) {
   using T6 = Team6<CHI, NCLS, PW_>;
-  const ChainMmaDev& c = p->cmma;
+  const ChainMmaDev& c = (src.pcie_bound && p->cmma_light_ok) ? p->cmma_light : p->cmma;
   const size_t smem = (size_t)NTEAM * T6::BYTES + (size_t)3 * NCLS * CHI * 8; // teams + leaf + root (re, im)
   auto kern = chain_mma6_kernel<CHI, NCLS, NTEAM, PW_>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

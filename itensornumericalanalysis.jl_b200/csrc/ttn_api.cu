@@ -415,8 +415,9 @@ class CopyPool {
 enum Space {
   SPACE_NONE = 0,
   SPACE_DIRECT,   // device memory of the plan's device (or managed): kernels use the pointer
-  SPACE_ASYNC,    // pinned host memory or another GPU's memory: cudaMemcpyAsync in place (PCIe / NVLink peer copy)
-  SPACE_PAGEABLE  // pageable host memory: through the pinned staging ring
+  SPACE_ASYNC,    // pinned host memory: cudaMemcpyAsync in place (PCIe)
+  SPACE_PAGEABLE, // pageable host memory: through the pinned staging ring
+  SPACE_PEER      // another GPU's memory: cudaMemcpyAsync in place (NVLink peer copy)
 };
 
 static Space classify(const void* ptr, int declared_mem, int device, int host_staging, size_t bytes) {
@@ -426,7 +427,7 @@ static Space classify(const void* ptr, int declared_mem, int device, int host_st
     cudaGetLastError();
     return declared_mem == TTN_MEM_DEVICE ? SPACE_DIRECT : SPACE_ASYNC;
   }
-  if (a.type == cudaMemoryTypeDevice) return a.device == device ? SPACE_DIRECT : SPACE_ASYNC;
+  if (a.type == cudaMemoryTypeDevice) return a.device == device ? SPACE_DIRECT : SPACE_PEER;
   if (a.type == cudaMemoryTypeManaged) return SPACE_DIRECT;
   if (a.type == cudaMemoryTypeHost) return SPACE_ASYNC;
   // unregistered host memory; small buffers are not worth the ring
@@ -613,10 +614,12 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   const size_t in_bytes = digits ? (size_t)npts * n_sites : sizeof(double) * (size_t)npts * std::max(base.n_coords, 1);
   Space sp_in = base.grid ? SPACE_NONE : classify(in_ptr, opts->coords_mem, p->device, opts->host_staging, in_bytes);
   // a sub-range of an SOA array is strided: only the staged copies can address it
-  if (sp_in == SPACE_DIRECT && !digits && base.layout == TTN_LAYOUT_SOA && soa_stride != npts) sp_in = SPACE_ASYNC;
-  const bool in_staged = sp_in == SPACE_ASYNC || sp_in == SPACE_PAGEABLE;
-  const bool out_staged = sp_out == SPACE_ASYNC || sp_out == SPACE_PAGEABLE;
-  const bool w_staged = sp_w == SPACE_ASYNC || sp_w == SPACE_PAGEABLE;
+  if (sp_in == SPACE_DIRECT && !digits && base.layout == TTN_LAYOUT_SOA && soa_stride != npts) sp_in = SPACE_PEER; // device-to-device copies
+  const bool in_staged = sp_in == SPACE_ASYNC || sp_in == SPACE_PAGEABLE || sp_in == SPACE_PEER;
+  const bool out_staged = sp_out == SPACE_ASYNC || sp_out == SPACE_PAGEABLE || sp_out == SPACE_PEER;
+  const bool w_staged = sp_w == SPACE_ASYNC || sp_w == SPACE_PAGEABLE || sp_w == SPACE_PEER;
+  // host buffers: the call is bound by the PCIe copies that run beside the kernels (launch_chain_team)
+  const bool pcie_bound = sp_in == SPACE_ASYNC || sp_in == SPACE_PAGEABLE || sp_out == SPACE_ASYNC || sp_out == SPACE_PAGEABLE;
   // the refine pass and its functionals need the values of a chunk in device memory
   const bool need_dout = out_staged || (refine && !out);
   const bool chunked = in_staged || need_dout || w_staged;
@@ -673,12 +676,13 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     src.npts = m;
     src.reduce_mode = opts->reduce_sum;
     src.weights = nullptr;
+    src.pcie_bound = pcie_bound ? 1 : 0;
     if (opts->reduce_sum == TTN_REDUCE_WEIGHTED) {
       if (sp_w == SPACE_PAGEABLE) {
         CopyPool::get().copy(st.h_weights, opts->weights + first, sizeof(double) * m);
         cudaMemcpyAsync(st.d_weights, st.h_weights, sizeof(double) * m, cudaMemcpyHostToDevice, st.s);
         src.weights = st.d_weights;
-      } else if (sp_w == SPACE_ASYNC) {
+      } else if (sp_w == SPACE_ASYNC || sp_w == SPACE_PEER) {
         cudaMemcpyAsync(st.d_weights, opts->weights + first, sizeof(double) * m, cudaMemcpyDefault, st.s);
         src.weights = st.d_weights;
       } else {
@@ -800,7 +804,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       if (ev[2 * ci] && ev[2 * ci + 1] && cudaEventElapsedTime(&ms, ev[2 * ci], ev[2 * ci + 1]) == cudaSuccess) total += ms;
     }
     opts->kernel_ms = total;
-    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? p->cmma_flops_exec
+    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? ((pcie_bound && p->cmma_light_ok && chain_team_applicable(p)) ? p->cmma_light_flops : p->cmma_flops_exec)
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
                             : kernel == TTN_KERNEL_TREE ? p->tgemm_flops_exec
                             : kernel == TTN_KERNEL_TABLE ? p->ctab_flops_exec

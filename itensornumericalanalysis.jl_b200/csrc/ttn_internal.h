@@ -58,6 +58,8 @@ struct CoordSource {
   const uint8_t* digits; // index-setting mode (ttn_evaluate_indices): digits[p * n_sites + site], else nullptr
   int32_t reduce_mode;   // TTN_REDUCE_* (what the kernels accumulate per point)
   const double* weights; // TTN_REDUCE_WEIGHTED: device pointer, one weight per point of this launch
+  int32_t pcie_bound;    // 1: this launch is one chunk of a host-buffer call (H2D / D2H copies run beside it): launchers may
+                         // pick the variant that leaves the memory system to the copy engines (launch_chain_team)
   unsigned long long* dbg_stream; // test hook (ttn_debug_slice_stream): the kernels with a FUSED K1 (team-sorted DMMA
                                   // kernel, table kernel) store the packed slice stream of point p — the digits they
                                   // really use — at dbg_stream[2p], [2p + 1]; nullptr in every product call
@@ -214,6 +216,9 @@ struct ttn_plan {
   bool chain_ok = false;
   ttn::ChainMmaDev cmma{};
   ttn::ChainMmaDev cmma_plain{}; // one vertex per position (leaf/root/frags only): grid-share kernel
+  ttn::ChainMmaDev cmma_light{}; // the merged image WITHOUT deep leaf / root tables (same stream layout): host-buffer calls
+  bool cmma_light_ok = false;
+  double cmma_light_flops = 0.0;
   bool cmma_plain_ok = false;
   double cgemm_flops_exec = 0.0; // flops per point the GEMM chain kernel executes
   double cmma_flops_exec = 0.0;  // flops per point the DMMA chain kernel executes (merged: about half the rule)

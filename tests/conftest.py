@@ -9,6 +9,13 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# The parity tests drive the kernels through HOST buffers.  Host-buffer calls of deep-table chains normally run the
+# "light" image (PCIe-bound calls, k_chain_mma.cu); TTN_MMA_LIGHT=0 makes them run the deep-table image instead, so
+# that the kernel variant device-resident callers get (and bench.py's `value` times) is the one under test.
+# tests/test_gpu_round2.py::test_light_variant_for_host_buffers covers the default.
+os.environ.setdefault("TTN_MMA_LIGHT", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
     # built artefacts are git-ignored: on a fresh checkout compile them first (nvcc cross-compiles without a GPU)

@@ -219,9 +219,12 @@ def test_device_pointer_path_with_torch():
     torch.cuda.synchronize()
     o = plan.evaluate_device(x.data_ptr(), x.shape[0], out.data_ptr(), reduce_sum=True)
     host, _ = plan.evaluate_host(x.cpu().numpy())
-    assert (out.cpu().numpy() == host).all()
+    # device-resident calls run the deep-table image, host-buffer (PCIe-bound) calls the image without deep tables
+    # (k_chain_mma.cu, "Light variant"): same digits, values equal up to the rounding of two FP64 evaluation orders
+    dev = out.cpu().numpy()
+    assert (np.abs(dev - host) <= 1e-12 * np.maximum(np.abs(host), 1e-3 * np.sqrt(np.mean(host ** 2)))).all()
     assert o.kernel_ms > 0 and o.n_launches == 2
-    assert abs(o.sum_out[0] - host.sum()) <= 1e-12 * np.abs(host).sum()
+    assert abs(o.sum_out[0] - dev.sum()) <= 1e-12 * np.abs(dev).sum()
 
 
 def test_linearity_at_scale():
