@@ -97,8 +97,9 @@ enum {
                              streamed through a shared-memory ring by bulk async copies (TMA) */
   TTN_KERNEL_DMMA = 3,    /* chains up to width 32: points grouped by digit, FP64 DMMA tiles, state in
                              shared memory */
-  TTN_KERNEL_TREE = 5,    /* real trees with <= 2 children per vertex, chi <= 64 (binary trees, combs): vertex by
-                             vertex over a chunk, degree-3 vertices as Khatri-Rao FP64 DMMA GEMMs */
+  TTN_KERNEL_TREE = 5,    /* trees with <= 2 children per vertex, chi <= 64 real / 32 complex (binary trees, combs):
+                             vertex by vertex over a chunk, degree-3 vertices as Khatri-Rao FP64 DMMA GEMMs, subtree
+                             message tables, runs of single-child vertices merged into one GEMM */
   TTN_KERNEL_GRID = 6,    /* ttn_evaluate_grid on a FULL dyadic grid of a binary chain: prefix-shared level-by-level
                              expansion (~L/2 times fewer flops than independent points) */
   TTN_KERNEL_TABLE = 7,   /* narrow chains of binary site indices (chi <= 4 real / 2 complex): groups of vertices

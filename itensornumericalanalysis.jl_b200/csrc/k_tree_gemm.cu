@@ -302,7 +302,12 @@ __global__ void tree_leaf_kernel(const uint8_t* __restrict__ sl, int pc, const d
 
 // M_v[rows of class d] = KhatriRao(M_a, M_b)[rows] * T_d   (NCH == 2)   or   M_c[rows] * T_d (NCH == 1)
 // frags[d][kb][nb][lane] = T_d[k = 4 kb + (lane & 3)][n = 8 nb + (lane >> 2)],  k = a * W + b.
-template <int W, int NCH>
+// CPLX (two children of a COMPLEX network): rows are interleaved (re, im) pairs of W / 2 complex entries; the
+// embedded tensor of one complex `a` is a W x W real matrix (k = a W + b', b' = 2 b + re/im), so the b-sum is the same
+// DMMA loop and a fragment's column pair (2t, 2t + 1) is one complex number: the fold with M_a[p, a] is a complex
+// multiply-add inside the thread.  Single-child vertices of complex networks are plain real GEMMs on the embedded
+// matrix [[re, im], [-im, re]] and need no kernel support.
+template <int W, int NCH, bool CPLX = false>
 __global__ void __launch_bounds__(256, 1)
     tree_vertex_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb, double* __restrict__ Mout,
                        const uint32_t* __restrict__ list, const int* __restrict__ cls_off,
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(256, 1)
   // instead of being copied into a message buffer first
   constexpr int RS = W + 4;            // row stride (doubles) of the child blocks in shared memory
   constexpr int NT = W / 16;           // 8-column tiles per warp (warp tile 32 x W/2)
-  constexpr int KTOT = (NCH == 2) ? W * W : W;
+  constexpr int KTOT = (NCH == 2) ? (CPLX ? W * W / 2 : W * W) : W;
   constexpr int NKC = KTOT / TBK;
   constexpr int BCHUNKS = W / TBK;     // K chunks per value of `a`
   constexpr int B_STAGE_D = TBK * W;   // doubles per B stage (TBK/4 k-blocks x W/8 n-blocks x 32 lanes)
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const uint32_t sa_base = smem_u32(Sa), sb_base = smem_u32(Sb);
-  double ma[4] = {1.0, 1.0, 1.0, 1.0};
+  double ma[4] = {1.0, 1.0, 1.0, 1.0}, mi[4] = {0.0, 0.0, 0.0, 0.0};
   double inner[NCH == 2 ? 4 : 1][NT][2]; // partial sums over b for the current a (two children)
 
   for (int kc = 0; kc < NKC; ++kc) {
@@ -390,7 +395,15 @@ __global__ void __launch_bounds__(256, 1)
     const int a = kc / BCHUNKS, b0 = (kc % BCHUNKS) * TBK;
     if (NCH == 2 && (kc % BCHUNKS) == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ma[i] = lds64(sa_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + a) * 8u);
+      for (int i = 0; i < 4; ++i) {
+        if (CPLX) {
+          const double2 z = lds128(sa_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + 2 * a) * 8u);
+          ma[i] = z.x;
+          mi[i] = z.y;
+        } else {
+          ma[i] = lds64(sa_base + (uint32_t)((wm * 32 + i * 8 + g) * RS + a) * 8u);
+        }
+      }
     }
     const uint32_t b_st = bs_base + (uint32_t)((kc % TSTAGES) * B_STAGE_D) * 8u;
     if (NCH == 2 && (kc % BCHUNKS) == 0) {
@@ -423,6 +436,10 @@ __global__ void __launch_bounds__(256, 1)
         for (int j = 0; j < NT; ++j) {
           acc[i][j][0] = fma(ma[i], inner[i][j][0], acc[i][j][0]);
           acc[i][j][1] = fma(ma[i], inner[i][j][1], acc[i][j][1]);
+          if (CPLX) {
+            acc[i][j][0] = fma(-mi[i], inner[i][j][1], acc[i][j][0]);
+            acc[i][j][1] = fma(mi[i], inner[i][j][0], acc[i][j][1]);
+          }
         }
     }
     __syncthreads();
@@ -485,6 +502,73 @@ __global__ void tree_root_kernel(int nch, const double* __restrict__ Ma, const d
   }
 }
 
+// root of a COMPLEX network: one thread per point, root tensor [slice][a][b] as (re, im) pairs with row strides
+// H = W / 2 complex entries, read through the read-only cache (threads of a warp share the few slices).
+__global__ void __launch_bounds__(128) tree_root_c_kernel(int nch, const double* __restrict__ Ma, const double* __restrict__ Mb,
+                                                          const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
+                                                          const double* __restrict__ T, int W, double* __restrict__ out,
+                                                          double* __restrict__ partial, int do_sum, CoordSource src,
+                                                          const uint32_t* __restrict__ ta, const uint32_t* __restrict__ tb) {
+  const int H = W / 2;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const bool live = i < pc && p0 + i < npts;
+  double vr = 0.0, vi = 0.0;
+  if (live) {
+    const int d = sl[i];
+    if (nch == 0) {
+      vr = __ldg(T + 2 * d);
+      vi = __ldg(T + 2 * d + 1);
+    } else if (nch == 1) {
+      const double2* Td = reinterpret_cast<const double2*>(T) + (size_t)d * H;
+      const double2* m = reinterpret_cast<const double2*>(Mb + (size_t)(tb ? tb[i] : (uint32_t)i) * W);
+      for (int a = 0; a < H; ++a) {
+        const double2 x = m[a], t = __ldg(Td + a);
+        vr = fma(x.x, t.x, vr);
+        vr = fma(-x.y, t.y, vr);
+        vi = fma(x.x, t.y, vi);
+        vi = fma(x.y, t.x, vi);
+      }
+    } else {
+      const double2* Td = reinterpret_cast<const double2*>(T) + (size_t)d * H * H;
+      const double2* ma_ = reinterpret_cast<const double2*>(Ma + (size_t)(ta ? ta[i] : (uint32_t)i) * W);
+      const double2* mb_ = reinterpret_cast<const double2*>(Mb + (size_t)(tb ? tb[i] : (uint32_t)i) * W);
+      for (int a = 0; a < H; ++a) {
+        double sr = 0.0, si = 0.0;
+        for (int b = 0; b < H; ++b) {
+          const double2 x = mb_[b], t = __ldg(Td + (size_t)a * H + b);
+          sr = fma(x.x, t.x, sr);
+          sr = fma(-x.y, t.y, sr);
+          si = fma(x.x, t.y, si);
+          si = fma(x.y, t.x, si);
+        }
+        const double2 z = ma_[a];
+        vr = fma(z.x, sr, vr);
+        vr = fma(-z.y, si, vr);
+        vi = fma(z.x, si, vi);
+        vi = fma(z.y, sr, vi);
+      }
+    }
+    if (out) reinterpret_cast<double2*>(out)[p0 + i] = make_double2(vr, vi);
+  }
+  if (do_sum) {
+    __shared__ double sh[2][128];
+    double a0 = 0.0, a1 = 0.0;
+    if (live) accumulate_point(src, p0 + i, vr, vi, a0, a1);
+    sh[0][threadIdx.x] = a0;
+    sh[1][threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k < 128; ++k) { // fixed order: deterministic
+        a += sh[0][k];
+        b += sh[1][k];
+      }
+      partial[2 * blockIdx.x] = a;
+      partial[2 * blockIdx.x + 1] = b;
+    }
+  }
+}
+
 // ---- subtree message tables (build_tree_tables): the message a subtree sends upwards depends only
 // on the digits inside the subtree; for subtrees with few bits every message is tabulated at plan time.
 // vs[3 j .. 3 j + 2] = (vertex, bit offset in the table index, slice mask) of the j-th subtree vertex.
@@ -529,14 +613,19 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   p->tgemm_ok = false;
   p->tg_tab_of.clear();
   const int n = d->n_vertices;
-  if (d->is_complex || n < 2) return TTN_OK; // real networks only (for now)
+  if (n < 2) return TTN_OK;
+  const bool cplx = d->is_complex != 0;
+  const int NC = cplx ? 2 : 1;
   int maxchi = 1;
   for (int v = 0; v < n; ++v) {
     maxchi = std::max(maxchi, d->link_dim[v]);
     if (p->child_ptr[v + 1] - p->child_ptr[v] > 2 || p->nslices[v] > 8) return TTN_OK;
   }
-  if (maxchi > 64) return TTN_OK;
-  const int W = maxchi <= 16 ? 16 : (maxchi <= 32 ? 32 : 64);
+  // row width in doubles: chi (real) or 2 chi (complex: interleaved (re, im) pairs)
+  const int wreal = NC * maxchi;
+  if (wreal > 64) return TTN_OK;
+  const int W = wreal <= 16 ? 16 : (wreal <= 32 ? 32 : 64);
+  const int H = W / NC; // entries per row
   TreeGemmDev& g = p->tgemm;
   g.n_vertices = n;
   g.W = W;
@@ -544,6 +633,11 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   const double* T = reinterpret_cast<const double*>(d->tensors);
   p->tg_frag_off.assign(n, 0);
   std::vector<double> blob;
+  // element (re, im) of vertex v at flat index idx
+  auto el = [&](int v, size_t idx, double* re, double* im) {
+    *re = T[(d->tensor_ptr[v] + idx) * NC];
+    *im = cplx ? T[(d->tensor_ptr[v] + idx) * NC + 1] : 0.0;
+  };
   for (int v = 0; v < n; ++v) {
     const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
     const int ns = p->nslices[v];
@@ -552,39 +646,73 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
     const int ca = nch >= 1 ? d->link_dim[p->child[p->child_ptr[v]]] : 1;
     const int cb = nch == 2 ? d->link_dim[p->child[p->child_ptr[v] + 1]] : 1;
     p->tg_frag_off[v] = (int64_t)blob.size();
-    const double* Tv = T + d->tensor_ptr[v];
+    double re, im;
     if (is_root) {
-      // plain padded layout [slice][a][b] (b only for two children), parent dim 1
-      const size_t per = nch == 2 ? (size_t)W * W : (nch == 1 ? (size_t)W : 1);
+      // plain padded layout [slice][a][b] (b only for two children), parent dim 1; complex: (re, im) pairs, strides H
+      const size_t per = (nch == 2 ? (size_t)H * H : (nch == 1 ? (size_t)H : 1)) * NC;
       std::vector<double> R(per * ns, 0.0);
       for (int s = 0; s < ns; ++s) {
-        if (nch == 0) R[s] = Tv[s];
-        else if (nch == 1)
-          for (int a = 0; a < ca; ++a) R[(size_t)s * W + a] = Tv[(size_t)s * ca + a];
-        else
+        double* Rs = R.data() + (size_t)s * per;
+        if (nch == 0) {
+          el(v, s, &re, &im);
+          Rs[0] = re;
+          if (cplx) Rs[1] = im;
+        } else if (nch == 1) {
+          for (int a = 0; a < ca; ++a) {
+            el(v, (size_t)s * ca + a, &re, &im);
+            Rs[(size_t)a * NC] = re;
+            if (cplx) Rs[(size_t)a * NC + 1] = im;
+          }
+        } else {
           for (int a = 0; a < ca; ++a)
-            for (int b = 0; b < cb; ++b) R[((size_t)s * W + a) * W + b] = Tv[((size_t)s * ca + a) * cb + b];
+            for (int b = 0; b < cb; ++b) {
+              el(v, ((size_t)s * ca + a) * cb + b, &re, &im);
+              Rs[((size_t)a * H + b) * NC] = re;
+              if (cplx) Rs[((size_t)a * H + b) * NC + 1] = im;
+            }
+        }
       }
       blob.insert(blob.end(), R.begin(), R.end());
     } else if (nch == 0) {
       std::vector<double> L((size_t)ns * W, 0.0);
       for (int s = 0; s < ns; ++s)
-        for (int j = 0; j < pdim; ++j) L[(size_t)s * W + j] = Tv[(size_t)s * pdim + j];
+        for (int j = 0; j < pdim; ++j) {
+          el(v, (size_t)s * pdim + j, &re, &im);
+          L[(size_t)s * W + (size_t)j * NC] = re;
+          if (cplx) L[(size_t)s * W + (size_t)j * NC + 1] = im;
+        }
       blob.insert(blob.end(), L.begin(), L.end());
     } else {
-      // fragment order over K = (a, b) (or a) and N = parent index
-      const int K = nch == 2 ? W * W : W;
+      // fragment order over K = (a, b') (or a') and N = parent index n'; complex entries are embedded as
+      // [[re, im], [-im, re]] on (b', n') (two children) / (a', n') (one child), rows and columns interleaved
+      const int K = nch == 2 ? H * W : W;
       std::vector<double> E((size_t)K * W), F((size_t)ns * K * W, 0.0);
+      auto put = [&](size_t krow, int q, double r_, double i_) {
+        // krow: row of the (re part); real networks: one row, one column
+        if (!cplx) {
+          E[krow * W + q] = r_;
+        } else {
+          E[krow * W + 2 * q] = r_;
+          E[krow * W + 2 * q + 1] = i_;
+          E[(krow + 1) * W + 2 * q] = -i_;
+          E[(krow + 1) * W + 2 * q + 1] = r_;
+        }
+      };
       for (int s = 0; s < ns; ++s) {
         std::fill(E.begin(), E.end(), 0.0);
         if (nch == 2) {
           for (int a = 0; a < ca; ++a)
             for (int b = 0; b < cb; ++b)
-              for (int q = 0; q < pdim; ++q)
-                E[((size_t)a * W + b) * W + q] = Tv[(((size_t)s * ca + a) * cb + b) * pdim + q];
+              for (int q = 0; q < pdim; ++q) {
+                el(v, (((size_t)s * ca + a) * cb + b) * pdim + q, &re, &im);
+                put((size_t)a * W + (size_t)b * NC, q, re, im);
+              }
         } else {
           for (int a = 0; a < ca; ++a)
-            for (int q = 0; q < pdim; ++q) E[(size_t)a * W + q] = Tv[((size_t)s * ca + a) * pdim + q];
+            for (int q = 0; q < pdim; ++q) {
+              el(v, ((size_t)s * ca + a) * pdim + q, &re, &im);
+              put((size_t)a * NC, q, re, im);
+            }
         }
         double* Fs = F.data() + (size_t)s * K * W;
         for (int kb = 0; kb < K / 4; ++kb)
@@ -610,12 +738,12 @@ int build_tree_gemm(ttn_plan* p, const ttn_desc* d) {
   return build_tree_merge(p, d);
 }
 
-template <int W, int NCH>
+template <int W, int NCH, bool CPLX = false>
 static int launch_vertex(const double* Ma, const double* Mb, double* Mout, const uint32_t* list, const int* cls_off,
                          const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s,
                          const uint32_t* ta = nullptr, const uint32_t* tb = nullptr) {
   constexpr size_t smem = ((size_t)(NCH == 2 ? 2 : 1) * TBM * (W + 4) + (size_t)TSTAGES * TBK * W) * 8;
-  auto kern = tree_vertex_kernel<W, NCH>;
+  auto kern = tree_vertex_kernel<W, NCH, CPLX>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = pc / TBM + nsl;
   kern<<<grid, 256, smem, s>>>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, ta, tb);
@@ -626,7 +754,8 @@ static int launch_vertex(const double* Ma, const double* Mb, double* Mout, const
 template <int W>
 static int launch_vertex_w(int nch, const double* Ma, const double* Mb, double* Mout, const uint32_t* list,
                            const int* cls_off, const int* tile_off, const double* frags, int nsl, int pc, cudaStream_t s,
-                           const uint32_t* ta = nullptr, const uint32_t* tb = nullptr) {
+                           const uint32_t* ta = nullptr, const uint32_t* tb = nullptr, bool cplx = false) {
+  if (nch == 2 && cplx) return launch_vertex<W, 2, true>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s, ta, tb);
   return nch == 2 ? launch_vertex<W, 2>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s, ta, tb)
                   : launch_vertex<W, 1>(Ma, Mb, Mout, list, cls_off, tile_off, frags, nsl, pc, s, ta, tb);
 }
@@ -675,7 +804,8 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   const int do_sum = d_partial != nullptr;
   const int64_t n_chunks = (src.npts + PC - 1) / PC;
   const int root_nch = p->child_ptr[g.root + 1] - p->child_ptr[g.root];
-  const bool fast_root = root_nch == 2 && W <= 32 && (size_t)p->nslices[g.root] * W * W * 8 <= 96 * 1024;
+  const bool cplx = p->info.is_complex != 0;
+  const bool fast_root = cplx || (root_nch == 2 && W <= 32 && (size_t)p->nslices[g.root] * W * W * 8 <= 96 * 1024);
   const int root_blocks = fast_root ? (PC + 127) / 128 : (PC * 32 + 255) / 256;
   double* big_partial = nullptr;
   if (do_sum) {
@@ -735,7 +865,11 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
       if (role == 1) continue; // absorbed into the merged run that ends higher up
       if (v == g.root) {
         double* part = do_sum ? big_partial + 2 * ck * root_blocks : nullptr;
-        if (fast_root) {
+        if (cplx) {
+          tree_root_c_kernel<<<root_blocks, 128, 0, s>>>(nch, nch == 2 ? msg_of(ca) : nullptr, nch >= 1 ? msg_of(nch == 2 ? cb : ca) : nullptr,
+                                                         slices + (size_t)v * PC, PC, p0, src.npts, blob, W, d_out, part, do_sum, src,
+                                                         nch == 2 ? idx_of(ca) : nullptr, nch >= 1 ? idx_of(nch == 2 ? cb : ca) : nullptr);
+        } else if (fast_root) {
           const size_t sm = (size_t)p->nslices[v] * W * W * 8;
           if (W == 16) {
             TTN_CUDA(cudaFuncSetAttribute(tree_root2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -762,9 +896,9 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
         const double* fr = role == 2 ? p->tg_mblob + p->tg_mfrag_off[v] : blob;
         const int nsl = role == 2 ? p->tg_mnsl[v] : p->nslices[v];
         int rc;
-        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
-        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
-        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib);
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib, cplx);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib, cplx);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(v), lists + (size_t)v * PC, cls_off + v * TOFF, tile_off + v * TOFF, fr, nsl, PC, s, ia, ib, cplx);
         if (rc) return rc;
       }
       *n_launches += 1;
@@ -820,27 +954,43 @@ static int build_tree_merge(ttn_plan* p, const ttn_desc* d) {
     if (mem.size() < 2) continue;
     const int top = mem.back(), ncls = 1 << bits;
     const int in_v = p->child[p->child_ptr[b0]];
-    // class matrices: row vector (child dim of the bottom member) x E_m0[s0] x E_m1[s1] ... (parent dim of the top)
+    // class matrices: row vector (child dim of the bottom member) x E_m0[s0] x E_m1[s1] ... (parent dim of the top);
+    // complex entries embedded as [[re, im], [-im, re]] with interleaved rows / columns (the embedding of a product
+    // is the product of the embeddings)
+    const int NCm = d->is_complex ? 2 : 1;
     std::vector<double> F((size_t)ncls * W * W, 0.0);
     for (int c = 0; c < ncls; ++c) {
       std::vector<ld> cur((size_t)W * W, 0.0L);
-      int rows = d->link_dim[in_v], cols = rows;
+      int rows = NCm * d->link_dim[in_v], cols = rows;
       for (int i = 0; i < rows; ++i) cur[(size_t)i * W + i] = 1.0L;
       int shift = 0;
       for (int m : mem) {
         const int bm = bits_of(m), sm = (c >> shift) & ((1 << bm) - 1);
         shift += bm;
-        const int ca = cols, pd = d->link_dim[m];
-        const double* Tm = T + d->tensor_ptr[m] + (size_t)sm * ca * pd;
+        const int ca = cols / NCm, pd = d->link_dim[m];
+        const double* Tm = T + (d->tensor_ptr[m] + (size_t)sm * ca * pd) * NCm;
+        std::vector<ld> Em((size_t)W * W, 0.0L); // embedded member matrix
+        for (int k = 0; k < ca; ++k)
+          for (int q = 0; q < pd; ++q) {
+            const ld re = Tm[((size_t)k * pd + q) * NCm], im = NCm == 2 ? Tm[((size_t)k * pd + q) * 2 + 1] : 0.0L;
+            if (NCm == 1) {
+              Em[(size_t)k * W + q] = re;
+            } else {
+              Em[(size_t)(2 * k) * W + 2 * q] = re;
+              Em[(size_t)(2 * k) * W + 2 * q + 1] = im;
+              Em[(size_t)(2 * k + 1) * W + 2 * q] = -im;
+              Em[(size_t)(2 * k + 1) * W + 2 * q + 1] = re;
+            }
+          }
         std::vector<ld> nxt((size_t)W * W, 0.0L);
         for (int i = 0; i < rows; ++i)
-          for (int k = 0; k < ca; ++k) {
+          for (int k = 0; k < NCm * ca; ++k) {
             const ld a = cur[(size_t)i * W + k];
             if (a == 0.0L) continue;
-            for (int q = 0; q < pd; ++q) nxt[(size_t)i * W + q] += a * (ld)Tm[(size_t)k * pd + q];
+            for (int q = 0; q < NCm * pd; ++q) nxt[(size_t)i * W + q] += a * Em[(size_t)k * W + q];
           }
         cur.swap(nxt);
-        cols = pd;
+        cols = NCm * pd;
       }
       double* Fs = F.data() + (size_t)c * W * W;
       for (int kb = 0; kb < W / 4; ++kb)
@@ -854,8 +1004,9 @@ static int build_tree_merge(ttn_plan* p, const ttn_desc* d) {
     p->tg_mnsl[top] = ncls;
     p->tg_mfrag_off[top] = (int64_t)mblob.size();
     mblob.insert(mblob.end(), F.begin(), F.end());
-    for (int m : mem) p->tgemm_flops_exec -= 2.0 * d->link_dim[p->child[p->child_ptr[m]]] * d->link_dim[m];
-    p->tgemm_flops_exec += 2.0 * d->link_dim[in_v] * d->link_dim[top];
+    const double fmac = d->is_complex ? 8.0 : 2.0;
+    for (int m : mem) p->tgemm_flops_exec -= fmac * d->link_dim[p->child[p->child_ptr[m]]] * d->link_dim[m];
+    p->tgemm_flops_exec += fmac * d->link_dim[in_v] * d->link_dim[top];
   }
   if (!mblob.empty()) {
     TTN_CUDA(cudaMalloc(&p->tg_mblob, mblob.size() * 8));
@@ -927,10 +1078,11 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
     const int nch = p->child_ptr[v + 1] - p->child_ptr[v];
     const double pd = v == d->root ? 1.0 : d->link_dim[v];
     if (nch == 0) return 0.0;
+    const double fm = d->is_complex ? 8.0 : 2.0; // flops per (complex) multiply-add
     const double ca = d->link_dim[p->child[p->child_ptr[v]]];
-    if (nch == 1) return 2.0 * ca * pd;
+    if (nch == 1) return fm * ca * pd;
     const double cb = d->link_dim[p->child[p->child_ptr[v] + 1]];
-    return 2.0 * (ca * cb * pd + cb * pd);
+    return fm * (ca * cb * pd + cb * pd);
   };
   p->tgemm_flops_exec = 0.0;
   for (int v = 0; v < n; ++v) p->tgemm_flops_exec += vertex_flops(v);
@@ -1035,9 +1187,10 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
         const int cb = nch == 2 ? p->child[p->child_ptr[u] + 1] : -1;
         const double* Ma = nch == 2 ? M(ca) : nullptr;
         const double* Mb = nch == 2 ? M(cb) : M(ca);
-        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
-        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
-        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0);
+        const bool cx = d->is_complex != 0;
+        if (W == 16) rc = launch_vertex_w<16>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0, nullptr, nullptr, cx);
+        else if (W == 32) rc = launch_vertex_w<32>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0, nullptr, nullptr, cx);
+        else rc = launch_vertex_w<64>(nch, Ma, Mb, M(u), d_lists + (size_t)u * PC, cls_off + u * 9, tile_off + u * 9, blob, p->nslices[u], PC, 0, nullptr, nullptr, cx);
         if (rc) break;
       }
     }

@@ -207,7 +207,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
-  else if (p->tgemm_ok && max_link >= 8) I.auto_kernel = TTN_KERNEL_TREE; // measured cross-over (scripts/tree_small_chi.py)
+  else if (p->tgemm_ok && max_link >= (d->is_complex ? 3 : 8)) I.auto_kernel = TTN_KERNEL_TREE; // measured cross-overs (scripts/tree_small_chi.py, tree_probe.py)
   else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |
@@ -601,7 +601,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   if (kernel == TTN_KERNEL_TABLE && !p->ctab_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TABLE: network is not a chain of binary site indices with chi <= 4 (real) / 2 (complex), <= 2 site indices per vertex and <= 128 slice bits");
   if (kernel == TTN_KERNEL_TREE && !p->tgemm_ok)
-    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a tree the per-vertex GEMM kernel covers (<= 2 children per vertex, chi <= 64, <= 8 slices per vertex)");
+    return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_TREE: network is not a tree the per-vertex GEMM kernel covers (<= 2 children per vertex, chi <= 64 real / 32 complex, <= 8 slices per vertex)");
   if (kernel == TTN_KERNEL_GEMM && !p->cgemm_ok)
     return fail(TTN_ERR_UNSUPPORTED, "TTN_KERNEL_GEMM: network is not a chain with 32 < (real-embedded) width <= 256 and <= 8 slices per vertex");
   if (kernel == TTN_KERNEL_DMMA && !p->cmma_ok)

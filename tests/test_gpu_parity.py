@@ -76,9 +76,12 @@ def test_chain_cases_really_use_the_chain_kernel():
     for n in ("mps2d_chi48_gemm", "cplx_cfg5_chi40_gemm"):
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GEMM, n
-    for n in ("comb3x4_chi4", "bintree4_chi5", "cplx_comb3x3"):
+    for n in ("comb3x4_chi4", "bintree4_chi5"):
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GENERIC, n
+    # complex trees with <= 2 children per vertex take the per-vertex GEMM kernel from chi = 3 (round 2)
+    _, f, dims, _ = names["cplx_comb3x3"]
+    assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_TREE
     for n in ("bintree4_chi5", "bintree5_chi20_tree"):   # real, <= 2 children: tree GEMM path available
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE), n
