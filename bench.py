@@ -548,6 +548,27 @@ def measure_multi_plan(ctx, plan, bufs, steps, warmup):
     return res
 
 
+def check_nccl_sharded(ctx, config):
+    """N > 1: the one-process-per-GPU driver with its REAL collectives (parallel.evaluate_sharded: contiguous blocks of
+    one shared point set, NCCL all_gather of the values, NCCL all_reduce of the quadrature sum), checked on rank 0
+    against a single-GPU evaluation of the same points."""
+    from itna_b200.parallel import evaluate_sharded
+    f, ncol, _, _ = build_workload(config)
+    n = 4_000_003
+    pts = np.random.default_rng(4321).random((n, ncol))     # the same array on every rank
+    t0 = time.perf_counter()
+    full = evaluate_sharded(f, pts, device=ctx.local_rank)
+    total = evaluate_sharded(f, pts, device=ctx.local_rank, reduce="sum")
+    dt = time.perf_counter() - t0
+    res = None
+    if ctx.rank == 0:
+        one = f.plan(device=ctx.local_rank).evaluate_host(pts)[0]
+        res = {"points": n, "ranks": ctx.world, "backend": ctx.dist.get_backend(),
+               "gathered_values_eq_single_gpu_bitwise": bool((full == one).all()),
+               "allreduce_sum_rel_err": float(abs(total - one.sum()) / np.abs(one).sum()), "seconds": dt}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -604,8 +625,13 @@ def main():
         line["fp64_peaks"] = ctx.peaks
         if world > 1:
             mp = measure_multi_plan(ctx, plan, bufs, args.steps, args.warmup)
+            try:
+                sh = check_nccl_sharded(ctx, args.config)
+            except Exception as e:
+                sh = {"error": repr(e)}
             if rank == 0:
                 line["multi_plan"] = mp
+                line["nccl_sharded_check"] = sh
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             x_np = bufs.x_np

@@ -1,6 +1,11 @@
-"""Multi-GPU sharding of a batched evaluate: one process per GPU (torch.distributed), the network
-replicated, the points partitioned into contiguous blocks (SURVEY §8 e).  There is no exchange
-step during evaluation; collectives are used only AFTER the kernels:
+"""Multi-GPU sharding of a batched evaluate (SURVEY §8 e): the network replicated, the points partitioned into
+contiguous blocks, no exchange step during evaluation.  Two drivers of the same partition:
+
+  * ONE process, G GPUs — `evaluate_multi` / `evaluate(f, pts, ngpus=G)`: a thin call into the library's
+    multi-device plan (ttn_plan_create_multi: one host thread and three streams per GPU, every GPU copies its block in
+    and its values out of the caller's arrays, per-GPU sums added in device order).  This is what a Julia caller gets.
+  * one process PER GPU (torch.distributed, the launch contract of bench.py) — `evaluate_sharded`: every rank evaluates
+    its block through a single-device plan; collectives only AFTER the kernels:
   * reduce="sum"  -> all_reduce(SUM) of one (real) or two (complex) doubles (grid quadrature),
   * gather=True   -> all_gather of the per-rank value blocks (otherwise every rank keeps its block).
 On GPUs the process group is NCCL (NVLink/NVSwitch); the CPU tests drive the same code with gloo
@@ -26,6 +31,15 @@ def _default_evaluator(fitn, dims, device):
         return out, complex(o.sum_out[0], o.sum_out[1])
 
     return run, plan.packed.is_complex
+
+
+def evaluate_multi(fitn, points, dims=None, *, ngpus=None, reduce=None, **kw):
+    """One process driving `ngpus` GPUs (default: all of them) through a multi-device plan."""
+    from . import _capi
+    from .itensornetworkfunction import evaluate
+    if ngpus is None:
+        ngpus = _capi.lib().ttn_device_count()
+    return evaluate(fitn, points, dims, ngpus=int(ngpus), reduce=reduce, **kw)
 
 
 def evaluate_sharded(fitn, points, dims=None, *, reduce=None, gather=True, group=None, device=None,
