@@ -526,6 +526,8 @@ def measure_multi_plan(ctx, plan, bufs, steps, warmup):
             for g in range(ctx.world):
                 xh[g * npts:(g + 1) * npts].copy_(bufs.x_host)
             xn, on = xh.numpy(), oh.numpy()
+            if bufs.key[2] == 2:
+                on = on.view(np.complex128)
             for _ in range(max(1, min(warmup, 2))):
                 mp.evaluate_host(xn, out=on)
             k = max(2, min(steps, 5))
@@ -535,8 +537,9 @@ def measure_multi_plan(ctx, plan, bufs, steps, warmup):
                 _, o = mp.evaluate_host(xn, out=on)
                 kms += o.kernel_ms
             dt = (time.perf_counter() - t0) / k
-            same = bool((on[:1 << 16] == bufs.out_np[:1 << 16]).all()) and \
-                bool((on[(ctx.world - 1) * npts:(ctx.world - 1) * npts + (1 << 16)] == bufs.out_np[:1 << 16]).all())
+            nchk = min(npts, 1 << 16)
+            ref = plan.evaluate_host(bufs.x_np[:nchk])[0]       # single-GPU plan, host buffers, same points
+            same = bool((on[:nchk] == ref).all()) and bool((on[(ctx.world - 1) * npts:(ctx.world - 1) * npts + nchk] == ref).all())
             res = {"e2e_value": total / dt, "unit": "points/s", "n_devices": int(o.n_devices_used), "ms_per_step": dt * 1e3,
                    "kernel_ms_max_over_devices": kms / k, "points_per_step": total, "blocks_eq_single_gpu_bitwise": same,
                    "api": "one process, ttn_plan_create_multi + ttn_evaluate(host pinned buffers): evaluate(f, pts; ngpus=N)"}
@@ -556,6 +559,8 @@ def check_nccl_sharded(ctx, config):
     f, ncol, _, _ = build_workload(config)
     n = 4_000_003
     pts = np.random.default_rng(4321).random((n, ncol))     # the same array on every rank
+    if f.plan(device=ctx.local_rank).packed.is_complex:     # ComplexIndexMap: points are complex numbers
+        pts = pts[:, 0::2] + 1j * pts[:, 1::2]
     t0 = time.perf_counter()
     full = evaluate_sharded(f, pts, device=ctx.local_rank)
     total = evaluate_sharded(f, pts, device=ctx.local_rank, reduce="sum")
