@@ -202,6 +202,22 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     {
       uint64_t w0[PPL];
       compute_words(tile, w0, w1);
+      if (deep) {
+        // the root-table row of every home point is known as soon as K1 is done: pull it into L2 now, the rounds
+        // hide the HBM latency (tables of 2^20 rows do not stay L2-resident)
+        const int off = ch.leaf_bits + R * BITS;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const uint64_t top = off == 0 ? w0[k] : (off < 64 ? ((w0[k] >> off) | (w1[k] << (64 - off))) : (w1[k] >> (off - 64)));
+          const double* Rp = ch.root + (size_t)(top & RMASK) * CHI;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(Rp));
+          if (CHI > 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Rp + 16));
+          if (ch.nout == 2) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Rp + ((size_t)CHI << ch.root_bits)));
+            if (CHI > 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Rp + ((size_t)CHI << ch.root_bits) + 16));
+          }
+        }
+      }
       if (src.dbg_stream) { // test hook: the fused K1's digits, compared as integers by the tests
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {

@@ -26,6 +26,21 @@ nets.append(("mps90 chi2 3-D, two-word stream (table)", t.rand_itn(s90, link_spa
 g40 = t.named_comb_tree((2, 40))
 s40 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
 nets.append(("comb2x40 chi1, 40-bit runs (table)", t.exp_itn(s40, k=-0.7, a=0.2, c=0.9, dim=2), 2, 5000))
+# round 2: base-3 / base-4 chains on the team-sorted and table kernels (Digit4 K1), deep leaf / root tables built on
+# the device (chains of > 32 bits), trees with merged single-child runs / multi-block classification / table-index
+# gathers (real and complex combs), the refined (double-double) pass
+s3l = t.continuous_siteinds(t.named_grid((24, 1)), base=3)
+nets.append(("r2 mps24 base3 chi16 (team, Digit4)", t.rand_itn(s3l, link_space=16, rng=9, normalise=True), 1, 3000))
+s4l = t.continuous_siteinds(t.named_grid((20, 1)), base=4, map_dimension=2)
+nets.append(("r2 mps20 base4 chi2 (table, Digit4)", t.rand_itn(s4l, link_space=2, rng=10, normalise=True), 2, 3000))
+s60 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
+nets.append(("r2 comb2x40 chi16 (team, deep tables built on the device)", t.rand_itn(s60, link_space=16, rng=11, normalise=True), 2, 3000))
+gc = t.named_comb_tree((3, 12))
+sc3 = t.continuous_siteinds(gc, [[(j, i) for i in range(1, 13)] for j in range(1, 4)])
+nets.append(("r2 comb3x12 chi16 (tree: tables, merged runs)", t.rand_itn(sc3, link_space=16, rng=12, normalise=True), 3, 3000))
+scc = t.complex_continuous_siteinds(gc, [[(j, i) for i in range(1, 13)] for j in range(1, 4)],
+                                    [[(j, i) for i in range(12, 0, -1)] for j in range(3, 0, -1)])
+nets.append(("r2 complex comb3x12 chi6 (tree, complex fold)", t.rand_itn(scc, link_space=6, rng=13, eltype=complex, normalise=True), 6, 2000))
 skip = os.environ.get('SAN_SKIP', '')
 only = os.environ.get('SAN_ONLY', '')
 # default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
@@ -47,5 +62,8 @@ for merge in (os.environ.get('SAN_MERGES', 'default,1').split(',')):
                 out, o = plan.evaluate_host(pts, kernel=kname, reduce_sum=True)
                 print(f"merge={merge}", name, kname, "ok", float(np.abs(out).max()))
         plan.digits_host(pts)
+        if name.startswith("r2") and merge == 'default':
+            out, o = plan.evaluate_host(pts, accuracy="refined", reduce_sum=True)
+            print(name, "refined ok", int(o.n_refined))
         f._plans.clear()
 print("done")
