@@ -436,3 +436,21 @@ function ind_values(fitn::ITensorNetworkFunction, points::AbstractMatrix, dims::
   rc == 0 || error("ttn_digits: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
   return dig, pl.packed.site_inds
 end
+
+"""
+    pin!(A::Array) / unpin!(A::Array)
+
+Optional: page-lock a Julia array that is passed to `evaluate` many times (`ttn_host_register`, portable), so that the
+library copies from / into it in place at the PCIe rate instead of staging it through its pinned ring.  Unpin before
+the array is freed or resized.  Plain (pageable) arrays need neither call.
+"""
+function pin!(A::Array)
+  rc = GC.@preserve A ccall((:ttn_host_register, LIBTTNEVAL), Cint, (Ptr{Cvoid}, UInt64), pointer(A), UInt64(sizeof(A)))
+  rc == 0 || error("ttn_host_register: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
+  return A
+end
+function unpin!(A::Array)
+  rc = GC.@preserve A ccall((:ttn_host_unregister, LIBTTNEVAL), Cint, (Ptr{Cvoid},), pointer(A))
+  rc == 0 || error("ttn_host_unregister: " * unsafe_string(ccall((:ttn_last_error, LIBTTNEVAL), Cstring, ())))
+  return A
+end
