@@ -315,7 +315,16 @@ def roofline_of(config, info, o_dev, npts, kernel_ms, peaks, _capi):
                         "shared-memory tables, one lookup per group; algorithmic bytes = 8 B per coordinate read + "
                         "8 (16 complex) B per value written"}
     peak_tf = peaks["denominator"]
-    return {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4; tcgen05 has no FP64 kind)",
+    hbm_view = None
+    if traffic:
+        hp, _ = hbm_peak()
+        hbm_view = {"dram_gb_per_s": traffic / (kernel_ms * 1e-3) / 1e9, "frac_of_hbm_peak": traffic / (kernel_ms * 1e-3) / 1e9 / hp,
+                    "algorithmic_bytes": info["bytes_per_point"] * npts, "traffic_over_algorithmic": traffic / (info["bytes_per_point"] * npts),
+                    "note": "recorded DRAM bytes of one launch / this run's kernel time.  Deep-table chains read two random "
+                            "128-byte table rows per point (traffic >> algorithmic bytes by design: 5 DMMA rounds per point "
+                            "instead of 13); neither pipe saturates — the kernel is bound by the latency of those gathers "
+                            "(profiles/r02_cfg2_mma6_deep.txt)"}
+    return {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA.8x8x4; tcgen05 has no FP64 kind)", "hbm_view": hbm_view,
             "achieved": exec_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": exec_tf / peak_tf if peak_tf else None, "traffic": traffic, "traffic_source": tsrc,
             "flops": "executed",
