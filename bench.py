@@ -397,10 +397,16 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
     same = bool((dv == hv).all())
     rel = float((np.abs(dv - hv) / np.maximum(np.abs(hv), 1e-3 * np.sqrt(np.mean(hv ** 2)) + 1e-300)).max())
 
-    h2d, d2h = int(npts * ncol * 8), int(npts * nc_out * 8)
-    e2e = {"value": npts * ctx.world / dt_e2e, "unit": "points/s", "h2d_bytes_per_step": h2d * ctx.world,
-           "d2h_bytes_per_step": d2h * ctx.world, "ms_per_step": dt_e2e * 1e3, "clocks": clocks_e2e,
-           "api": "ttn_evaluate(host pinned buffers) via the Python mirror's Plan.evaluate_host"}
+    h2d, d2h = int(npts * ncol * 8), int(npts * nc_out * 8)   # the caller's arrays: float64 coordinates in, values out
+    e2e = {"value": npts * ctx.world / dt_e2e, "unit": "points/s",
+           "h2d_bytes_per_step": int(o_e2e.h2d_bytes) * ctx.world, "d2h_bytes_per_step": int(o_e2e.d2h_bytes) * ctx.world,
+           "host_array_bytes_per_step": {"coords_f64": h2d * ctx.world, "values": d2h * ctx.world},
+           "coords_quantised_on_host": bool(o_e2e.staged & 4),
+           "ms_per_step": dt_e2e * 1e3, "clocks": clocks_e2e,
+           "api": "ttn_evaluate(host pinned float64 buffers) via the Python mirror's Plan.evaluate_host; h2d / d2h bytes are what "
+                  "the call really moved over PCIe (ttn_opts.h2d_bytes / d2h_bytes): where every coordinate's digits are the bits "
+                  "of floor(x 2^L) the staging threads quantise it to that 32-bit grid index on the host (bit-exact), "
+                  "halving the H2D bytes"}
     if extras:
         # the same bytes with NO kernel: H2D of the coordinates and D2H of the values on two streams, all ranks at
         # once — what this box's PCIe / host memory system can move; e2e is reported as a fraction of it
@@ -426,8 +432,10 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
         dt_page, _, _, o_pg, _ = timed(lambda: plan.evaluate_host(xp, out=op)[1], k=3, w=1)
         e2e["pageable"] = {"value": len(xp) * ctx.world / dt_page, "unit": "points/s", "points_per_step": len(xp),
                            "staged_bits": int(o_pg.staged),
-                           "what": "same call on unpinned numpy arrays (what a Julia Matrix{Float64} is): copied "
-                                   "through the library's pinned staging ring by its host thread pool"}
+                           "h2d_bytes_per_point": float(o_pg.h2d_bytes) / len(xp),
+                           "what": "same call on unpinned numpy arrays (what a Julia Matrix{Float64} is): moved through "
+                                   "the library's pinned staging ring by its host thread pool; staged_bits 4 = the "
+                                   "coordinates were quantised to their 32-bit grid index on the way (bit-exact)"}
         del xp, op
 
     in_gb, out_gb = h2d / 1e9, d2h / 1e9

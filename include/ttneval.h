@@ -67,8 +67,13 @@ enum {
  * (cudaHostAlloc / ttn_host_register) are used in place.  A registration is never cached across calls: a stale
  * one would outlive a freed Julia / numpy array. */
 enum {
-  TTN_STAGE_AUTO = 0, /* pinned buffers in place, pageable buffers through the staging ring */
-  TTN_STAGE_OFF = 1   /* hand every host pointer straight to cudaMemcpyAsync */
+  TTN_STAGE_AUTO = 0, /* pinned buffers in place, pageable buffers through the staging ring; and, where the digits of
+                         every coordinate are the bits of floor(x 2^L) (binary digits 1..L on consecutive chain
+                         vertices, L <= 32: the K1 run path), PAGEABLE coordinates are QUANTISED to that L-bit grid
+                         index by the staging threads on their way into the ring — 4 bytes per coordinate cross PCIe
+                         instead of 8, bit-exact (the evaluation depends on nothing else); opts->staged bit 2 reports it */
+  TTN_STAGE_OFF = 1,  /* hand every host pointer straight to cudaMemcpyAsync */
+  TTN_STAGE_COPY = 2  /* like AUTO, but coordinates always travel as doubles */
 };
 
 /* ---- accuracy modes (ABI 3) */
@@ -190,8 +195,11 @@ typedef struct ttn_opts {
                             re-evaluated in double-double arithmetic; 0 = default (0.02) */
   /* outputs (ABI 3) */
   int32_t n_devices_used; /* GPUs that took part in this call (multi-device plans shard the points) */
-  int32_t staged;         /* bit 0: coords went through the pinned staging ring, bit 1: out did */
+  int32_t staged;         /* bit 0: coords went through the pinned staging ring, bit 1: out did, bit 2: coords were
+                             quantised on the host (TTN_STAGE_AUTO) */
   int64_t n_refined;      /* points re-evaluated by TTN_ACCURACY_REFINED */
+  int64_t h2d_bytes;      /* bytes this call copied host -> device (coordinates / index settings / weights) */
+  int64_t d2h_bytes;      /* bytes this call copied device -> host (values) */
 } ttn_opts;
 
 /* Uniform grid generator — grid_points(imap, N, d), src/IndexMaps/realindexmap.jl:78-86:

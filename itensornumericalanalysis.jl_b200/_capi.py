@@ -17,7 +17,7 @@ KERNEL_NAMES = {0: "auto", 1: "generic", 2: "chain", 3: "dmma", 4: "gemm", 5: "t
 KERNEL_IDS = {v: k for k, v in KERNEL_NAMES.items()}
 TTN_REDUCE_NONE, TTN_REDUCE_SUM, TTN_REDUCE_ABS2, TTN_REDUCE_WEIGHTED = range(4)
 REDUCE_IDS = {None: 0, False: 0, "none": 0, True: 1, "sum": 1, "abs2": 2, "weighted": 3}
-TTN_STAGE_AUTO, TTN_STAGE_OFF = 0, 1
+TTN_STAGE_AUTO, TTN_STAGE_OFF, TTN_STAGE_COPY = 0, 1, 2
 TTN_ACCURACY_FP64, TTN_ACCURACY_REFINED = 0, 1
 ACCURACY_IDS = {None: 0, "fp64": 0, "refined": 1}
 
@@ -65,6 +65,8 @@ class ttn_opts(C.Structure):
         ("n_devices_used", C.c_int32),
         ("staged", C.c_int32),
         ("n_refined", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
     ]
 
 

@@ -146,6 +146,25 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
 #pragma unroll
     for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
     for (int c = 0; c < dg.n_coords; ++c) {
+      if (src.qcoords) {
+        // coordinates quantised on the host while they were staged (ttn_api.cu, pack_coords): q = floor(x 2^L), x >= 1
+        // saturated, domain checked there — every coordinate is on the run path (the host checked that too)
+        const int L = ch.run_L[c], plow = ch.run_plow[c];
+        const bool rev = ch.run_rev[c] != 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int64_t p = p0 + k * 32 + lane;
+          unsigned long long q = p < src.npts ? (unsigned long long)__ldg(src.qcoords + p * dg.n_coords + c) : 0ull;
+          if (rev) q = __brevll(q) >> (64 - L);
+          if (plow < 64) {
+            w0[k] += q << plow;
+            if (plow + L > 64) w1[k] += q >> (64 - plow);
+          } else {
+            w1[k] += q << (plow - 64);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int k = 0; k < PPL; ++k) {
         const int64_t p = p0 + k * 32 + lane;

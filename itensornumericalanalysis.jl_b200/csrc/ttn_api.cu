@@ -258,6 +258,8 @@ static void destroy_plan(ttn_plan* p) {
     if (st.h_out) cudaFreeHost(st.h_out);
     if (st.h_weights) cudaFreeHost(st.h_weights);
     if (st.h_digits) cudaFreeHost(st.h_digits);
+    if (st.h_q) cudaFreeHost(st.h_q);
+    if (st.d_q) cudaFree(st.d_q);
     if (st.k0) cudaEventDestroy(st.k0);
     if (st.k1) cudaEventDestroy(st.k1);
     if (st.ev_h2d) cudaEventDestroy(st.ev_h2d);
@@ -332,6 +334,79 @@ static void stream_copy(void* dst, const void* src, size_t n) {
   else memcpy(dst, src, n);
 }
 
+// Host-side quantisation of run-path coordinates (TTN_STAGE_AUTO): q = floor(x 2^L) with x >= 1 saturating to
+// 2^L - 1 — exactly what the kernels' K1 run path computes from the double (k_chain_team.cu), so the digits are
+// bit-identical — written as uint32 into the pinned ring with streaming stores.  Returns true if a coordinate is
+// negative or NaN (TTN_ERR_DOMAIN, as on the device).
+struct PackParams {
+  int nc = 0;
+  double scale[TTN_MAX_COORDS];
+  uint32_t qmax[TTN_MAX_COORDS];
+};
+// AVX2 body for 1, 2 or 4 coordinates per point and L <= 31 (signed 32-bit conversion): four doubles per step,
+// q = trunc(min(x 2^L, 2^L - 1)) — the min IS the saturation of x >= 1, and for x < 1 it never bites
+// (floor(x 2^L) <= 2^L - 1) — one compare for the domain flag, one streaming 16-byte store.
+__attribute__((target("avx2"))) static bool pack_coords_avx2(uint32_t* dst, const double* src, size_t n_doubles, const PackParams& pp) {
+  double sc[4], qm[4];
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = pp.scale[i % pp.nc];
+    qm[i] = (double)pp.qmax[i % pp.nc];
+  }
+  const __m256d vs = _mm256_loadu_pd(sc), vq = _mm256_loadu_pd(qm), zero = _mm256_setzero_pd();
+  int ok = 0xF;
+  size_t i = 0;
+  for (; i + 4 <= n_doubles; i += 4) {
+    const __m256d x = _mm256_loadu_pd(src + i);
+    ok &= _mm256_movemask_pd(_mm256_cmp_pd(x, zero, _CMP_GE_OQ));
+    // max(t, 0) with t first: a NaN / negative lane (flagged above) becomes 0, never an out-of-range field
+    const __m128i q = _mm256_cvttpd_epi32(_mm256_max_pd(_mm256_min_pd(_mm256_mul_pd(x, vs), vq), zero));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), q);
+  }
+  _mm_sfence();
+  bool bad = ok != 0xF;
+  for (; i < n_doubles; ++i) { // tail (n_doubles is a multiple of nc; i % 4 == 0 keeps the coordinate phase)
+    const double x = src[i];
+    const int c = (int)(i % pp.nc);
+    if (!(x >= 0.0)) {
+      bad = true;
+      dst[i] = 0u;
+    } else {
+      dst[i] = x >= 1.0 ? pp.qmax[c] : (uint32_t)(unsigned long long)(x * pp.scale[c]);
+    }
+  }
+  return bad;
+}
+
+static bool pack_coords(uint32_t* dst, const double* src, size_t npts, const PackParams& pp) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2 && (pp.nc == 1 || pp.nc == 2 || pp.nc == 4) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    bool l31 = true;
+    for (int c = 0; c < pp.nc; ++c) l31 = l31 && pp.qmax[c] <= 0x7fffffffu;
+    if (l31) return pack_coords_avx2(dst, src, npts * pp.nc, pp);
+  }
+  bool bad = false;
+  auto one = [&](double x, int c) -> uint32_t {
+    if (!(x >= 0.0)) {
+      bad = true;
+      return 0u;
+    }
+    if (x >= 1.0) return pp.qmax[c];
+    return (uint32_t)(unsigned long long)(x * pp.scale[c]);
+  };
+  if (pp.nc == 2 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    for (size_t p = 0; p < npts; ++p) {
+      const unsigned long long lo = one(src[2 * p], 0), hi = one(src[2 * p + 1], 1);
+      _mm_stream_si64(reinterpret_cast<long long*>(dst) + p, (long long)(lo | (hi << 32)));
+    }
+    _mm_sfence();
+  } else {
+    const int nc = pp.nc;
+    for (size_t p = 0; p < npts; ++p)
+      for (int c = 0; c < nc; ++c) dst[p * nc + c] = one(src[p * nc + c], c);
+  }
+  return bad;
+}
+
 class CopyPool {
  public:
   static CopyPool& get() {
@@ -359,6 +434,27 @@ class CopyPool {
     std::unique_lock<std::mutex> lk(job->mu);
     job->cv.wait(lk, [&] { return job->done.load() == job->n_slices; });
   }
+  // dst[0 : npts * nc) = quantised src[0 : npts * nc), in parallel (slices of 64 Ki points); returns the domain flag
+  bool pack(uint32_t* dst, const double* src, size_t npts, const PackParams& pp) {
+    constexpr size_t kPts = (size_t)1 << 16;
+    if (npts <= 2 * kPts || workers_ == 0) return pack_coords(dst, src, npts, pp);
+    auto job = std::make_shared<Job>();
+    job->dst = reinterpret_cast<char*>(dst);
+    job->src = reinterpret_cast<const char*>(src);
+    job->bytes = npts; // points
+    job->n_slices = (npts + kPts - 1) / kPts;
+    job->kind = 1;
+    job->pp = pp;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      jobs_.push_back(job);
+    }
+    cv_.notify_all();
+    work_on(*job);
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->cv.wait(lk, [&] { return job->done.load() == job->n_slices; });
+    return job->bad.load() != 0;
+  }
   int threads() const { return workers_ + 1; }
 
  private:
@@ -366,6 +462,9 @@ class CopyPool {
     char* dst;
     const char* src;
     size_t bytes, n_slices;
+    int kind = 0; // 0: streaming copy of `bytes` bytes; 1: pack_coords of `bytes` POINTS
+    PackParams pp;
+    std::atomic<int> bad{0};
     std::atomic<size_t> next{0}, done{0};
     std::mutex mu;
     std::condition_variable cv;
@@ -383,8 +482,15 @@ class CopyPool {
     for (;;) {
       const size_t i = j.next.fetch_add(1);
       if (i >= j.n_slices) return;
-      const size_t off = i * kSlice, len = std::min(kSlice, j.bytes - off);
-      stream_copy(j.dst + off, j.src + off, len);
+      if (j.kind == 1) {
+        constexpr size_t kPts = (size_t)1 << 16;
+        const size_t p0 = i * kPts, np = std::min(kPts, j.bytes - p0);
+        if (pack_coords(reinterpret_cast<uint32_t*>(j.dst) + p0 * j.pp.nc, reinterpret_cast<const double*>(j.src) + p0 * j.pp.nc, np, j.pp))
+          j.bad.store(1);
+      } else {
+        const size_t off = i * kSlice, len = std::min(kSlice, j.bytes - off);
+        stream_copy(j.dst + off, j.src + off, len);
+      }
       if (j.done.fetch_add(1) + 1 == j.n_slices) {
         std::lock_guard<std::mutex> lk(j.mu);
         j.cv.notify_all();
@@ -484,7 +590,7 @@ static int validate_opts(const ttn_opts* opts, const void* out) {
   if (opts->reduce_sum == TTN_REDUCE_WEIGHTED && !opts->weights) return fail(TTN_ERR_INVALID, "TTN_REDUCE_WEIGHTED needs opts->weights");
   if (!out && opts->reduce_sum == TTN_REDUCE_NONE) return fail(TTN_ERR_INVALID, "out is NULL and reduce_sum is 0: nothing to compute");
   if (opts->accuracy != TTN_ACCURACY_FP64 && opts->accuracy != TTN_ACCURACY_REFINED) return fail(TTN_ERR_INVALID, "bad accuracy mode");
-  if (opts->host_staging != TTN_STAGE_AUTO && opts->host_staging != TTN_STAGE_OFF) return fail(TTN_ERR_INVALID, "bad host_staging mode");
+  if (opts->host_staging < TTN_STAGE_AUTO || opts->host_staging > TTN_STAGE_COPY) return fail(TTN_ERR_INVALID, "bad host_staging mode");
   if (!(opts->refine_tau >= 0.0) || opts->refine_tau > 1e3) return fail(TTN_ERR_INVALID, "refine_tau must be in [0, 1000]");
   return TTN_OK;
 }
@@ -508,6 +614,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   opts->staged = 0;
   opts->n_refined = 0;
   opts->flops_executed = 0.0;
+  opts->h2d_bytes = opts->d2h_bytes = 0;
   int rc = validate_opts(opts, out);
   if (rc) return rc;
   if (npts < 0) return fail(TTN_ERR_INVALID, "npts < 0");
@@ -565,6 +672,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
         const int64_t slice = (int64_t)1 << 22;
         for (int64_t f0 = 0; f0 < npts && rc == TTN_OK; f0 += slice) {
           const int64_t m = std::min(slice, npts - f0);
+          opts->d2h_bytes += (int64_t)(sizeof(double) * m * NC);
           if (sp_out == SPACE_PAGEABLE) {
             rc = ensure_host_ring(p, st, slice, false, true, false);
             if (rc) break;
@@ -620,6 +728,29 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   const bool w_staged = sp_w == SPACE_ASYNC || sp_w == SPACE_PAGEABLE || sp_w == SPACE_PEER;
   // host buffers: the call is bound by the PCIe copies that run beside the kernels (launch_chain_team)
   const bool pcie_bound = sp_in == SPACE_ASYNC || sp_in == SPACE_PAGEABLE || sp_out == SPACE_ASYNC || sp_out == SPACE_PAGEABLE;
+  // Host-side quantisation of the coordinates (include/ttneval.h, TTN_STAGE_AUTO): every coordinate on the K1 run path
+  // of the team-sorted kernel with L <= 32, AoS host doubles in PAGEABLE memory — the staging threads touch every byte
+  // of such an array anyway, and writing 4 bytes per coordinate into the ring instead of 8 takes a quarter off their
+  // DRAM traffic and half off the H2D bytes (config 2, 1 GPU: 2.0 -> 2.5 G points/s).  Pinned arrays are read by the
+  // copy engines directly, which is the cheapest path for the HOST memory system (16 B per point, no CPU pass): with
+  // TTN_HOST_QUANT=2 they are quantised too, +8 % on one GPU (3.19 -> 3.46 G points/s, then bound by host DRAM at
+  // ~140 GB/s instead of PCIe) but a loss as soon as several GPUs share that DRAM, so it is not the default.
+  PackParams pp;
+  const int quant_mode = getenv("TTN_HOST_QUANT") ? atoi(getenv("TTN_HOST_QUANT")) : 1;
+  bool quant = opts->host_staging == TTN_STAGE_AUTO && !base.grid && !digits && coords && !refine && base.layout == TTN_LAYOUT_AOS &&
+               (sp_in == SPACE_PAGEABLE || (sp_in == SPACE_ASYNC && quant_mode == 2)) && quant_mode != 0 &&
+               kernel == TTN_KERNEL_DMMA && chain_team_applicable(p) && base.n_coords >= 1 && npts >= ((int64_t)1 << 20);
+  if (quant) {
+    pp.nc = base.n_coords;
+    for (int c = 0; c < base.n_coords && quant; ++c) {
+      const int L = p->cmma.run_L[c];
+      quant = L >= 1 && L <= 32;
+      pp.scale[c] = p->cmma.run_scale[c];
+      pp.qmax[c] = L >= 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u);
+    }
+  }
+  (void)pcie_bound; // quantised or not, a host-buffer call is bound by its copies / the host pass: light image
+  bool host_bad = false;
   // the refine pass and its functionals need the values of a chunk in device memory
   const bool need_dout = out_staged || (refine && !out);
   const bool chunked = in_staged || need_dout || w_staged;
@@ -658,7 +789,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     CopyPool::get().copy(pend[si].dst, p->streams[si].h_out, pend[si].bytes);
     pend[si].dst = nullptr;
   };
-  const bool any_pageable = sp_in == SPACE_PAGEABLE || sp_out == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE;
+  const bool any_pageable = sp_in == SPACE_PAGEABLE || sp_out == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE || quant;
   for (int ci = 0; ci < n_chunks && rc == TTN_OK; ++ci) {
     const int si = ci % n_streams;
     Stream& st = p->streams[si];
@@ -667,10 +798,10 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     rc = ensure_stream_buffers(p, st, chunked ? chunk : 1, in_staged && !digits, need_dout);
     if (rc) break;
     if (any_pageable) {
-      rc = ensure_host_ring(p, st, chunk, sp_in == SPACE_PAGEABLE && !digits, sp_out == SPACE_PAGEABLE, sp_w == SPACE_PAGEABLE);
+      rc = ensure_host_ring(p, st, chunk, sp_in == SPACE_PAGEABLE && !digits && !quant, sp_out == SPACE_PAGEABLE, sp_w == SPACE_PAGEABLE);
       if (rc) break;
       drain(si);                                                  // values of chunk ci - 3 -> caller's array
-      if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE) cudaEventSynchronize(st.ev_h2d); // ring slot free again
+      if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE || quant) cudaEventSynchronize(st.ev_h2d); // ring slot free again
     }
     CoordSource src = base;
     src.npts = m;
@@ -678,6 +809,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     src.weights = nullptr;
     src.pcie_bound = pcie_bound ? 1 : 0;
     if (opts->reduce_sum == TTN_REDUCE_WEIGHTED) {
+      if (w_staged) opts->h2d_bytes += (int64_t)(sizeof(double) * m);
       if (sp_w == SPACE_PAGEABLE) {
         CopyPool::get().copy(st.h_weights, opts->weights + first, sizeof(double) * m);
         cudaMemcpyAsync(st.d_weights, st.h_weights, sizeof(double) * m, cudaMemcpyHostToDevice, st.s);
@@ -713,14 +845,33 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
           opts->staged |= 1;
         }
         cudaMemcpyAsync(st.d_digits, hsrc, nbytes, cudaMemcpyDefault, st.s);
+        opts->h2d_bytes += (int64_t)nbytes;
         src.digits = st.d_digits;
       } else {
         src.digits = digits + (size_t)first * p->info.n_sites;
       }
     } else if (base.grid) {
       src.first = base.first + first;
+    } else if (quant) {
+      if (st.q_cap_points < chunk) {
+        if (st.h_q) cudaFreeHost(st.h_q);
+        if (st.d_q) cudaFree(st.d_q);
+        st.h_q = st.d_q = nullptr;
+        st.q_cap_points = 0;
+        TTN_CUDA(cudaHostAlloc(&st.h_q, sizeof(uint32_t) * (size_t)chunk * base.n_coords, cudaHostAllocPortable));
+        TTN_CUDA(cudaMalloc(&st.d_q, sizeof(uint32_t) * (size_t)chunk * base.n_coords));
+        st.q_cap_points = chunk;
+      }
+      host_bad = CopyPool::get().pack(st.h_q, coords + first * base.n_coords, (size_t)m, pp) || host_bad;
+      const size_t qb = sizeof(uint32_t) * (size_t)m * base.n_coords;
+      cudaMemcpyAsync(st.d_q, st.h_q, qb, cudaMemcpyHostToDevice, st.s);
+      opts->h2d_bytes += (int64_t)qb;
+      opts->staged |= 4 | (sp_in == SPACE_PAGEABLE ? 1 : 0);
+      src.qcoords = st.d_q;
+      src.coords = nullptr;
     } else if (in_staged) {
       const size_t row = sizeof(double) * (size_t)m;
+      opts->h2d_bytes += (int64_t)(row * base.n_coords);
       if (base.layout == TTN_LAYOUT_AOS) {
         const double* hsrc = coords + first * base.n_coords;
         if (sp_in == SPACE_PAGEABLE) {
@@ -745,7 +896,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       // device coordinates: a chunk is a sub-range of the caller's array
       src.coords = base.layout == TTN_LAYOUT_AOS ? coords + first * base.n_coords : coords;
     }
-    if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE) cudaEventRecord(st.ev_h2d, st.s);
+    if (sp_in == SPACE_PAGEABLE || sp_w == SPACE_PAGEABLE || quant) cudaEventRecord(st.ev_h2d, st.s);
     double* d_out = nullptr;
     if (need_dout) d_out = st.d_out;
     else if (out) d_out = reinterpret_cast<double*>(out) + first * NC;
@@ -779,6 +930,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     if (out && need_dout) {
       double* dst = reinterpret_cast<double*>(out) + first * NC;
       const size_t nbytes = sizeof(double) * (size_t)m * NC;
+      opts->d2h_bytes += (int64_t)nbytes;
       if (sp_out == SPACE_PAGEABLE) {
         cudaMemcpyAsync(st.h_out, st.d_out, nbytes, cudaMemcpyDeviceToHost, st.s);
         cudaEventRecord(st.ev_d2h, st.s);
@@ -814,7 +966,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     cudaMemcpy(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost);
     if (herr & 2)
       rc = fail(TTN_ERR_INVALID, "an index value is out of range for its site index");
-    else if (herr)
+    else if (herr || host_bad)
       rc = fail(TTN_ERR_DOMAIN,
                 "a coordinate is negative or NaN (the reference's digit loop, abstractindexmap.jl:121-138, does not terminate on such input)");
     if (do_sum && rc == TTN_OK) {
@@ -897,6 +1049,7 @@ static int evaluate_any(ttn_plan* p, CoordSource base, const double* coords, voi
   opts->staged = 0;
   opts->n_refined = 0;
   opts->flops_executed = 0.0;
+  opts->h2d_bytes = opts->d2h_bytes = 0;
   opts->kernel_used = ro[0].kernel_used;
   for (int g = 0; g < G; ++g) {
     if (rrc[g] != TTN_OK && rc == TTN_OK) {
@@ -911,6 +1064,8 @@ static int evaluate_any(ttn_plan* p, CoordSource base, const double* coords, voi
     opts->staged |= ro[g].staged;
     opts->n_refined += ro[g].n_refined;
     opts->flops_executed += ro[g].flops_executed;
+    opts->h2d_bytes += ro[g].h2d_bytes;
+    opts->d2h_bytes += ro[g].d2h_bytes;
   }
   opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   return rc;

@@ -58,6 +58,8 @@ struct CoordSource {
   const uint8_t* digits; // index-setting mode (ttn_evaluate_indices): digits[p * n_sites + site], else nullptr
   int32_t reduce_mode;   // TTN_REDUCE_* (what the kernels accumulate per point)
   const double* weights; // TTN_REDUCE_WEIGHTED: device pointer, one weight per point of this launch
+  const uint32_t* qcoords; // host-quantised coordinates (TTN_STAGE_AUTO): qcoords[p * n_coords + c] = min(floor(x 2^L_c), 2^L_c - 1);
+                           // nullptr otherwise.  Only kernels whose K1 runs every coordinate on the run path read it
   int32_t pcie_bound;    // 1: this launch is one chunk of a host-buffer call (H2D / D2H copies run beside it): launchers may
                          // pick the variant that leaves the memory system to the copy engines (launch_chain_team)
   unsigned long long* dbg_stream; // test hook (ttn_debug_slice_stream): the kernels with a FUSED K1 (team-sorted DMMA
@@ -189,6 +191,9 @@ struct Stream {
   int64_t h_cap_points = 0;
   size_t h_digits_cap = 0;
   cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;
+  uint32_t* h_q = nullptr;    // quantised coordinates: pinned ring slot and device buffer (chunk capacity)
+  uint32_t* d_q = nullptr;
+  int64_t q_cap_points = 0;
   // refine pass (TTN_ACCURACY_REFINED): compacted point list + values
   int32_t* d_sel = nullptr;   // [1 + points]: count, then the selected point indices
   size_t sel_cap = 0;         // in points

@@ -64,19 +64,22 @@ mutable struct TTNOpts
   weights_mem::Int32
   reserved_::Int32
   flops_executed::Float64
-  host_staging::Int32   # 0 = pageable Julia arrays go through the library's pinned staging ring
+  host_staging::Int32   # 0 = pageable Julia arrays go through the library's pinned staging ring (run-path coordinates quantised
+                        # to their grid index on the way), 1 = raw cudaMemcpyAsync, 2 = ring, coordinates stay doubles
   accuracy::Int32       # 0 = FP64, 1 = refined (double-double re-evaluation of the points that cancel)
   refine_tau::Float64
   n_devices_used::Int32
   staged::Int32
   n_refined::Int64
+  h2d_bytes::Int64
+  d2h_bytes::Int64
 end
 # reduce: TTN_REDUCE_NONE = 0, _SUM = 1 (sum f), _ABS2 = 2 (sum |f|^2), _WEIGHTED = 3 (sum w f)
 const REDUCE_MODES = Dict(:none => Int32(0), :sum => Int32(1), :abs2 => Int32(2), :weighted => Int32(3))
 const ACCURACY_MODES = Dict(:fp64 => Int32(0), :refined => Int32(1))
 TTNOpts(; reduce::Symbol=:none, weights::Ptr{Float64}=Ptr{Float64}(C_NULL), accuracy::Symbol=:fp64) =
   TTNOpts(TTN_MEM_HOST, TTN_MEM_HOST, 0, REDUCE_MODES[reduce], 0, 0.0, 0.0, 0.0f0, 0.0f0, 0, 0, weights, TTN_MEM_HOST, 0, 0.0,
-    0, ACCURACY_MODES[accuracy], 0.0, 0, 0, 0)
+    0, ACCURACY_MODES[accuracy], 0.0, 0, 0, 0, 0, 0)
 
 "Flat arrays of one packed network; keeps everything the C side points at alive."
 struct PackedNetwork

@@ -384,6 +384,50 @@ def test_pageable_end_to_end_rate_close_to_pinned():
     assert r_page > 0.6 * r_pin     # measured 0.70-0.78 on the 16-core GPU boxes (host memcpy bandwidth beside the DMA traffic)
 
 
+def test_host_side_coordinate_quantisation():
+    """TTN_STAGE_AUTO: the coordinates of a run-path chain travel as floor(x 2^L) (uint32) instead of float64 — packed
+    by the staging threads, half the H2D bytes.  Bit-for-bit the same values as the float64 path (TTN_STAGE_COPY), for
+    pinned and pageable arrays, edge coordinates included; domain errors are raised from the host pass."""
+    g = t.named_comb_tree((2, 30))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    f = t.rand_itn(s, link_space=16, rng=20262, normalise=True)
+    plan = f.plan()
+    rng = np.random.default_rng(12)
+    pts = cases.edge_points(30, 2, rng, 3_000_000)
+    js = np.arange(1, 31)
+    thr = np.concatenate([2.0 ** -js, np.nextafter(2.0 ** -js, 0), np.nextafter(2.0 ** -js, 1), [1.0, 2.0, 1e300, 5e-324]])
+    pts = np.concatenate([pts, np.stack([thr, np.roll(thr, 11)], axis=1)])
+    a, oa = plan.evaluate_host(pts, reduce_sum="sum", want_values=True)                          # pageable, quantised
+    b, ob = plan.evaluate_host(pts, reduce_sum="sum", want_values=True, host_staging=_capi.TTN_STAGE_COPY)
+    assert oa.staged & 4 and not (ob.staged & 4)
+    assert oa.h2d_bytes == pts.size * 4 and ob.h2d_bytes == pts.size * 8 and oa.d2h_bytes == ob.d2h_bytes == len(pts) * 8
+    assert (a == b).all() and oa.sum_out[0] == ob.sum_out[0]
+    pp, outp = pts.copy(), np.empty(len(pts))
+    _pin(pp), _pin(outp)
+    try:
+        c, oc = plan.evaluate_host(pp, out=outp)           # pinned arrays are read by the copy engines directly
+        assert oc.staged == 0 and oc.h2d_bytes == pts.size * 8 and (c == a).all()
+    finally:
+        _unpin(pp), _unpin(outp)
+    sub = np.concatenate([np.arange(20_000), np.arange(len(pts) - 150, len(pts))])
+    ref = orc.evaluate(plan.packed, pts[sub], orc.ORACLE_LD, nthreads=orc.max_threads())
+    err = orc.error_metric(a[sub], ref)
+    assert np.quantile(err, 0.999) < TOL and err.max() < 5e-12
+    bad = pts.copy()
+    bad[1_234_567, 1] = -1e-300
+    with pytest.raises(_capi.TTNError) as ei:
+        plan.evaluate_host(bad)
+    assert ei.value.code == _capi.TTN_ERR_DOMAIN
+    bad[1_234_567, 1] = np.nan
+    with pytest.raises(_capi.TTNError):
+        plan.evaluate_host(bad)
+    # a chain whose digits are interleaved (no run path in the team-sorted kernel's stream): coordinates stay doubles
+    s2 = t.continuous_siteinds(t.named_grid((40, 1)), map_dimension=2)
+    f2 = t.rand_itn(s2, link_space=16, rng=3, normalise=True)
+    _, o2 = f2.plan().evaluate_host(rng.random((1_200_000, 2)))
+    assert not (o2.staged & 4) and o2.h2d_bytes == 1_200_000 * 16
+
+
 def test_light_variant_for_host_buffers(monkeypatch):
     """Default plans: device-resident calls run the deep-table image of a long chain, host-buffer calls (bound by the
     PCIe copies beside the kernels) the image without deep tables.  Same digits; both within 1e-12 of the oracle."""

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes computed by hand from include/ttneval.h (LP64)
     assert C.sizeof(_capi.ttn_desc) == 6 * 4 + 10 * 8
-    assert C.sizeof(_capi.ttn_opts) == 4 * 4 + 8 + 16 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + (4 + 4 + 8 + 4 + 4 + 8)
+    assert C.sizeof(_capi.ttn_opts) == 4 * 4 + 8 + 16 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8 + (4 + 4 + 8 + 4 + 4 + 8) + 16
     assert C.sizeof(_capi.ttn_grid) == 8 + 8 + 8 + 8 + 8
     assert C.sizeof(_capi.ttn_info) == 10 * 4 + 8 + 8 + 8
 
