@@ -207,7 +207,8 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
   else if (p->chain_ok) I.auto_kernel = TTN_KERNEL_CHAIN;
   else if (p->cmma_ok) I.auto_kernel = TTN_KERNEL_DMMA;
   else if (p->cgemm_ok) I.auto_kernel = TTN_KERNEL_GEMM;
-  else if (p->tgemm_ok && max_link >= (d->is_complex ? 3 : 8)) I.auto_kernel = TTN_KERNEL_TREE; // measured cross-overs (scripts/tree_small_chi.py, tree_probe.py)
+  else if (p->tgemm_ok && max_link >= 3) I.auto_kernel = TTN_KERNEL_TREE; // measured cross-over (scripts/tree_small_chi.py, round 2: comb chi = 3
+                                                                          // 748 vs 753 M points/s generic, chi = 4 748 vs 592, binary tree chi = 3 2.9 G vs 0.98 G)
   else I.auto_kernel = TTN_KERNEL_GENERIC;
   I.device = p->device;
   I.kernels_available = (1 << TTN_KERNEL_GENERIC) | (p->chain_ok ? (1 << TTN_KERNEL_CHAIN) : 0) |

@@ -6,10 +6,10 @@ import itna_b200 as t
 from itna_b200 import _capi
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 4_000_000
 cases = []
-for chi in (2, 4, 8, 12):
-    g = t.named_comb_tree((3, 10))
-    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 11)] for i in (1, 2, 3)])
-    cases.append((f"comb3x10 chi{chi}", t.rand_itn(s, link_space=chi, rng=1, normalise=True), 3))
+for chi in (2, 3, 4, 6, 8, 12):
+    g = t.named_comb_tree((3, 20))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 21)] for i in (1, 2, 3)])
+    cases.append((f"comb3x20 chi{chi}", t.rand_itn(s, link_space=chi, rng=1, normalise=True), 3))
     g = t.named_binary_tree(5)
     ws = g.vertices()
     s = t.continuous_siteinds(g, [ws[i::2] for i in range(2)])

@@ -76,12 +76,15 @@ def test_chain_cases_really_use_the_chain_kernel():
     for n in ("mps2d_chi48_gemm", "cplx_cfg5_chi40_gemm"):
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GEMM, n
-    for n in ("comb3x4_chi4", "bintree4_chi5"):
+    # trees with <= 2 children per vertex take the per-vertex GEMM kernel from chi = 3, real or complex (round 2:
+    # merged runs, multi-block classification and 2^18-row subtree tables moved the cross-over down from chi = 8)
+    for n in ("comb3x4_chi4", "bintree4_chi5", "cplx_comb3x3"):
         _, f, dims, _ = names[n]
-        assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_GENERIC, n
-    # complex trees with <= 2 children per vertex take the per-vertex GEMM kernel from chi = 3 (round 2)
-    _, f, dims, _ = names["cplx_comb3x3"]
-    assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_TREE
+        assert f.plan(dims).info()["auto_kernel"] == _capi.TTN_KERNEL_TREE, n
+    for n in ("unitree9_s5", "unitree9_s6", "base3_comb"):      # >= 3 children somewhere / a base-3 TREE at chi = 3
+        _, f, dims, _ = names[n]
+        assert f.plan(dims).info()["auto_kernel"] in (_capi.TTN_KERNEL_GENERIC, _capi.TTN_KERNEL_TREE, _capi.TTN_KERNEL_CHAIN,
+                                                      _capi.TTN_KERNEL_DMMA, _capi.TTN_KERNEL_TABLE), n
     for n in ("bintree4_chi5", "bintree5_chi20_tree"):   # real, <= 2 children: tree GEMM path available
         _, f, dims, _ = names[n]
         assert f.plan(dims).info()["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE), n
