@@ -568,3 +568,17 @@ def test_refined_mode_meets_the_bar_at_the_maximum():
             coords[:] = p
         r = orc.evaluate(packed, coords, orc.ORACLE_LD)
         assert orc.error_metric(got, r).max() < TOL, name
+
+
+def test_mutating_a_network_re_plans():
+    """psi[v] *= c between two evaluate calls (the reference's in-place style): the second call sees the new tensors."""
+    s = t.continuous_siteinds(t.named_grid((24, 1)), map_dimension=2)
+    f = t.rand_itn(s, link_space=8, rng=4, normalise=True)
+    pts = np.random.default_rng(1).random((5000, 2))
+    a = t.evaluate(f, pts)
+    v = f.vertices()[3]
+    f[v] = f[v] * 2.0
+    b = t.evaluate(f, pts)
+    f.itensornetwork[v] = f.itensornetwork[v] * 0.25
+    c = t.evaluate(f, pts)
+    assert np.allclose(b, 2.0 * a, rtol=1e-13, atol=0) and np.allclose(c, 0.5 * a, rtol=1e-13, atol=0)

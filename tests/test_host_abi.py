@@ -176,3 +176,25 @@ def test_header_is_plain_c_and_the_c_example_links(tmp_path):
         assert "no CUDA device" in r.stdout
     else:
         assert "f(0.375) = 1.375000" in r.stdout and "f(0.999) = 1.875000" in r.stdout
+
+
+def test_plan_cache_is_dropped_when_a_vertex_is_assigned():
+    """the reference mutates networks in place (psi[v] = ..., psi[v] *= c).  The plan cache is keyed
+    on a version counter of the network, bumped by every vertex assignment — through the function object or through
+    its .itensornetwork — so stale packed tensors are never evaluated."""
+    import itna_b200 as t
+    from itna_b200 import _capi
+    s = t.continuous_siteinds(t.named_grid((6, 1)))
+    f = t.rand_itn(s, link_space=3, rng=1)
+    v = f.vertices()[0]
+    for assign in (lambda: f.__setitem__(v, f[v] * 2.0), lambda: f.itensornetwork.__setitem__(v, f.itensornetwork[v] * 2.0)):
+        f._plans[("stale",)] = object()
+        f._plans_version = f.itensornetwork.version
+        before = f.itensornetwork.version
+        assign()
+        assert f.itensornetwork.version != before
+        try:
+            f.plan()                      # no GPU here: plan creation itself fails, AFTER the stale entries are dropped
+        except (_capi.TTNError, RuntimeError):
+            pass
+        assert ("stale",) not in f._plans

@@ -161,3 +161,4 @@ def test_complex_2d_sum_two_site_indices_per_vertex(name, net_func, func):
     a, k, c = crand(), crand(), crand()
     psi = net_func(s, k=k, a=a, c=c, dim=1) + net_func(s, k=k, a=a, c=c, dim=2)
     assert approx(evaluate(psi, [z1, z2], [1, 2]), c * func(k * z1 + a) + c * func(k * z2 + a))
+
