@@ -32,13 +32,18 @@ __device__ __forceinline__ void t_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// slices[v][i] = slice index of vertex v at point i of the chunk.  A vertex with exactly one site index gets one
+// direct store; only the vertices listed in zero_v (no site index, or several) are zero-filled and accumulated.
 __global__ void tree_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, int pc, int n_vertices,
-                                   uint8_t* __restrict__ slices, int* err) {
+                                   uint8_t* __restrict__ slices, int* err, const int32_t* __restrict__ zero_v, int n_zero) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pc) return;
   const int64_t p = p0 + i;
-  for (int v = 0; v < n_vertices; ++v) slices[(size_t)v * pc + i] = 0;
-  if (p >= src.npts) return;
+  if (p >= src.npts) { // padding points of the last chunk: slice 0 everywhere (table rows / classes stay in range)
+    for (int v = 0; v < n_vertices; ++v) slices[(size_t)v * pc + i] = 0;
+    return;
+  }
+  for (int k = 0; k < n_zero; ++k) slices[(size_t)zero_v[k] * pc + i] = 0;
   for (int c = 0; c < dg.n_coords; ++c) {
     double x = load_coord(src, p, c);
     if (!coord_in_domain(x)) {
@@ -48,7 +53,8 @@ __global__ void tree_digits_kernel(DigitTable dg, CoordSource src, int64_t p0, i
     for (int k = dg.coord_ptr[c]; k < dg.coord_ptr[c + 1]; ++k) {
       const DigitEntry e = dg.entries[k];
       const int v = src.digits ? given_digit(src, p, dg.n_sites, e.site, e.base, err) : greedy_digit(x, dg.thr + e.thr_off, e.base);
-      slices[(size_t)e.vertex * pc + i] += (uint8_t)(v * e.stride);
+      if (e.pad_) slices[(size_t)e.vertex * pc + i] = (uint8_t)(v * e.stride);
+      else slices[(size_t)e.vertex * pc + i] += (uint8_t)(v * e.stride);
     }
   }
 }
@@ -243,7 +249,9 @@ __global__ void __launch_bounds__(256) tree_scatter_kernel(const uint8_t* __rest
 
 // root with two children and W <= 32: one THREAD per point, the root tensor of every slice in shared memory
 // (value = sum_a M_a[a] sum_b T_d[a][b] M_b[b]); the warp-per-point kernel below spent a quarter of a narrow
-// tree's time here.
+// tree's time here.  (A DMMA variant — S = M_b x T_d^T over tiles of 128 consecutive points with a dot-product epilogue —
+// was measured slower: 78 vs 63 us per 3e5-point chunk; both are bound by the latency of two row gathers per point, and
+// this kernel keeps more blocks resident.)
 template <int W>
 __global__ void __launch_bounds__(128) tree_root2_kernel(const double* __restrict__ Ma, const double* __restrict__ Mb,
                                                          const uint8_t* __restrict__ sl, int pc, int64_t p0, int64_t npts,
@@ -832,7 +840,7 @@ int launch_tree_gemm(ttn_plan* p, Stream& st, const CoordSource& src, double* d_
   const int nseg = (PC + TSEG - 1) / TSEG;
   for (int64_t ck = 0; ck < n_chunks; ++ck) {
     const int64_t p0 = ck * PC;
-    tree_digits_kernel<<<(PC + 255) / 256, 256, 0, s>>>(p->digits, src, p0, PC, n, slices, p->d_err);
+    tree_digits_kernel<<<(PC + 255) / 256, 256, 0, s>>>(p->digits, src, p0, PC, n, slices, p->d_err, p->tg_zero_v, p->tg_n_zero);
     *n_launches += 1;
     if (n_tab > 0) {
       tree_tabidx_kernel<<<dim3((PC + 255) / 256, n_tab), 256, 0, s>>>(slices, PC, reinterpret_cast<const TgTabRef*>(p->tg_tabrefs), tabidx);
@@ -1039,6 +1047,17 @@ static int build_tree_merge(ttn_plan* p, const ttn_desc* d) {
     }
     gv.push_back(c);
   }
+  {
+    std::vector<int32_t> zv;
+    for (int v = 0; v < n; ++v)
+      if (d->site_ptr[v + 1] - d->site_ptr[v] != 1) zv.push_back(v);
+    p->tg_n_zero = (int)zv.size();
+    if (!zv.empty()) {
+      TTN_CUDA(cudaMalloc(&p->tg_zero_v, zv.size() * sizeof(int32_t)));
+      p->allocs.push_back(p->tg_zero_v);
+      TTN_CUDA(cudaMemcpy(p->tg_zero_v, zv.data(), zv.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+  }
   if (!p->tg_tab.empty()) {
     std::vector<TgTabRef> refs(p->tg_tab.size());
     for (size_t i = 0; i < refs.size(); ++i) refs[i] = TgTabRef{p->tg_tab_vs[i], p->tg_tab_ns[i]};
@@ -1065,8 +1084,16 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
   const int n = d->n_vertices;
   const TreeGemmDev& g = p->tgemm;
   const int W = g.W;
-  int budget = 18; // W = 16: 2^18 rows, W = 32: 2^17, W = 64: 2^16 — 32 MB per table
-  while (budget > 0 && ((size_t)1 << budget) * W * 8 > ((size_t)32 << 20)) --budget;
+  // rows per table: W = 16: 2^20, W = 32: 2^19 (128 MB: a whole 20-vertex tooth of a comb is ONE row gather), W = 64: 2^16
+  // (32 MB; config 3's subtrees jump from 15 to 31 bits); all tables of a plan together <= 1 GB, and the build workspace
+  // (every message of the largest subtree over all its settings) must fit half of the free device memory
+  int budget = 20;
+  while (budget > 0 && ((size_t)1 << budget) * W * 8 > ((size_t)(W <= 32 ? 128 : 32) << 20)) --budget;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    free_b = (size_t)8 << 30;
+  }
   if (const char* e = getenv("TTN_TREE_TABLE_BITS")) budget = std::min(atoi(e), 20);
   p->tg_tab_of.assign(n, -1);
   p->tg_tab.clear();
@@ -1117,7 +1144,9 @@ static int build_tree_tables(ttn_plan* p, const ttn_desc* d) {
       frontier.push_back(v);
       total += ((size_t)1 << bits[v]) * W * 8;
     }
-    if (total <= ((size_t)1 << 30)) break;
+    size_t ws = 0; // build workspace of the largest table at this budget
+    for (int v : frontier) ws = std::max(ws, (size_t)std::max(TBM, 1 << bits[v]) * ((size_t)size[v] * W * 8 + (size_t)n * 5));
+    if (total <= ((size_t)1 << 30) && ws <= free_b / 2) break;
   }
   if (frontier.empty()) return TTN_OK;
   // workspace for the largest table

@@ -150,6 +150,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
         e.thr_off = d->thr_ptr[s];
         e.vertex = site_vertex[s];
         e.stride = site_stride[s];
+        e.pad_ = (d->site_ptr[site_vertex[s] + 1] - d->site_ptr[site_vertex[s]] == 1) ? 1 : 0; // the vertex's only site index
         entries.push_back(e);
       }
       coord_ptr[c + 1] = (int)entries.size();

@@ -32,7 +32,7 @@ struct DigitEntry {
   int32_t stride;  // stride of this digit inside the vertex's mixed-radix slice index
   int32_t word;    // chain kernel: which 64-bit word of the packed slice stream
   int32_t shift;   // chain kernel: bit offset inside that word
-  int32_t pad_;
+  int32_t pad_;    // 1: the owner vertex carries no other site index (its slice index IS this digit times stride)
 };
 
 struct DigitTable {
@@ -252,6 +252,8 @@ struct ttn_plan {
   double* tg_mblob = nullptr;         // (in allocs)
   void* tg_gv = nullptr;              // device array of TgClass: the vertices that run as GEMMs (in allocs)
   int tg_ngv = 0;
+  int32_t* tg_zero_v = nullptr;       // vertices whose slice index is accumulated (0 or >= 2 site indices): zero-filled per chunk
+  int tg_n_zero = 0;
   void* tg_tabrefs = nullptr;         // device array of (vs, ns) per subtree table (in allocs)
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
