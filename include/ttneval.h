@@ -191,8 +191,10 @@ typedef struct ttn_opts {
   /* inputs (appended in ABI 3) */
   int32_t host_staging;  /* TTN_STAGE_*: what to do with PAGEABLE host buffers (a Julia Array, a numpy array) */
   int32_t accuracy;      /* TTN_ACCURACY_* */
-  double refine_tau;     /* TTN_ACCURACY_REFINED: points with |f| < refine_tau * rms(f over this call) are
-                            re-evaluated in double-double arithmetic; 0 = default (0.02) */
+  double refine_tau;     /* TTN_ACCURACY_REFINED: points with |f| < refine_tau * rms(f) are re-evaluated in
+                            double-double arithmetic, rms taken over the chunk of the call the point belongs to (the
+                            whole call for device-resident buffers, <= chunk_points for host buffers, one block per
+                            GPU of a multi-device plan); 0 = default (0.02) */
   /* outputs (ABI 3) */
   int32_t n_devices_used; /* GPUs that took part in this call (multi-device plans shard the points) */
   int32_t staged;         /* bit 0: coords went through the pinned staging ring, bit 1: out did, bit 2: coords were
