@@ -774,11 +774,16 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   if (!chunked && npts > (int64_t)0x7fffff00 && refine) return fail(TTN_ERR_UNSUPPORTED, "TTN_ACCURACY_REFINED: more than 2^31 points in one un-chunked call");
   if (sp_in == SPACE_DIRECT && !digits && base.layout == TTN_LAYOUT_SOA && n_chunks > 1)
     return fail(TTN_ERR_UNSUPPORTED, "SOA device coordinates with a host output buffer are not supported; use AOS");
-  std::vector<cudaEvent_t> ev(2 * (size_t)n_chunks, nullptr);
-  auto cleanup_events = [&]() {
-    for (auto e : ev)
-      if (e) cudaEventDestroy(e);
-  };
+  // per-chunk timing events, destroyed on EVERY exit path (TTN_CUDA returns early on allocation failures)
+  struct EventSet {
+    std::vector<cudaEvent_t> v;
+    ~EventSet() {
+      for (auto e : v)
+        if (e) cudaEventDestroy(e);
+    }
+  } evs;
+  evs.v.assign(2 * (size_t)n_chunks, nullptr);
+  std::vector<cudaEvent_t>& ev = evs.v;
   const int n_streams = chunked ? 3 : 1;
   // pending D2H of a staged-pageable output: (destination, bytes) per stream, drained before the slot is reused
   struct Pending {
@@ -988,7 +993,6 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       for (int32_t v : hn) opts->n_refined += v;
     }
   }
-  cleanup_events();
   opts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   return rc;
 }
