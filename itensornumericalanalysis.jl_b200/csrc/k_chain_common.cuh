@@ -29,13 +29,25 @@ struct __align__(16) Digit2 {
   uint32_t wv;   // (site << 16) | (word << 8) | stride
 };
 
+// (w1:w0) += val << (64 * hi + sh) as ONE 128-bit number: a radix-3 field (several digits, each adding v * 3^i) may
+// straddle the two stream words, and the partial sums must carry across the boundary.
+__device__ __forceinline__ void stream_add128(uint64_t& w0, uint64_t& w1, uint64_t val, uint32_t sh, bool hi) {
+  if (hi) {
+    w1 += val << sh;
+  } else {
+    const uint64_t lo = val << sh;
+    w0 += lo;
+    w1 += (sh ? (val >> (64 - sh)) : 0ull) + (w0 < lo ? 1ull : 0ull);
+  }
+}
+
 // base 3 / 4 digit entry for the branch-free form of the greedy loop (32 bytes).  With strictly increasing
 // thresholds thr[1] < thr[2] < thr[3] the loop "largest v with x >= thr[v]" (abstractindexmap.jl:121-138) picks
 // v = (x >= thr[1]) + (x >= thr[2]) + (x >= thr[3]); thresholds a base does not have are +inf.
 struct __align__(16) Digit4 {
   double t1, t2, t3;
-  uint32_t sh;   // shift inside the word
-  uint32_t wv;   // (base << 24) | (site << 16) | (word << 8) | stride
+  uint32_t sh;   // (stride << 8) | shift inside the word   (radix-3 fields: stride up to 3^12)
+  uint32_t wv;   // (base << 24) | (site << 16) | (word << 8)
 };
 __device__ __forceinline__ Digit4 make_digit4(const DigitTable& dg, int i) {
   const DigitEntry e = dg.entries[i];
@@ -43,14 +55,14 @@ __device__ __forceinline__ Digit4 make_digit4(const DigitTable& dg, int i) {
   d4.t1 = e.base > 1 ? dg.thr[e.thr_off + 1] : __longlong_as_double(0x7ff0000000000000ll);
   d4.t2 = e.base > 2 ? dg.thr[e.thr_off + 2] : __longlong_as_double(0x7ff0000000000000ll);
   d4.t3 = e.base > 3 ? dg.thr[e.thr_off + 3] : __longlong_as_double(0x7ff0000000000000ll);
-  d4.sh = (uint32_t)e.shift;
-  d4.wv = ((uint32_t)e.base << 24) | ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8) | (uint32_t)e.stride;
+  d4.sh = ((uint32_t)e.stride << 8) | (uint32_t)e.shift;
+  d4.wv = ((uint32_t)e.base << 24) | ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8);
   return d4;
 }
 template <int NP>
 __device__ __forceinline__ void k1_digit4(const Digit4 e, const DigitTable& dg, const CoordSource& src, int64_t p0, int64_t step,
                                           double (&x)[NP], uint64_t (&w0)[NP], uint64_t (&w1)[NP], int* err) {
-  const uint32_t stride = e.wv & 0xffu;
+  const uint32_t stride = e.sh >> 8, sh = e.sh & 0xffu;
   const bool hi = ((e.wv >> 8) & 0xffu) != 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
@@ -62,9 +74,7 @@ __device__ __forceinline__ void k1_digit4(const Digit4 e, const DigitTable& dg, 
       v = (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3;
       x[k] = __dsub_rn(x[k], g3 ? e.t3 : (g2 ? e.t2 : (g1 ? e.t1 : 0.0)));
     }
-    const uint64_t bb = (uint64_t)(v * stride) << e.sh;
-    if (hi) w1[k] += bb;
-    else w0[k] += bb;
+    stream_add128(w0[k], w1[k], (uint64_t)(v * stride), sh, hi);
   }
 }
 
@@ -83,9 +93,7 @@ __device__ __forceinline__ void k1_generic_site(const DigitTable& dg, const Coor
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     const int v = src.digits ? given_digit(src, p0 + k * step, dg.n_sites, e.site, e.base, err) : greedy_digit(x[k], thr, e.base);
-    const uint64_t bb = (uint64_t)(uint32_t)(v * e.stride) << e.shift;
-    if (e.word) w1[k] += bb;
-    else w0[k] += bb;
+    stream_add128(w0[k], w1[k], (uint64_t)(uint32_t)(v * e.stride), (uint32_t)e.shift, e.word != 0);
   }
 }
 

@@ -56,29 +56,35 @@ struct ChainImage {
 // exactly the same packed bit stream read k*bits0 bits at a time — so K1 and the run fast path are
 // untouched while a point needs 1/k as many matrix-vector products.  Products are accumulated in
 // long double and rounded once.  Needs (#positions) % k == 0 and >= 2k positions.
-static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int bits0, int kL, int kR, int kLh, int kRh) {
+static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, int kL, int kR, int kLh, int kRh) {
   // positions: leaf group = leaf + steps[0, kL-1), middle groups of k steps, root group =
   // steps[T-(kR-1), T) + root.  kL and kR may be much larger than k ("deep" leaf / root tables of
   // 2^(bits0 kL) vectors, kept in global memory): those are built with vector products only, one
   // member at a time (rounded to double per member, dot products accumulated in long double).
   typedef long double ld;
   const size_t M = (size_t)CHI * CHI;
-  const int T = (int)a.steps.size(), S0 = a.nsl, SK = 1 << (bits0 * k);
+  // Slice indices are mixed-radix numbers in radix S0 = a.nsl (member i of a group has weight S0^i): for S0 = 2 / 4
+  // that is the bit-field form, for S0 = 3 (base-3 digits, one site index per vertex) the fields are dense — 3^k
+  // classes per position in a ceil(log2 3^k)-bit field, 3^12 rows in a 2^20-row table budget.
+  const int T = (int)a.steps.size(), S0 = a.nsl;
+  int SK = 1, pk = 1;
+  for (int i = 0; i < k; ++i) pk *= S0;
+  while (SK < pk) SK <<= 1; // classes per merged position, padded to a power of two (rows >= S0^k stay zero)
   ChainImage m;
   m.nsl = SK;
   // ---- leaf table: T_i[s + (b << bits0 i)] = T_{i-1}[s] . E_{i-1}[b]
   {
     std::vector<double> cur((size_t)S0 * CHI);
     for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.leaf[i];
-    size_t n_cur = (size_t)1 << bits0;
+    size_t n_cur = (size_t)S0;
     for (int i = 1; i < kLh; ++i) { // levels kLh .. kL - 1 are added on the device (extend_deep_tables)
-      std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
+      std::vector<double> nxt(n_cur * (size_t)S0 * CHI, 0.0);
       const std::vector<double>& E = a.steps[i - 1];
       for (int bsl = 0; bsl < S0; ++bsl) {
         const double* B = E.data() + (size_t)bsl * M;
         for (size_t sidx = 0; sidx < n_cur; ++sidx) {
           const double* A = cur.data() + sidx * CHI;
-          double* C = nxt.data() + (sidx + ((size_t)bsl << (bits0 * i))) * CHI;
+          double* C = nxt.data() + (sidx + (size_t)bsl * n_cur) * CHI;
           ld acc[32];
           for (int j = 0; j < CHI; ++j) acc[j] = 0.0L;
           for (int kk = 0; kk < CHI; ++kk) {
@@ -90,18 +96,19 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
         }
       }
       cur.swap(nxt);
-      n_cur <<= bits0;
+      n_cur *= S0;
     }
+    if (cur.size() < (size_t)SK * CHI) cur.resize((size_t)SK * CHI, 0.0); // the kernels stage SK rows of a uniform group
     m.leaf.swap(cur);
   }
   // ---- middle groups: matrix products in long double, rounded once
-  auto extend = [&](const std::vector<ld>& cur, int n_cur, const std::vector<double>& E, int member) {
-    std::vector<ld> nxt((size_t)n_cur * (1 << bits0) * M, 0.0L);
+  auto extend = [&](const std::vector<ld>& cur, int n_cur, const std::vector<double>& E) {
+    std::vector<ld> nxt((size_t)n_cur * S0 * M, 0.0L);
     for (int sidx = 0; sidx < n_cur; ++sidx)
       for (int bsl = 0; bsl < S0; ++bsl) {
         const ld* A = cur.data() + (size_t)sidx * M;
         const double* B = E.data() + (size_t)bsl * M;
-        ld* C = nxt.data() + (size_t)(sidx + (bsl << (bits0 * member))) * M;
+        ld* C = nxt.data() + (size_t)(sidx + bsl * n_cur) * M;
         for (int i = 0; i < CHI; ++i)
           for (int kk = 0; kk < CHI; ++kk) {
             const ld av = A[(size_t)i * CHI + kk];
@@ -114,35 +121,41 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
   const int G = (T - (kL - 1) - (kR - 1)) / k;
   for (int g = 0; g < G; ++g) {
     const int t0 = kL - 1 + g * k;
-    std::vector<ld> cur((size_t)(1 << bits0) * M, 0.0L);
+    std::vector<ld> cur((size_t)S0 * M, 0.0L);
     for (int sl = 0; sl < S0; ++sl)
       for (size_t i = 0; i < M; ++i) cur[(size_t)sl * M + i] = a.steps[t0][(size_t)sl * M + i];
-    int n_cur = 1 << bits0;
+    int n_cur = S0;
     for (int i = 1; i < k; ++i) {
-      cur = extend(cur, n_cur, a.steps[t0 + i], i);
-      n_cur <<= bits0;
+      cur = extend(cur, n_cur, a.steps[t0 + i]);
+      n_cur *= S0;
     }
-    std::vector<double> E((size_t)SK * M);
-    for (size_t i = 0; i < E.size(); ++i) E[i] = (double)cur[i];
+    std::vector<double> E((size_t)SK * M, 0.0);
+    for (size_t i = 0; i < cur.size(); ++i) E[i] = (double)cur[i];
     m.steps.push_back(std::move(E));
   }
   // ---- root table, built from the root backwards (the member nearest the leaf owns the LOW bits):
   // R_j[s + (idx << bits0)][i] = sum_l E_j[s][i][l] R_{j+1}[idx][l]
   {
-    const size_t SR = (size_t)1 << (bits0 * kRh); // members kR - kRh - 1 .. 0 are added on the device
+    size_t SRr = 1; // members kR - kRh - 1 .. 0 are added on the device
+    for (int i = 0; i < kRh; ++i) SRr *= S0;
+    size_t SRp = 1;
+    while (SRp < SRr) SRp <<= 1;
+    // table o starts at row o * SR with SR a power of two: the kernels address the second (imaginary-part) table of a
+    // complex network as root + (CHI << root_bits); a uniform group is staged with SK rows
+    const size_t SR = std::max(SRp, (size_t)SK);
     m.root.assign((size_t)nout * SR * CHI, 0.0);
     for (int o = 0; o < nout; ++o) {
       std::vector<double> cur((size_t)S0 * CHI);
       for (size_t i = 0; i < cur.size(); ++i) cur[i] = a.root[(size_t)o * S0 * CHI + i];
-      size_t n_cur = (size_t)1 << bits0;
+      size_t n_cur = (size_t)S0;
       for (int j = kR - 2; j >= kR - kRh; --j) { // step index T - (kR - 1) + j
         const std::vector<double>& E = a.steps[T - (kR - 1) + j];
-        std::vector<double> nxt(n_cur * ((size_t)1 << bits0) * CHI, 0.0);
+        std::vector<double> nxt(n_cur * (size_t)S0 * CHI, 0.0);
         for (int sl = 0; sl < S0; ++sl) {
           const double* A = E.data() + (size_t)sl * M;
           for (size_t idx = 0; idx < n_cur; ++idx) {
             const double* Rv = cur.data() + idx * CHI;
-            double* C = nxt.data() + ((size_t)sl + (idx << bits0)) * CHI;
+            double* C = nxt.data() + ((size_t)sl + idx * S0) * CHI;
             for (int i = 0; i < CHI; ++i) {
               ld acc = 0.0L;
               for (int l = 0; l < CHI; ++l) acc += (ld)A[(size_t)i * CHI + l] * (ld)Rv[l];
@@ -151,7 +164,7 @@ static ChainImage merge_groups(const ChainImage& a, int CHI, int nout, int k, in
           }
         }
         cur.swap(nxt);
-        n_cur <<= bits0;
+        n_cur *= S0;
       }
       std::copy(cur.begin(), cur.end(), m.root.begin() + (size_t)o * SR * CHI);
     }
@@ -209,9 +222,9 @@ __device__ __forceinline__ void dd2_mac(dd2& acc, double a, double b) {
   acc.lo = __dadd_rn(acc.lo, __dadd_rn(err, e));
   acc.hi = t;
 }
-// nxt[s + (b << shift)][j] = sum_k cur[s][k] E[b][k][j]
+// nxt[s + b * n_cur][j] = sum_k cur[s][k] E[b][k][j]
 __global__ void deep_leaf_extend_kernel(const double* __restrict__ cur, size_t n_cur, const double* __restrict__ E, int S0,
-                                        int shift, int CHI, double* __restrict__ nxt) {
+                                        int CHI, double* __restrict__ nxt) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cur * S0 * CHI) return;
   const int j = (int)(idx % CHI), b = (int)((idx / CHI) % S0);
@@ -220,11 +233,11 @@ __global__ void deep_leaf_extend_kernel(const double* __restrict__ cur, size_t n
   const double* B = E + (size_t)b * CHI * CHI + j;
   dd2 acc{0.0, 0.0};
   for (int k = 0; k < CHI; ++k) dd2_mac(acc, A[k], __ldg(B + (size_t)k * CHI));
-  nxt[(sidx + ((size_t)b << shift)) * CHI + j] = __dadd_rn(acc.hi, acc.lo);
+  nxt[(sidx + (size_t)b * n_cur) * CHI + j] = __dadd_rn(acc.hi, acc.lo);
 }
-// nxt[sl + (idx << bits0)][i] = sum_l E[sl][i][l] cur[idx][l]
+// nxt[sl + idx * S0][i] = sum_l E[sl][i][l] cur[idx][l]
 __global__ void deep_root_extend_kernel(const double* __restrict__ cur, size_t n_cur, const double* __restrict__ E, int S0,
-                                        int bits0, int CHI, double* __restrict__ nxt) {
+                                        int CHI, double* __restrict__ nxt) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_cur * S0 * CHI) return;
   const int i = (int)(idx % CHI), sl = (int)((idx / CHI) % S0);
@@ -233,11 +246,16 @@ __global__ void deep_root_extend_kernel(const double* __restrict__ cur, size_t n
   const double* Rv = cur + ridx * CHI;
   dd2 acc{0.0, 0.0};
   for (int l = 0; l < CHI; ++l) dd2_mac(acc, __ldg(A + l), Rv[l]);
-  nxt[((size_t)sl + (ridx << bits0)) * CHI + i] = __dadd_rn(acc.hi, acc.lo);
+  nxt[((size_t)sl + ridx * (size_t)S0) * CHI + i] = __dadd_rn(acc.hi, acc.lo);
 }
 
-static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nout, int bits0, int kLh, int kL, int kRh,
-                              int kR, ChainMmaDev& c) {
+static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nout, int kLh, int kL, int kRh,
+                              int kR, int SK, ChainMmaDev& c) {
+  auto ipow = [](size_t b, int e) {
+    size_t r = 1;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+  };
   const int S0 = a.nsl, T = (int)a.steps.size();
   const size_t M = (size_t)CHI * CHI;
   double* d_E = nullptr;
@@ -245,7 +263,7 @@ static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nou
   int rc = TTN_OK;
   auto run = [&](bool leaf, const double* start, size_t n_start, int lv0, int lv1, double** result) -> int {
     // levels lv0 .. lv1 - 1; ping-pong between two buffers of the final size, the last level lands in `fin`
-    const size_t rows_fin = n_start << (bits0 * (lv1 - lv0));
+    const size_t rows_fin = n_start * ipow((size_t)S0, lv1 - lv0);
     double *fin = nullptr, *tmp = nullptr;
     TTN_CUDA(cudaMalloc(&fin, rows_fin * CHI * 8));
     p->allocs.push_back(fin);
@@ -263,11 +281,11 @@ static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nou
       cudaMemcpy(d_E, a.steps[step].data(), (size_t)S0 * M * 8, cudaMemcpyHostToDevice);
       const size_t total = n_cur * S0 * CHI;
       const unsigned grid = (unsigned)((total + 255) / 256);
-      if (leaf) deep_leaf_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, bits0 * (lv0 + q), CHI, dst);
-      else deep_root_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, bits0, CHI, dst);
+      if (leaf) deep_leaf_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, CHI, dst);
+      else deep_root_extend_kernel<<<grid, 256>>>(cur, n_cur, d_E, S0, CHI, dst);
       cudaDeviceSynchronize(); // d_E is reused by the next level
       cur = dst;
-      n_cur <<= bits0;
+      n_cur *= S0;
     }
     cudaFree(tmp);
     const cudaError_t e = cudaGetLastError();
@@ -280,25 +298,31 @@ static int extend_deep_tables(ttn_plan* p, const ChainImage& a, int CHI, int nou
   };
   if (kL > kLh) {
     double* fin = nullptr;
-    rc = run(true, c.leaf, (size_t)1 << (bits0 * kLh), kLh, kL, &fin);
+    rc = run(true, c.leaf, ipow((size_t)S0, kLh), kLh, kL, &fin);
     if (rc == TTN_OK) c.leaf = fin;
   }
   if (rc == TTN_OK && kR > kRh) {
     // nout tables back to back: [o][2^(bits0 kR)][CHI]
-    const size_t rows_h = (size_t)1 << (bits0 * kRh), rows_f = (size_t)1 << (bits0 * kR);
+    const size_t rows_h = ipow((size_t)S0, kRh), rows_f = ipow((size_t)S0, kR);
+    auto pow2_ceil = [](size_t x) {
+      size_t r = 1;
+      while (r < x) r <<= 1;
+      return r;
+    };
+    const size_t stride_h = std::max(pow2_ceil(rows_h), (size_t)SK), stride_f = pow2_ceil(rows_f); // rows between two tables
     double* all = nullptr;
     if (nout == 1) {
       rc = run(false, c.root, rows_h, kRh, kR, &all);
     } else {
-      if (cudaMalloc(&all, (size_t)nout * rows_f * CHI * 8) != cudaSuccess) {
+      if (cudaMalloc(&all, (size_t)nout * stride_f * CHI * 8) != cudaSuccess) {
         set_error("deep tables: out of device memory");
         rc = TTN_ERR_NOMEM;
       } else {
         p->allocs.push_back(all);
         for (int o = 0; o < nout && rc == TTN_OK; ++o) {
           double* one = nullptr;
-          rc = run(false, c.root + (size_t)o * rows_h * CHI, rows_h, kRh, kR, &one);
-          if (rc == TTN_OK) cudaMemcpy(all + (size_t)o * rows_f * CHI, one, rows_f * CHI * 8, cudaMemcpyDeviceToDevice);
+          rc = run(false, c.root + (size_t)o * stride_h * CHI, rows_h, kRh, kR, &one); // host stride: merge_groups' SR
+          if (rc == TTN_OK) cudaMemcpy(all + (size_t)o * stride_f * CHI, one, rows_f * CHI * 8, cudaMemcpyDeviceToDevice);
           if (rc == TTN_OK) { // `one` was pushed to p->allocs by run(): release it now
             p->allocs.pop_back();
             cudaFree(one);
@@ -327,12 +351,47 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   const int CHI = cplx ? mma_width(2 * maxchi) : mma_width(maxchi);
   const int H = CHI / 2; // complex: row = [re(H) | im(H)]
   if (CHI == 0 || maxsl > 4) return TTN_OK;
-  const int NSL0 = maxsl == 3 ? 4 : maxsl; // slices per vertex; a base-3 index takes a 2-bit field (slice 3: zero matrix, never selected)
-  const int bits0 = NSL0 <= 1 ? 0 : (NSL0 <= 2 ? 1 : 2); // stream bits per VERTEX
+  p->v6_teams = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
+  // Base-3 chains (every site-carrying vertex has ONE site index of dimension 3): RADIX mode — the slice indices of a
+  // group of vertices are packed as one radix-3 number (3^3 = 27 classes in a 5-bit field per round, 3^12 rows in a
+  // 2^20-row table) instead of one 2-bit field per vertex (16 classes per round of which 9 are populated, 4^10 rows
+  // of which 3^10 are reachable): a 60-site chain runs 12 rounds per point instead of 20.  Needs the team-sorted
+  // kernel (the only one that reads odd field widths from the 128-bit stream) and a chain that splits into whole
+  // groups; anything else keeps the 2-bit fields.  TTN_MMA_RADIX=0 switches it off.
+  bool radix = maxsl == 3 && p->v6_teams != 0 && !(getenv("TTN_MMA_RADIX") && atoi(getenv("TTN_MMA_RADIX")) == 0) && !getenv("TTN_MMA_MERGE");
+  for (int v = 0; v < n && radix; ++v) radix = p->nslices[v] == 3 || p->nslices[v] == 1;
+  int rk = 0, rkL = 0, rkR = 0; // radix: vertices per round, in the leaf table, in the root table
+  if (radix) {
+    auto max_k = [](int bitsb) { // largest k with 3^k <= 2^bitsb
+      int k = 0;
+      double pw = 1.0;
+      while (pw * 3.0 <= std::ldexp(1.0, bitsb)) pw *= 3.0, ++k;
+      return k;
+    };
+    rk = CHI <= 16 ? 3 : 2;
+    int deep_bits = 20;
+    if (const char* e = getenv("TTN_MMA_DEEP")) deep_bits = std::min(atoi(e), 22);
+    const int lb = deep_bits - (CHI >= 32 ? 1 : 0) + (CHI <= 8 ? 1 : 0), rb = lb - (cplx ? 1 : 0);
+    rkL = deep_bits > 0 ? std::max(rk, std::min(max_k(lb), n / 2)) : rk;
+    rkR = deep_bits > 0 ? std::max(rk, std::min(max_k(rb), n - rkL)) : rk;
+    const int mid = n - rkL - rkR;
+    const int delta = mid >= 0 ? (rk - mid % rk) % rk : 0;
+    if (mid >= 0 && rkR - delta >= rk) rkR -= delta;
+    radix = n >= 2 * rk && n - rkL - rkR >= 0 && (n - rkL - rkR) % rk == 0;
+  }
+  const int NSL0 = radix ? 3 : (maxsl == 3 ? 4 : maxsl); // slices per vertex; without radix mode a base-3 index takes a
+                                                         // 2-bit field (slice 3: zero matrix, never selected)
+  const int bits0 = NSL0 <= 1 ? 0 : (NSL0 <= 2 ? 1 : 2); // stream bits per VERTEX (bit-field mode)
+  auto ceil_log2 = [](double x) {
+    int b = 0;
+    while (std::ldexp(1.0, b) < x) ++b;
+    return b;
+  };
+  // stream bits of a field holding k vertices
+  auto fbits = [&](int k) { return radix ? ceil_log2(std::pow(3.0, k)) : bits0 * k; };
   // group merging (merge_groups): k vertices per stream position when the slice indices are bit
   // fields, the merged position has <= 16 slices and one position's matrices stay <= 32 KB (one
   // ring stage).  TTN_MMA_MERGE caps k (0 or 1: one vertex per position).
-  p->v6_teams = getenv("TTN_MMA_V6") ? atoi(getenv("TTN_MMA_V6")) : 3;
   int kmerge = 1;
   {
     // measured on B200 (scripts/merge_probe.py): 4 > 3 > 2 > 1 for binary chains; TTN_MMA_MERGE=k
@@ -345,7 +404,8 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     // the team-sorted kernel (v6) reads site matrices straight from L2 into registers: no ring-stage
     // limit and up to 32 slices per position; the ring kernels take <= 16 slices and <= 32 KB per position
     const bool v6_on = p->v6_teams != 0;
-    if (NSL0 == 2 || NSL0 == 4)
+    if (radix) kmerge = rk;
+    else if (NSL0 == 2 || NSL0 == 4)
       for (int kk : cand) {
         const int sb = bits0 * kk;
         const bool fits = v6_on ? sb <= (CHI <= 16 ? 5 : 4) : (sb <= 4 && ((size_t)1 << sb) * CHI * CHI * 8 <= 32 * 1024);
@@ -370,7 +430,10 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
     // the host loop took 2 s).  TTN_MMA_DEEP=b overrides (0 disables).
     int deep_bits = (n * bits0 <= 32) ? 16 : 20;
     if (const char* e = getenv("TTN_MMA_DEEP")) deep_bits = std::min(atoi(e), 22);
-    if (merge && v6_on && deep_bits > 0) {
+    if (radix) {
+      kL = rkL;
+      kR = rkR;
+    } else if (merge && v6_on && deep_bits > 0) {
       const int lb = deep_bits - (CHI >= 32 ? 1 : 0) + (CHI <= 8 ? 1 : 0), rb = lb - (cplx ? 1 : 0);
       kL = std::max(kmerge, std::min(lb / bits0, n / 2));
       kR = std::max(kmerge, std::min(rb / bits0, n - kL));
@@ -405,7 +468,9 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   const int n_steps_p = merge ? kL + kR + (n - kL - kR + kmerge - 1) / kmerge * kmerge - 2 : (n_steps + spr - 1) / spr * spr;
   const int root_pos = n >= 2 ? 1 + n_steps_p : 0; // in vertices
   const int n_pos = root_pos + 1;
-  const int n_words = bits0 == 0 ? 0 : (n_pos * bits0 + 63) / 64;
+  const int grp_bits = radix ? slice_bits(32 >> (kmerge == 2 ? 1 : 0)) : bits0 * kmerge; // radix: 27 -> 5 bits, 9 -> 4 bits
+  const int n_groups_mid = merge ? (n_steps_p + 2 - kL - kR) / kmerge : 0;
+  const int n_words = radix ? (fbits(kL) + n_groups_mid * grp_bits + fbits(kR) + 63) / 64 : (bits0 == 0 ? 0 : (n_pos * bits0 + 63) / 64);
   if (n_words > 2) return TTN_OK;
 
   std::vector<int> order(n), pos_of(n);
@@ -524,12 +589,13 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   int NSL = NSL0, bits = bits0;
   if (merge) {
     // host levels: up to 2^10 rows per table; the rest of a deep table is built on the device
-    const int kLh = std::min(kL, std::max(kmerge, 10 / bits0)), kRh = std::min(kR, std::max(kmerge, 10 / bits0));
-    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, bits0, kL, kR, kLh, kRh);
+    const int khost = radix ? 6 : 10 / bits0; // 3^6 = 729 rows
+    const int kLh = std::min(kL, std::max(kmerge, khost)), kRh = std::min(kR, std::max(kmerge, khost));
+    const ChainImage mg = merge_groups(im, CHI, nout, kmerge, kL, kR, kLh, kRh);
     if ((rc = upload_chain_image(p, mg, CHI, c))) return rc;
-    if ((kL > kLh || kR > kRh) && (rc = extend_deep_tables(p, im, CHI, nout, bits0, kLh, kL, kRh, kR, c))) return rc;
+    if ((kL > kLh || kR > kRh) && (rc = extend_deep_tables(p, im, CHI, nout, kLh, kL, kRh, kR, mg.nsl, c))) return rc;
     NSL = mg.nsl;
-    bits = bits0 * kmerge;
+    bits = grp_bits;
     spr = 1;
     c.n_steps = (int)mg.steps.size();
   } else if (p->cmma_plain_ok) {
@@ -543,8 +609,8 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   }
   c.merged = merge ? kmerge : 0;
   c.k1_generic = k1_generic_mode(d);
-  c.leaf_bits = merge ? bits0 * kL : bits0; // stream bits the leaf / root group consumes
-  c.root_bits = merge ? bits0 * kR : bits0;
+  c.leaf_bits = merge ? fbits(kL) : bits0; // stream bits the leaf / root group consumes
+  c.root_bits = merge ? fbits(kR) : bits0;
   c.nsl = NSL;
   c.bits = bits;
   c.per_word = bits == 0 ? (1 << 30) : 64 / bits;
@@ -559,10 +625,24 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   std::vector<DigitEntry> ent(std::max(d->n_sites, 1));
   if (d->n_sites > 0) {
     TTN_CUDA(cudaMemcpy(ent.data(), p->digits.entries, sizeof(DigitEntry) * d->n_sites, cudaMemcpyDeviceToHost));
+    p->cmma_site_fbits.assign(d->n_sites, std::max(bits0, 1));
     for (int i = 0; i < d->n_sites; ++i) {
-      const int bitpos = pos_of[ent[i].vertex] * bits0;
-      ent[i].word = bits0 ? bitpos / 64 : 0;
-      ent[i].shift = bits0 ? bitpos % 64 : 0;
+      int bitpos = pos_of[ent[i].vertex] * bits0;
+      if (radix) {
+        // field of the vertex's group and its weight inside it: leaf table | middle groups | root table
+        const int q = pos_of[ent[i].vertex]; // chain position (radix mode has no identity padding)
+        int field, idx, fb;
+        if (q < kL) field = 0, idx = q, fb = fbits(kL);
+        else if (q >= n - kR) field = fbits(kL) + n_groups_mid * grp_bits, idx = q - (n - kR), fb = fbits(kR);
+        else field = fbits(kL) + ((q - kL) / kmerge) * grp_bits, idx = (q - kL) % kmerge, fb = grp_bits;
+        int mult = 1;
+        for (int t = 0; t < idx; ++t) mult *= 3;
+        ent[i].stride *= mult;
+        bitpos = field;
+        p->cmma_site_fbits[ent[i].site] = fb;
+      }
+      ent[i].word = (bits0 || radix) ? bitpos / 64 : 0;
+      ent[i].shift = (bits0 || radix) ? bitpos % 64 : 0;
     }
     DigitEntry* d_ent;
     TTN_CUDA(cudaMalloc(&d_ent, sizeof(DigitEntry) * d->n_sites));
@@ -610,12 +690,12 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
   // Same packed stream (built only when both images pad the chain identically), same digits, same kernel instance.
   p->cmma_light_ok = false;
   const bool light_on = !(getenv("TTN_MMA_LIGHT") && atoi(getenv("TTN_MMA_LIGHT")) == 0); // 0: host-buffer calls run the deep image too
-  if (light_on && merge && (kL > kmerge || kR > kmerge)) {
+  if (light_on && merge && !radix && (kL > kmerge || kR > kmerge)) {
     const int n_steps_u = kmerge + kmerge + (n - 2 * kmerge + kmerge - 1) / kmerge * kmerge - 2;
     if (n_steps_u == n_steps_p) {
       ChainMmaDev& q = p->cmma_light;
       q = c; // layout, run fast path, k1 mode are shared; (leaf, root, frags, rounds) replaced below
-      const ChainImage mu = merge_groups(im, CHI, nout, kmerge, bits0, kmerge, kmerge, kmerge, kmerge);
+      const ChainImage mu = merge_groups(im, CHI, nout, kmerge, kmerge, kmerge, kmerge, kmerge);
       if ((rc = upload_chain_image(p, mu, CHI, q))) return rc;
       q.n_steps = (int)mu.steps.size();
       q.n_rounds = q.n_steps;

@@ -740,6 +740,7 @@ int build_chain_table(ttn_plan* p, const ttn_desc* d) {
   TTN_CUDA(cudaMemcpy(d_img, im.image.data(), im.image.size() * 8, cudaMemcpyHostToDevice));
   c.image = d_img;
   p->ctab_flops_exec = im.flops_exec;
+  p->ctab_bits0 = im.bits0;
 
   // own copy of the digit table: (word, shift) = bit position of the vertex in THIS kernel's stream
   const int bits0 = im.bits0;

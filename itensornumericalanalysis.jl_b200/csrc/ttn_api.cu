@@ -1371,8 +1371,9 @@ int ttn_debug_table_image(const ttn_desc* desc, int32_t budget_kb, int32_t* meta
 
  * description (its digit = the field of ceil(log2(dim)) bits starting there).  tests/test_gpu_round2.py compares these integers with the CPU greedy loop. */
 int ttn_debug_slice_stream(ttn_plan* plan, const double* coords, int64_t npts, int32_t kernel, uint64_t* words_out,
-                           int32_t* site_bit) {
-  if (!plan || !coords || !words_out || !site_bit || npts <= 0) return fail(TTN_ERR_INVALID, "null / empty argument");
+                           int32_t* site_bit, int32_t* site_stride, int32_t* site_fbits) {
+  if (!plan || !coords || !words_out || !site_bit || !site_stride || !site_fbits || npts <= 0)
+    return fail(TTN_ERR_INVALID, "null / empty argument");
   if (!plan->replicas.empty()) plan = plan->replicas[0];
   const DigitTable* dt = nullptr;
   if (kernel == TTN_KERNEL_DMMA && plan->cmma_ok && chain_team_applicable(plan)) dt = &plan->digits_mma;
@@ -1407,10 +1408,11 @@ int ttn_debug_slice_stream(ttn_plan* plan, const double* coords, int64_t npts, i
   if (rc) return rc;
   std::vector<DigitEntry> ent((size_t)std::max(ns, 1));
   TTN_CUDA(cudaMemcpy(ent.data(), dt->entries, sizeof(DigitEntry) * (size_t)ns, cudaMemcpyDeviceToHost));
+  // digit of site s = (field / stride) % dim(s), field = site_fbits[s] stream bits starting at bit site_bit[s]
   for (int i = 0; i < ns; ++i) {
-    int lg = 0;
-    while ((1 << lg) < ent[i].stride) ++lg;
-    site_bit[ent[i].site] = ent[i].word * 64 + ent[i].shift + lg;
+    site_bit[ent[i].site] = ent[i].word * 64 + ent[i].shift;
+    site_stride[ent[i].site] = ent[i].stride;
+    site_fbits[ent[i].site] = kernel == TTN_KERNEL_DMMA ? plan->cmma_site_fbits[ent[i].site] : plan->ctab_bits0;
   }
   return TTN_OK;
 }

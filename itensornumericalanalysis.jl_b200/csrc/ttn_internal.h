@@ -216,6 +216,7 @@ struct ttn_plan {
   std::vector<void*> allocs;
   ttn::DigitTable digits{};
   ttn::DigitTable digits_mma{}; // same table, (word, shift) for the DMMA kernels' stream layout
+  std::vector<int32_t> cmma_site_fbits; // per site index: width of the stream field its digit lives in (test hook)
   ttn::TreeDev tree{};
   ttn::ChainDev chain{};
   bool chain_ok = false;
@@ -236,6 +237,7 @@ struct ttn_plan {
   bool ctab_ok = false;
   ttn::DigitTable digits_tab{}; // same table, (word, shift) for the table kernel's stream layout
   double ctab_flops_exec = 0.0;
+  int ctab_bits0 = 1;           // stream bits per vertex of the table kernel's image (test hook)
   ttn::TreeGemmDev tgemm{};
   bool tgemm_ok = false;
   std::vector<int64_t> tg_frag_off;

@@ -119,21 +119,31 @@ def test_baseline_config5_instance(variant, monkeypatch):
 
 def _slice_stream_digits(plan, coords, kernel):
     """The digits the kernel's FUSED K1 really used (ttn_debug_slice_stream: a test hook of libttneval.so that is not
-    part of include/ttneval.h) as a (npts, n_sites) uint8 array in the description's site order."""
+    part of include/ttneval.h) as a (npts, n_sites) uint8 array in the description's site order.  A site's digit is
+    (field // stride) % dim, field = a few stream bits (a bit / 2-bit field per vertex, or a radix-3 group field)."""
     L = _capi.lib()
     fn = L.ttn_debug_slice_stream
-    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     fn.restype = C.c_int
     coords = np.ascontiguousarray(coords, dtype=np.float64)
     npts, ns = coords.shape[0], len(plan.packed.site_dim)
     words = np.zeros((npts, 2), dtype=np.uint64)
-    site_bit = np.zeros(ns, dtype=np.int32)
+    site_bit, site_stride, site_fbits = (np.zeros(ns, dtype=np.int32) for _ in range(3))
     _capi.check(fn(plan._h, coords.ctypes.data_as(C.c_void_p), npts, kernel, words.ctypes.data_as(C.c_void_p),
-                   site_bit.ctypes.data_as(C.c_void_p)))
+                   site_bit.ctypes.data_as(C.c_void_p), site_stride.ctypes.data_as(C.c_void_p),
+                   site_fbits.ctypes.data_as(C.c_void_p)))
     out = np.empty((npts, ns), dtype=np.uint8)
-    for s_, b in enumerate(site_bit):
-        mask = 1 if plan.packed.site_dim[s_] <= 2 else 3      # base 3 / 4 digits sit in 2-bit fields
-        out[:, s_] = (words[:, b // 64] >> np.uint64(b % 64)) & np.uint64(mask)
+    lo, hi = words[:, 0], words[:, 1]
+    for s_ in range(ns):
+        b, fb = int(site_bit[s_]), int(site_fbits[s_])
+        if b >= 64:
+            field = hi >> np.uint64(b - 64)
+        elif b == 0:
+            field = lo.copy()
+        else:
+            field = (lo >> np.uint64(b)) | (hi << np.uint64(64 - b))
+        field &= np.uint64((1 << fb) - 1)
+        out[:, s_] = (field // np.uint64(site_stride[s_])) % np.uint64(plan.packed.site_dim[s_])
     return out
 
 
