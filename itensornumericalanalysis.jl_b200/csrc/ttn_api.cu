@@ -38,7 +38,109 @@ static int fail(int code, const std::string& msg) {
   return code;
 }
 
-static int build_plan(ttn_plan* p, const ttn_desc* d) {
+// ---- vertices with more than two children ------------------------------------------------------------------
+// The per-vertex GEMM tree kernel contracts at most two children per vertex (a Khatri-Rao GEMM).  A vertex with
+// children c_1 < ... < c_k (k > 2; uniform_tree, test/test_realitensorfunction.jl:129) is BINARISED at plan time:
+// its last two children are hung under a new site-less vertex u whose tensor is the identity
+// T_u[a][b][(a, b)] = 1 — u's message is the Kronecker product of theirs, dimension chi_a chi_b — and v keeps u as
+// its last child; v's own tensor [site..][c_1]..[c_{k-1}][c_k][parent] is untouched, the merged axis (c_{k-1}, c_k)
+// is already contiguous in it.  Repeated until two children remain.  Done only when every new link fits the tree
+// kernel (<= 64 real / 32 complex) and every vertex has <= 8 slices; otherwise the network is left as it is (generic
+// kernel).  The function evaluated is the same; flops_per_point stays the rule of the ORIGINAL network.
+struct BinDesc {
+  ttn_desc d{};
+  std::vector<int32_t> parent, link_dim, site_ptr;
+  std::vector<int64_t> tensor_ptr;
+  std::vector<double> tensors;
+};
+static bool binarize_desc(const ttn_desc* o, BinDesc* b) {
+  const int n = o->n_vertices;
+  if (getenv("TTN_TREE_BINARIZE") && atoi(getenv("TTN_TREE_BINARIZE")) == 0) return false;
+  if (n <= 0 || o->root < 0 || o->root >= n || !o->parent || !o->link_dim || !o->site_ptr || !o->tensor_ptr || !o->tensors) return false;
+  const int NC = o->is_complex ? 2 : 1, WL = 64 / NC;
+  std::vector<std::vector<int>> ch((size_t)n);
+  int maxk = 0;
+  for (int v = 0; v < n; ++v) {
+    const int q = o->parent[v];
+    if (v == o->root) continue;
+    if (q < 0 || q >= n || q == v || o->link_dim[v] < 1) return false;
+    ch[q].push_back(v);
+    maxk = std::max(maxk, (int)ch[q].size());
+  }
+  if (maxk <= 2) return false;
+  for (int v = 0; v < n; ++v) {
+    int64_t ns = 1;
+    for (int si = o->site_ptr[v]; si < o->site_ptr[v + 1]; ++si) ns *= std::max(o->site_dim[si], 1);
+    if (ns > 8 || o->link_dim[v] > WL) return false;
+  }
+  b->parent.assign(o->parent, o->parent + n);
+  b->link_dim.assign(o->link_dim, o->link_dim + n);
+  b->site_ptr.assign(o->site_ptr, o->site_ptr + n + 1);
+  b->tensor_ptr.assign(o->tensor_ptr, o->tensor_ptr + n + 1);
+  const double* T = reinterpret_cast<const double*>(o->tensors);
+  b->tensors.assign(T, T + o->tensor_ptr[n] * NC);
+  for (int v = 0; v < n; ++v) {
+    std::vector<int> cur = ch[v];
+    while (cur.size() > 2) {
+      const int c2 = cur.back(), c1 = cur[cur.size() - 2];
+      const int64_t dim = (int64_t)b->link_dim[c1] * b->link_dim[c2];
+      if (dim > WL) return false;
+      const int u = (int)b->parent.size();
+      b->parent.push_back(v);
+      b->link_dim.push_back((int32_t)dim);
+      b->parent[c1] = b->parent[c2] = u;
+      b->site_ptr.push_back(b->site_ptr.back());
+      const size_t off = b->tensors.size();
+      b->tensors.resize(off + (size_t)dim * dim * NC, 0.0);
+      for (int64_t i = 0; i < dim; ++i) b->tensors[off + (size_t)(i * dim + i) * NC] = 1.0;
+      b->tensor_ptr.push_back(b->tensor_ptr.back() + dim * dim);
+      cur.pop_back();
+      cur.pop_back();
+      cur.push_back(u);
+    }
+  }
+  b->d = *o;
+  b->d.n_vertices = (int32_t)b->parent.size();
+  b->d.parent = b->parent.data();
+  b->d.link_dim = b->link_dim.data();
+  b->d.site_ptr = b->site_ptr.data();
+  b->d.tensor_ptr = b->tensor_ptr.data();
+  b->d.tensors = b->tensors.data();
+  return true;
+}
+
+static int build_plan_impl(ttn_plan* p, const ttn_desc* d);
+
+static int build_plan(ttn_plan* p, const ttn_desc* o) {
+  BinDesc bin;
+  if (!o->parent || o->n_vertices <= 0 || !binarize_desc(o, &bin)) return build_plan_impl(p, o);
+  const int rc = build_plan_impl(p, &bin.d);
+  if (rc != TTN_OK) return rc;
+  // report the network the caller described: vertex count, link dimensions and the flop rule of the ORIGINAL tree
+  const int n = o->n_vertices;
+  std::vector<std::vector<int>> ch((size_t)n);
+  for (int v = 0; v < n; ++v)
+    if (v != o->root) ch[o->parent[v]].push_back(v);
+  double macs = 0.0;
+  int max_link = 1;
+  for (int v = 0; v < n; ++v) {
+    max_link = std::max(max_link, o->link_dim[v]);
+    double rest = o->link_dim[v];
+    for (int c : ch[v]) rest *= o->link_dim[c];
+    for (int c : ch[v]) {
+      macs += rest; // sum_j c_j ... c_k p
+      rest /= o->link_dim[c];
+    }
+  }
+  p->info.n_vertices = n;
+  p->info.max_link_dim = max_link;
+  p->info.flops_per_point = (o->is_complex ? 8.0 : 2.0) * macs;
+  p->info.tensor_bytes = o->tensor_ptr[n] * (o->is_complex ? 2 : 1) * 8;
+  p->binarized = true;
+  return TTN_OK;
+}
+
+static int build_plan_impl(ttn_plan* p, const ttn_desc* d) {
   const int n = d->n_vertices;
   if (d->abi_version != TTN_ABI_VERSION) return fail(TTN_ERR_INVALID, "ttn_desc.abi_version mismatch");
   if (n <= 0) return fail(TTN_ERR_INVALID, "n_vertices must be positive");
@@ -217,6 +319,7 @@ static int build_plan(ttn_plan* p, const ttn_desc* d) {
                         (p->tgemm_ok ? (1 << TTN_KERNEL_TREE) : 0) | (p->gshare_ok ? (1 << TTN_KERNEL_GRID) : 0) |
                         (p->ctab_ok ? (1 << TTN_KERNEL_TABLE) : 0);
   I.flops_per_point = (d->is_complex ? 8.0 : 2.0) * macs;
+  p->exec_rule_flops = I.flops_per_point;
   I.bytes_per_point = 8.0 * d->n_coords + (d->is_complex ? 16.0 : 8.0);
   I.tensor_bytes = d->tensor_ptr[n] * NC * 8;
   return TTN_OK;
@@ -967,7 +1070,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
                             : kernel == TTN_KERNEL_TREE ? p->tgemm_flops_exec
                             : kernel == TTN_KERNEL_TABLE ? p->ctab_flops_exec
-                                                                             : p->info.flops_per_point) *
+                                                                             : p->exec_rule_flops) *
                            (double)npts;
     int herr = 0;
     cudaMemcpy(&herr, p->d_err, sizeof(int), cudaMemcpyDeviceToHost);

@@ -212,6 +212,8 @@ struct ttn_plan {
   std::vector<int64_t> slice_size, tensor_off, msg_off;
   std::vector<int32_t> nslices;
   bool is_chain = false;
+  double exec_rule_flops = 0.0; // flop rule of the tree the kernels really walk (== info.flops_per_point unless binarized)
+  bool binarized = false; // vertices with > 2 children were split with Kronecker pair vertices (ttn_api.cu, binarize_desc)
   // device memory
   std::vector<void*> allocs;
   ttn::DigitTable digits{};

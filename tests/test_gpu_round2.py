@@ -592,3 +592,65 @@ def test_mutating_a_network_re_plans():
     f.itensornetwork[v] = f.itensornetwork[v] * 0.25
     c = t.evaluate(f, pts)
     assert np.allclose(b, 2.0 * a, rtol=1e-13, atol=0) and np.allclose(c, 0.5 * a, rtol=1e-13, atol=0)
+
+
+def _star_and_random_trees():
+    out = {}
+    # a star: centre with 4 / 5 neighbours (as root it has 4 / 5 children), every vertex one binary site index
+    for k in (4, 5):
+        g = t.NamedGraph([(i, 1) for i in range(k + 1)], [((0, 1), (i, 1)) for i in range(1, k + 1)])
+        s = t.continuous_siteinds(g, map_dimension=2)
+        out[f"star{k}_chi3"] = (t.rand_itn(s, link_space=3 if k == 4 else 2, rng=k, normalise=True), 2)
+    # caterpillar: a path whose inner vertices each carry two extra leaves (degree 4: three children once rooted)
+    verts = [(i, 1) for i in range(5)] + [(i, 2) for i in range(1, 4)] + [(i, 3) for i in range(1, 4)]
+    edges = [((i, 1), (i + 1, 1)) for i in range(4)] + [((i, 1), (i, 2)) for i in range(1, 4)] + [((i, 1), (i, 3)) for i in range(1, 4)]
+    g = t.NamedGraph(verts, edges)
+    out["caterpillar_chi4"] = (t.rand_itn(t.continuous_siteinds(g, map_dimension=3), link_space=4, rng=9, normalise=True), 3)
+    out["caterpillar_cplx_chi3"] = (t.rand_itn(t.complex_continuous_siteinds(g, map_dimension=2), link_space=3, rng=10,
+                                               eltype=complex, normalise=True), 2)
+    for seed in (5, 6, 7, 8):
+        g = t.uniform_tree(12, rng=seed).rename_vertices(lambda v: (v, 1))
+        out[f"unitree12_s{seed}_chi3"] = (t.rand_itn(t.continuous_siteinds(g, map_dimension=2), link_space=3, rng=seed, normalise=True), 2)
+    return out
+
+
+@pytest.mark.parametrize("which", list(_star_and_random_trees()))
+def test_trees_with_more_than_two_children_are_binarised(which, monkeypatch):
+    """uniform_tree (test/test_realitensorfunction.jl:129) and other trees with vertices of degree > 3: the plan splits
+    such vertices with Kronecker pair vertices (ttn_api.cu, binarize_desc) so that the per-vertex GEMM tree kernel
+    applies; same values as the generic kernel on the ORIGINAL tree and as the 80-bit oracle."""
+    f, ndim = _star_and_random_trees()[which]
+    dims = f.indexmap.dimensions()
+    plan = f.plan(dims)
+    info = plan.info()
+    n = len(f.vertices())
+    assert info["n_vertices"] == n                      # the caller's network is what is reported
+    cm = isinstance(f.indexmap, t.ComplexIndexMap)
+    rng = np.random.default_rng(3)
+    L = 6
+    p = cases.complex_points(L, len(dims), rng, 5000) if cm else cases.edge_points(L, len(dims), rng, 5000)
+    packed = plan.packed
+    coords = np.empty((len(p), packed.n_coords))
+    if cm:
+        coords[:, 0::2], coords[:, 1::2] = p.real, p.imag
+    else:
+        coords[:] = p
+    ref = orc.evaluate(packed, coords, orc.ORACLE_LD, nthreads=orc.max_threads())
+    maxdeg = max(len(list(f.itensornetwork.graph.neighbors(v))) for v in f.vertices())
+    got, o = t.evaluate(f, p, dims, return_opts=True)
+    assert orc.error_metric(got, ref).max() < TOL
+    if info["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE):
+        gt = t.evaluate(f, p, dims, kernel="tree")
+        assert orc.error_metric(gt, ref).max() < TOL
+    gg = t.evaluate(f, p, dims, kernel="generic")
+    assert orc.error_metric(gg, ref).max() < TOL
+    assert (plan.digits_host(coords) == orc.digits(packed, coords)).all()
+    if maxdeg >= 4 and which.startswith(("star", "caterpillar")):
+        assert info["kernels_available"] & (1 << _capi.TTN_KERNEL_TREE), which      # binarised: the tree kernel applies
+        assert o.kernel_used == _capi.TTN_KERNEL_TREE
+    # the original tree through the generic kernel gives the same function
+    f.invalidate_plans()
+    monkeypatch.setenv("TTN_TREE_BINARIZE", "0")
+    g0 = t.evaluate(f, p, dims)
+    assert orc.error_metric(g0, ref).max() < TOL
+    f.invalidate_plans()
