@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libttneval.so")
+LIB_PATH = os.environ.get("LIBTTNEVAL") or os.path.join(_HERE, "csrc", "libttneval.so")   # same override as the Julia wrapper
 
 TTN_ABI_VERSION = 3
 TTN_OK, TTN_ERR_INVALID, TTN_ERR_DOMAIN, TTN_ERR_CUDA, TTN_ERR_UNSUPPORTED, TTN_ERR_NOMEM = range(6)

@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(NT, MINB)
   constexpr int E = CPLX ? 2 : 1, HE = H * E, MM = H * H * E;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NT / 32];
-  __shared__ __align__(16) unsigned char s_dig[kFeMaxSites * sizeof(Digit4)]; // Digit2[] (binary) or Digit4[] (base 3 / 4)
-  Digit2* s_d2 = reinterpret_cast<Digit2*>(s_dig);
-  Digit4* s_d4 = reinterpret_cast<Digit4*>(s_dig);
+  __shared__ Digit2 s_d2[kFeMaxSites];
+  // The base-3 / base-4 digit table lives in DYNAMIC shared memory behind the group tables, only for networks that need
+  // it.  As a static array (5 KB) it pushed the chi = 1 bench instance — 192 KB of tables + 2.9 KB static + 1 KB reserved —
+  // past the 196 KB shared-memory carveout into the 228 KB one, i.e. from 60 KB of L1 to 28 KB, and the HBM-bound
+  // kernel ran 17 % slower (0.470 vs 0.400 ms per 1e8 points; scripts/microbench/ab_table.sh against the round-start build).
+  Digit4* s_d4 = reinterpret_cast<Digit4*>(smem + (((size_t)ct.total_doubles * 8 + 15) & ~(size_t)15));
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -812,7 +815,8 @@ template <int H, bool CPLX, int NT, int MINB, int PPT, int NCV, bool W2, bool RE
 static int launch_tab_inst(ttn_plan* p, const CoordSource& src, double* d_out, double* d_partial, int* n_partial,
                            cudaStream_t s) {
   const ChainTabDev& c = p->ctab;
-  const size_t smem = (size_t)c.total_doubles * 8;
+  const size_t smem = (((size_t)c.total_doubles * 8 + 15) & ~(size_t)15) +
+                      (c.k1_generic == 1 ? (size_t)p->digits_tab.n_sites * sizeof(Digit4) : 0); // tables [+ Digit4 entries]
   auto kern = chain_table_kernel<H, CPLX, NT, MINB, PPT, NCV, W2, REP>;
   TTN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;

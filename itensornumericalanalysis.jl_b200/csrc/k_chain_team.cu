@@ -76,9 +76,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ double red[2][NTEAM * TW];
-  __shared__ __align__(16) unsigned char s_dig[kFeMaxSites * sizeof(Digit4)]; // Digit2[] (binary) or Digit4[] (base 3 / 4)
-  Digit2* s_d2 = reinterpret_cast<Digit2*>(s_dig);
-  Digit4* s_d4 = reinterpret_cast<Digit4*>(s_dig);
+  __shared__ Digit2 s_d2[kFeMaxSites]; // binary digits
+  __shared__ Digit4 s_d4[kFeMaxSites]; // base 3 / 4 (two plain arrays: see k_chain_table.cu)
   __shared__ int s_cptr[TTN_MAX_COORDS + 1];
 
   const int tid = threadIdx.x, lane = tid & 31;
