@@ -220,9 +220,10 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     {
       uint64_t w0[PPL];
       compute_words(tile, w0, w1);
-      if (deep) {
+      if (deep && R > 0 && ch.root_bits > 16) {
         // the root-table row of every home point is known as soon as K1 is done: pull it into L2 now, the rounds
-        // hide the HBM latency (tables of 2^20 rows do not stay L2-resident)
+        // hide the HBM latency (tables of 2^20 rows do not stay L2-resident; smaller ones do, and with no rounds
+        // in between the prefetch would only cost instructions)
         const int off = ch.leaf_bits + R * BITS;
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
