@@ -41,6 +41,10 @@ nets.append(("r2 comb3x12 chi16 (tree: tables, merged runs)", t.rand_itn(sc3, li
 scc = t.complex_continuous_siteinds(gc, [[(j, i) for i in range(1, 13)] for j in range(1, 4)],
                                     [[(j, i) for i in range(12, 0, -1)] for j in range(3, 0, -1)])
 nets.append(("r2 complex comb3x12 chi6 (tree, complex fold)", t.rand_itn(scc, link_space=6, rng=13, eltype=complex, normalise=True), 6, 2000))
+s3r = t.continuous_siteinds(t.named_grid((45, 1)), base=3)
+nets.append(("r2 mps45 base3 chi16 (team, radix-3 group fields: 12 + 7 x 3 + 12 vertices)", t.rand_itn(s3r, link_space=16, rng=14, normalise=True), 1, 3000))
+gs = t.NamedGraph([(i, 1) for i in range(6)], [((0, 1), (i, 1)) for i in range(1, 6)])
+nets.append(("r2 star with 5 leaves chi2 (tree, binarised at plan time)", t.rand_itn(t.continuous_siteinds(gs, map_dimension=2), link_space=2, rng=15, normalise=True), 2, 3000))
 skip = os.environ.get('SAN_SKIP', '')
 only = os.environ.get('SAN_ONLY', '')
 # default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
@@ -66,4 +70,11 @@ for merge in (os.environ.get('SAN_MERGES', 'default,1').split(',')):
             out, o = plan.evaluate_host(pts, accuracy="refined", reduce_sum=True)
             print(name, "refined ok", int(o.n_refined))
         f._plans.clear()
+if not only or only == 'r2':
+    # host-side quantisation of pageable run-path coordinates (pack_coords -> CoordSource::qcoords), >= 2^20 points
+    s2 = t.continuous_siteinds(g40, [[(i, j) for j in range(1, 41)] for i in (1, 2)])
+    s2b = t.continuous_siteinds(t.named_comb_tree((2, 30)), [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    fq = t.rand_itn(s2b, link_space=16, rng=16, normalise=True)
+    out, o = fq.plan().evaluate_host(rng.random((1_100_000, 2)), reduce_sum=True)
+    print("r2 quantised pageable coordinates ok", int(o.staged), int(o.h2d_bytes))
 print("done")
