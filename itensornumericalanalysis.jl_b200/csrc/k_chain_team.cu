@@ -340,26 +340,21 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         for (int i = lane; i < HS; i += 32) hist[((qh + 2) % 3) * HS + i] = 0u; // last read before the previous barrier
       named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 final
 
-      // ---- owned classes: B in registers, rows streamed through gather -> DMMA -> scatter
-#pragma unroll
-      for (int j = 0; j < CPW; ++j) {
-        const int c = warp + j * TW;
-        {
-          // prefetch the next class in the flattened (round, class) sequence; the sequence of the
-          // next tile starts again at (0, warp)
-          const int rn = (j + 1 < CPW) ? r : ((r + 1 < R) ? r + 1 : 0);
-          const int cn_ = (j + 1 < CPW) ? c + TW : warp;
-          load_b(bnxt, rn, cn_);
-        }
-        const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
-        const int ng = (n_c + 7) >> 3;
+      // ---- classes of this warp: B in registers, rows streamed through gather -> DMMA -> scatter.  Warp w owns
+      // classes w, w + 4, ...  A BIG class (more than BIG_G groups of 8 rows) is split into four quarters, one per
+      // warp, so that a skewed class distribution — a coordinate held constant along a cut, dyadic grid points whose
+      // low digits are all zero: every point of the tile in ONE class — keeps all four warps busy instead of one
+      // (measured on such inputs: rounds 3.5x slower with static ownership; now as fast as random points).  A round
+      // without a big class — every round of random points at 16 classes — takes the static, fully unrolled schedule.
+      // Either way the first class of a round is the warp's own class w, whose B is prefetched across the barrier.
+      auto run_groups = [&](int st, int g_lo, int ng) {
         const uint16_t* Lc = list + st;
         int rows_nx[4] = {0, 0, 0, 0};
-        if (ng > 0) {
+        if (ng > g_lo) {
 #pragma unroll
-          for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(b, ng - 1) << 3) + g];
+          for (int b = 0; b < GB; ++b) rows_nx[b] = (int)Lc[(min(g_lo + b, ng - 1) << 3) + g];
         }
-        for (int gi = 0; gi < ng; gi += GB) {
+        for (int gi = g_lo; gi < ng; gi += GB) {
           const int nbat = min(GB, ng - gi);
           int rows[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -373,8 +368,41 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
           else if (nbat == 2) batch6<CHI, 2>(state_base, rows, tq, ZROW, bcur);
           else batch6<CHI, 1>(state_base, rows, tq, ZROW, bcur);
         }
+      };
+      constexpr int BIG_G = 8;
+      const int ngl = (total + 7) >> 3; // lane c: 8-row groups of class c
+      if (__ballot_sync(0xffffffffu, lane < NCLS && ngl > BIG_G) == 0u) {
 #pragma unroll
-        for (int i = 0; i < NBF; ++i) bcur[i] = bnxt[i];
+        for (int j = 0; j < CPW; ++j) {
+          const int c = warp + j * TW;
+          {
+            // prefetch the next class in the flattened (round, class) sequence; the sequence of the
+            // next tile starts again at (0, warp)
+            const int rn = (j + 1 < CPW) ? r : ((r + 1 < R) ? r + 1 : 0);
+            const int cn_ = (j + 1 < CPW) ? c + TW : warp;
+            load_b(bnxt, rn, cn_);
+          }
+          const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
+          run_groups(st, 0, (n_c + 7) >> 3);
+#pragma unroll
+          for (int i = 0; i < NBF; ++i) bcur[i] = bnxt[i];
+        }
+      } else {
+        uint32_t rest = __ballot_sync(0xffffffffu, lane < NCLS && ngl > 0 && (ngl > BIG_G || (lane % TW) == warp)) & ~(1u << warp);
+        int c = warp;
+        for (;;) {
+          const int cn = rest ? __ffs(rest) - 1 : -1; // next class of this warp in this round
+          load_b(bnxt, cn >= 0 ? r : ((r + 1 < R) ? r + 1 : 0), cn >= 0 ? cn : warp);
+          const int n_c = __shfl_sync(0xffffffffu, total, c), st = __shfl_sync(0xffffffffu, mystart, c);
+          const int ng_all = (n_c + 7) >> 3;
+          const bool big = ng_all > BIG_G;
+          run_groups(st, big ? (ng_all * warp) / TW : 0, big ? (ng_all * (warp + 1)) / TW : ng_all);
+#pragma unroll
+          for (int i = 0; i < NBF; ++i) bcur[i] = bnxt[i];
+          if (cn < 0) break;
+          c = cn;
+          rest &= rest - 1;
+        }
       }
     }
     if (R > 0) named_bar_sync(bar_id, TW * 32); // rows of the last round complete

@@ -654,3 +654,38 @@ def test_trees_with_more_than_two_children_are_binarised(which, monkeypatch):
     g0 = t.evaluate(f, p, dims)
     assert orc.error_metric(g0, ref).max() < TOL
     f.invalidate_plans()
+
+
+def test_skewed_class_distributions():
+    """A cut at constant y, a coarse dyadic grid (low digits all zero), all points equal: whole tiles fall into one class
+    per round and the team-sorted kernel splits such classes across its four warps (k_chain_team.cu).  Same values as
+    the oracle / as the same points evaluated one class per warp's worth at a time (random points mixed in)."""
+    g = t.named_comb_tree((2, 30))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+    f = t.rand_itn(s, link_space=16, rng=20262, normalise=True)
+    rng = np.random.default_rng(21)
+    n = 300_000
+    base = rng.random((n, 2))
+    sets = {"cut": base.copy(), "dyadic": np.floor(base * 64) / 64, "same": np.tile(base[:1], (n, 1)),
+            "mixed": np.where(rng.random((n, 1)) < 0.7, np.floor(base * 8) / 8, base)}
+    sets["cut"][:, 1] = 0.3141592653589793
+    import os
+    for deep in ("0", None):
+        if deep is None:
+            os.environ.pop("TTN_MMA_DEEP", None)
+        else:
+            os.environ["TTN_MMA_DEEP"] = deep
+        f.invalidate_plans()
+        plan = f.plan()
+        try:
+            for name, pts in sets.items():
+                got, o = plan.evaluate_host(pts, reduce_sum="sum", want_values=True)
+                assert o.kernel_used == _capi.TTN_KERNEL_DMMA
+                idx = rng.integers(0, n, 4000)
+                ref = orc.evaluate(plan.packed, pts[idx], orc.ORACLE_LD, nthreads=orc.max_threads())
+                err = orc.error_metric(got[idx], ref)
+                assert err.max() < 5e-12 and np.quantile(err, 0.99) < TOL, (name, deep, err.max())
+                assert abs(o.sum_out[0] - got.sum()) <= 1e-11 * np.abs(got).sum()
+        finally:
+            os.environ.pop("TTN_MMA_DEEP", None)
+    f.invalidate_plans()
