@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -1518,6 +1519,38 @@ int ttn_debug_slice_stream(ttn_plan* plan, const double* coords, int64_t npts, i
     site_fbits[ent[i].site] = kernel == TTN_KERNEL_DMMA ? plan->cmma_site_fbits[ent[i].site] : plan->ctab_bits0;
   }
   return TTN_OK;
+}
+
+/* Test hooks without CUDA calls (CPU test suite), not part of include/ttneval.h.
+ * ttn_debug_pack_coords: the host-side quantisation of run-path coordinates exactly as the staging threads do it
+ *   (pack_coords): q[p * nc + c] = min(floor(x 2^L[c]), 2^L[c] - 1); returns 1 if a coordinate is negative / NaN, else 0.
+ * ttn_debug_binarize: the plan-time splitting of vertices with more than two children (binarize_desc).  Returns the
+ *   new vertex count (0: the description is left as it is); fills parent / link_dim / tensor_ptr (cap entries, + 1 for
+ *   tensor_ptr) and copies the new tensor blob (tensor_cap doubles) when the buffers are large enough, else returns -1. */
+int ttn_debug_pack_coords(const double* coords, int64_t npts, int32_t nc, const int32_t* L, uint32_t* q_out) {
+  if (!coords || !L || !q_out || nc < 1 || nc > TTN_MAX_COORDS || npts < 0) return -1;
+  PackParams pp;
+  pp.nc = nc;
+  for (int c = 0; c < nc; ++c) {
+    if (L[c] < 1 || L[c] > 32) return -1;
+    pp.scale[c] = std::ldexp(1.0, L[c]);
+    pp.qmax[c] = L[c] >= 32 ? 0xffffffffu : ((1u << L[c]) - 1u);
+  }
+  return pack_coords(q_out, coords, (size_t)npts, pp) ? 1 : 0;
+}
+
+int ttn_debug_binarize(const ttn_desc* desc, int32_t cap, int32_t* parent, int32_t* link_dim, int64_t* tensor_ptr,
+                       double* tensors, int64_t tensor_cap) {
+  if (!desc || !parent || !link_dim || !tensor_ptr || !tensors) return -1;
+  BinDesc b;
+  if (!binarize_desc(desc, &b)) return 0;
+  const int n = b.d.n_vertices;
+  if (n > cap || (int64_t)b.tensors.size() > tensor_cap) return -1;
+  std::copy(b.parent.begin(), b.parent.end(), parent);
+  std::copy(b.link_dim.begin(), b.link_dim.end(), link_dim);
+  std::copy(b.tensor_ptr.begin(), b.tensor_ptr.end(), tensor_ptr);
+  std::copy(b.tensors.begin(), b.tensors.end(), tensors);
+  return n;
 }
 
 int ttn_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops) {
