@@ -683,6 +683,35 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       c.run_scale[cidx] = std::ldexp(1.0, L);
     }
   }
+  // Base-4 digits (one site index of dimension 4 per vertex, thresholds exactly v 4^-k): digit k of the greedy loop is the
+  // bit PAIR (2(L-k)+1, 2(L-k)) of floor(x 4^L) — the same argument as for base 2 with two bits per step (x_rn stays an
+  // exact multiple of 4^-L's grid, the compare picks floor(x_rn 4^k)) — so a coordinate whose digits sit on consecutive
+  // 2-bit fields takes the run path as a run of 2L bits; run_rev = 2: digit 1 on the LOWEST field (pairs reversed).
+  if (bits0 == 2 && !radix) {
+    std::vector<int32_t> cptr(d->n_coords + 1);
+    TTN_CUDA(cudaMemcpy(cptr.data(), p->digits_mma.coord_ptr, sizeof(int32_t) * (d->n_coords + 1), cudaMemcpyDeviceToHost));
+    for (int cidx = 0; cidx < d->n_coords; ++cidx) {
+      const int L = cptr[cidx + 1] - cptr[cidx];
+      if (L < 1 || 2 * L > 62) continue;
+      bool ok = true;
+      int step = 0, first_pos = -1;
+      for (int k = 0; k < L && ok; ++k) {
+        const DigitEntry& e = ent[cptr[cidx] + k];
+        const int pos = e.word * 64 + e.shift;
+        ok = ok && e.base == 4 && e.stride == 1 && p->nslices[e.vertex] == 4 && d->site_digit[e.site] == k + 1;
+        for (int v = 1; v < 4 && ok; ++v) ok = d->thr[e.thr_off + v] == v * std::ldexp(1.0, -2 * (k + 1));
+        if (k == 0) first_pos = pos;
+        else if (k == 1) step = pos - first_pos;
+        if (k >= 1) ok = ok && (pos - first_pos == step * k);
+      }
+      if (L == 1) step = 2;
+      if (!ok || (step != 2 && step != -2)) continue;
+      c.run_L[cidx] = 2 * L;
+      c.run_rev[cidx] = step == 2 ? 2 : 0;
+      c.run_plow[cidx] = step == 2 ? first_pos : first_pos - 2 * (L - 1);
+      c.run_scale[cidx] = std::ldexp(1.0, 2 * L);
+    }
+  }
   // Light variant for host-buffer calls: measured on config 2 (bench.py e2e, pinned buffers, 2 Mi-point chunks) the
   // deep-table kernel — two random 128-byte row gathers per point at > 5 G points/s — slows the H2D / D2H copies
   // that run beside it (e2e 2.79 G points/s for ANY table size, L2-resident ones included, against 3.19 = the

@@ -149,12 +149,13 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         // coordinates quantised on the host while they were staged (ttn_api.cu, pack_coords): q = floor(x 2^L), x >= 1
         // saturated, domain checked there — every coordinate is on the run path (the host checked that too)
         const int L = ch.run_L[c], plow = ch.run_plow[c];
-        const bool rev = ch.run_rev[c] != 0;
+        const int rev = ch.run_rev[c]; // 1: bits reversed, 2: bit PAIRS reversed (base-4 digits)
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           const int64_t p = p0 + k * 32 + lane;
           unsigned long long q = p < src.npts ? (unsigned long long)__ldg(src.qcoords + p * dg.n_coords + c) : 0ull;
           if (rev) q = __brevll(q) >> (64 - L);
+          if (rev == 2) q = ((q & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((q & 0x5555555555555555ull) << 1);
           if (plow < 64) {
             w0[k] += q << plow;
             if (plow + L > 64) w1[k] += q >> (64 - plow);
@@ -179,11 +180,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       if (ch.run_L[c] > 0 && !src.digits) {
         const int L = ch.run_L[c], plow = ch.run_plow[c];
         const double scale = ch.run_scale[c];
-        const bool rev = ch.run_rev[c] != 0;
+        const int rev = ch.run_rev[c]; // 1: bits reversed, 2: bit PAIRS reversed (base-4 digits)
 #pragma unroll
         for (int k = 0; k < PPL; ++k) {
           unsigned long long q = x[k] >= 1.0 ? ((1ull << L) - 1ull) : (unsigned long long)(x[k] * scale);
           if (rev) q = __brevll(q) >> (64 - L);
+          if (rev == 2) q = ((q & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((q & 0x5555555555555555ull) << 1);
           if (plow < 64) {
             w0[k] += q << plow;
             if (plow + L > 64) w1[k] += q >> (64 - plow);
