@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   const int tid = threadIdx.x, lane = tid & 31;
   const int team = tid / (TW * 32), warp = (tid >> 5) % TW;
   const int g = lane >> 2, tq = lane & 3;
+  constexpr int RPI = 32 / CPR;            // deep tables: table rows per warp instruction (CPR lanes share a row)
+  const int coj = lane % CPR, coq = lane / CPR;
   for (int i = tid; i <= dg.n_coords; i += NT) s_cptr[i] = dg.coord_ptr[i];
   for (int i = tid; i < (ch.k1_generic == 1 ? dg.n_sites : 0); i += NT) s_d4[i] = make_digit4(dg, i);
   for (int i = tid; i < (ch.k1_generic == 0 ? dg.n_sites : 0); i += NT) {
@@ -250,20 +252,27 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         }
       }
       // ---- leaf rows
+      if (deep) {
+        // CPR lanes share one table row: a warp instruction copies 32 / CPR whole 128-byte-aligned rows global -> shared
+        // (cp.async: 1 L1 wavefront per row where a lane walking its own row with 256-bit loads costs 4, no registers,
+        // and every copy of the warp's 128 rows is in flight at once); the row index comes from the owner lane
+        __syncwarp(); // the owners' root reads of the previous tile precede the other lanes' copies into those rows
 #pragma unroll
-      for (int k = 0; k < PPL; ++k) {
-        cw[k] = w0[k];
-        const int row = warp * PW + k * 32 + lane;
-        if (deep) {
-          const double* L = ch.leaf + (size_t)(cw[k] & LMASK) * CHI;
+        for (int k = 0; k < PPL; ++k) {
+          cw[k] = w0[k];
+          const uint32_t li = (uint32_t)(w0[k] & LMASK);
 #pragma unroll
-          for (int j = 0; j < CPR; j += 2) {
-            double a0, a1, a2, a3;
-            ldg256(L + 2 * j, a0, a1, a2, a3);
-            sts128(row_chunk<CHI>(state_base, row, j), a0, a1);
-            sts128(row_chunk<CHI>(state_base, row, j + 1), a2, a3);
+          for (int s = 0; s < CPR; ++s) {
+            const int ol = s * RPI + coq;
+            const uint32_t ri = __shfl_sync(0xffffffffu, li, ol);
+            cp_async16_cg(row_chunk<CHI>(state_base, warp * PW + k * 32 + ol, coj), ch.leaf + (size_t)ri * CHI + 2 * coj);
           }
-        } else {
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          cw[k] = w0[k];
+          const int row = warp * PW + k * 32 + lane;
           const int sl = (int)(cw[k] & MASK);
           const uint32_t L = s_leaf_u32 + (uint32_t)sl * (CHI * 8);
 #pragma unroll
@@ -307,6 +316,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       shift_stream();
     };
     if (R > 0) count_round(qh % 3);
+    if (deep) cp_async_wait_all();
     named_bar_sync(bar_id, TW * 32); // leaf rows + counts of round 0
 
     for (int r = 0; r < R; ++r, ++qh) {
@@ -410,33 +420,54 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     if (R > 0) named_bar_sync(bar_id, TW * 32); // rows of the last round complete
 
     // ---- root: out = row . R[d_{n-1}] for the home rows
+    if (deep) {
+      // cooperative: the CPR lanes of a group read one state row and one root-table row chunk by chunk (coalesced:
+      // 1 L1 wavefront per table row instead of 4), CPR rows per group and pass; a reduce-scatter over the group
+      // leaves lane j with the dot product of the group's j-th row, and the 32 results of a pass are 32
+      // consecutive points (owner lane = j * RPI + group)
 #pragma unroll
-    for (int k = 0; k < PPL; ++k) {
-      const int row = warp * PW + k * 32 + lane;
-      const int64_t p = p0 + k * 32 + lane;
-      double o0 = 0.0, o1 = 0.0;
-      if (deep) {
-        const double* R0 = ch.root + (size_t)(cw[k] & RMASK) * CHI;
-        const double* R1 = R0 + ((size_t)CHI << ch.root_bits);
+      for (int k = 0; k < PPL; ++k) {
+        const uint32_t ri_own = (uint32_t)(cw[k] & RMASK);
+        const int ol_out = coj * RPI + coq;
+        const int64_t p = p0 + k * 32 + ol_out;
+        double o[2] = {0.0, 0.0};
+        for (int oi = 0; oi < ch.nout; ++oi) {
+          const double* Rt = ch.root + ((size_t)oi * CHI << ch.root_bits);
+          double part[CPR];
 #pragma unroll
-        for (int j = 0; j < CPR; j += 2) {
-          const double2 v = lds128(row_chunk<CHI>(state_base, row, j));
-          const double2 w = lds128(row_chunk<CHI>(state_base, row, j + 1));
-          double q0, q1, q2, q3;
-          ldg256(R0 + 2 * j, q0, q1, q2, q3);
-          o0 = fma(v.x, q0, o0);
-          o0 = fma(v.y, q1, o0);
-          o0 = fma(w.x, q2, o0);
-          o0 = fma(w.y, q3, o0);
-          if (ch.nout == 2) {
-            ldg256(R1 + 2 * j, q0, q1, q2, q3);
-            o1 = fma(v.x, q0, o1);
-            o1 = fma(v.y, q1, o1);
-            o1 = fma(w.x, q2, o1);
-            o1 = fma(w.y, q3, o1);
+          for (int s = 0; s < CPR; ++s) {
+            const int ol = s * RPI + coq;
+            const uint32_t ri = __shfl_sync(0xffffffffu, ri_own, ol);
+            const double2 q = ldg128(Rt + (size_t)ri * CHI + 2 * coj);
+            const double2 v = lds128(row_chunk<CHI>(state_base, warp * PW + k * 32 + ol, coj));
+            part[s] = fma(v.y, q.y, v.x * q.x);
           }
+#pragma unroll
+          for (int off = CPR / 2; off > 0; off >>= 1) {
+            const bool up = (coj & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const double send = up ? part[i] : part[i + off];
+              const double keep = up ? part[i + off] : part[i];
+              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          o[oi] = part[0];
         }
-      } else {
+        if (p < src.npts) {
+          if (out) {
+            if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o[0], o[1]);
+            else out[p] = o[0];
+          }
+          accumulate_point(src, p, o[0], o[1], sum_re, sum_im);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int row = warp * PW + k * 32 + lane;
+        const int64_t p = p0 + k * 32 + lane;
+        double o0 = 0.0, o1 = 0.0;
         const int sl = (int)(cw[k] & MASK);
         const uint32_t R0 = s_root_u32 + (uint32_t)sl * (CHI * 8), R1 = R0 + (uint32_t)(NCLS * CHI * 8);
 #pragma unroll
@@ -452,13 +483,13 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
             o1 = fma(v.y, q1.y, o1);
           }
         }
-      }
-      if (p < src.npts) {
-        if (out) {
-          if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
-          else out[p] = o0;
+        if (p < src.npts) {
+          if (out) {
+            if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o0, o1);
+            else out[p] = o0;
+          }
+          accumulate_point(src, p, o0, o1, sum_re, sum_im);
         }
-        accumulate_point(src, p, o0, o1, sum_re, sum_im);
       }
     }
     // the next tile's leaf rows overwrite home rows only: no barrier needed here, the first barrier
