@@ -60,7 +60,7 @@ __device__ __forceinline__ void ldg256(const double* p, double& a, double& b, do
 // 128-bit read-only global load
 __device__ __forceinline__ double2 ldg128(const double* p) {
   double2 r;
-  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
 }
 // 16-byte asynchronous copy global -> shared past L1 (SASS LDGSTS.E.BYPASS.128)

@@ -48,6 +48,18 @@ __device__ __forceinline__ void batch6(uint32_t state_base, const int (&rows)[4]
     }
 }
 
+#ifdef TTN_TEAM_CLOCKS
+// debug build (make dbgteam, scripts/team_clocks.py): per-warp clock accounting of the phases of a tile
+__device__ unsigned long long g_tphase[12];
+#define TPH_DECL long long ph_t = clock64(); unsigned long long ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TPH_MARK(i) { const long long t_ = clock64(); ph_acc[i] += (unsigned long long)(t_ - ph_t); ph_t = t_; }
+#define TPH_FLUSH if (lane == 0) { for (int i_ = 0; i_ < 10; ++i_) atomicAdd(&g_tphase[i_], ph_acc[i_]); atomicAdd(&g_tphase[11], 1ull); }
+#else
+#define TPH_DECL
+#define TPH_MARK(i)
+#define TPH_FLUSH
+#endif
+
 template <int CHI, int NCLS, int PW_>
 struct Team6 {
   static constexpr int TW = 4, PW = PW_, TP = TW * PW;
@@ -143,9 +155,17 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
   // ---- K1: packed slice streams of the lane's PPL home points of one tile (interleaved for ILP)
   auto compute_words = [&](int64_t tile_, uint64_t (&w0)[PPL], uint64_t (&w1)[PPL]) {
     const int64_t p0 = tile_ * TP + warp * PW;
-    double x[PPL];
+    double x[PPL], xn[PPL];
+    auto load_x = [&](int c, double (&v)[PPL]) {
+#pragma unroll
+      for (int k = 0; k < PPL; ++k) {
+        const int64_t p = p0 + k * 32 + lane;
+        v[k] = p < src.npts ? load_coord(src, p, c) : 0.0;
+      }
+    };
 #pragma unroll
     for (int k = 0; k < PPL; ++k) w0[k] = w1[k] = 0;
+    if (!src.qcoords && dg.n_coords > 0) load_x(0, xn);
     for (int c = 0; c < dg.n_coords; ++c) {
       if (src.qcoords) {
         // coordinates quantised on the host while they were staged (ttn_api.cu, pack_coords): q = floor(x 2^L), x >= 1
@@ -167,17 +187,21 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         }
         continue;
       }
+      // the loads of coordinate c + 1 are issued before coordinate c is converted, and nothing with a side effect sits
+      // between the loads of one coordinate (the domain flag is raised once, afterwards): K1 waits for ONE memory
+      // round trip per tile where a load -> check -> atomic sequence per point made it eight
 #pragma unroll
-      for (int k = 0; k < PPL; ++k) {
-        const int64_t p = p0 + k * 32 + lane;
-        x[k] = 0.0;
-        if (p < src.npts) {
-          x[k] = load_coord(src, p, c);
+      for (int k = 0; k < PPL; ++k) x[k] = xn[k];
+      if (c + 1 < dg.n_coords) load_x(c + 1, xn);
+      {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k)
           if (!coord_in_domain(x[k])) {
-            atomicOr(err, 1);
+            bad = true;
             x[k] = 0.0;
           }
-        }
+        if (bad) atomicOr(err, 1);
       }
       if (ch.run_L[c] > 0 && !src.digits) {
         const int L = ch.run_L[c], plow = ch.run_plow[c];
@@ -218,12 +242,30 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
     }
   };
 
+  TPH_DECL
   for (int64_t tile = (int64_t)blockIdx.x * NTEAM + team; tile < n_tiles; tile += tstride) {
     const int64_t p0 = tile * TP + warp * PW; // first home point of this warp
     uint64_t w1[PPL], cw[PPL];
     {
       uint64_t w0[PPL];
       compute_words(tile, w0, w1);
+      if (tile + tstride < n_tiles && (src.qcoords || (!src.grid && !src.digits))) {
+        // the warp's coordinates of the team's NEXT tile -> L2 (a tile later K1's one round trip is an L2 hit)
+        const int64_t pn = (tile + tstride) * TP + warp * PW;
+        const int64_t np_ = min((int64_t)PW, src.npts - pn);
+        auto pf = [&](const void* b, int64_t nbytes) {
+          const char* e = reinterpret_cast<const char*>(b) + nbytes;
+          for (const char* a = reinterpret_cast<const char*>((uintptr_t)b & ~(uintptr_t)127) + lane * 128; a < e; a += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        };
+        if (np_ > 0) {
+          if (src.qcoords) pf(src.qcoords + pn * dg.n_coords, np_ * dg.n_coords * 4);
+          else if (src.layout == TTN_LAYOUT_AOS) pf(src.coords + pn * dg.n_coords, np_ * dg.n_coords * 8);
+          else
+            for (int c = 0; c < dg.n_coords; ++c) pf(src.coords + (int64_t)c * src.npts + pn, np_ * 8);
+        }
+      }
+      TPH_MARK(0)
       if (deep && R > 0 && ch.root_bits > 16) {
         // the root-table row of every home point is known as soon as K1 is done: pull it into L2 now, the rounds
         // hide the HBM latency (tables of 2^20 rows do not stay L2-resident; smaller ones do, and with no rounds
@@ -316,8 +358,11 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       shift_stream();
     };
     if (R > 0) count_round(qh % 3);
+    TPH_MARK(1)
     if (deep) cp_async_wait_all();
+    TPH_MARK(2)
     named_bar_sync(bar_id, TW * 32); // leaf rows + counts of round 0
+    TPH_MARK(3)
 
     for (int r = 0; r < R; ++r, ++qh) {
       const int buf = r & 1, hb = qh % 3;
@@ -350,7 +395,9 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       if (r + 1 < R) count_round((qh + 1) % 3);
       if (warp == 0)
         for (int i = lane; i < HS; i += 32) hist[((qh + 2) % 3) * HS + i] = 0u; // last read before the previous barrier
+      TPH_MARK(4)
       named_bar_sync(bar_id, TW * 32); // list r complete; rows of round r-1 written; counts r+1 final
+      TPH_MARK(5)
 
       // ---- classes of this warp: B in registers, rows streamed through gather -> DMMA -> scatter.  Warp w owns
       // classes w, w + 4, ...  A BIG class (more than BIG_G groups of 8 rows) is split into four quarters, one per
@@ -417,7 +464,9 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         }
       }
     }
+    TPH_MARK(6)
     if (R > 0) named_bar_sync(bar_id, TW * 32); // rows of the last round complete
+    TPH_MARK(7)
 
     // ---- root: out = row . R[d_{n-1}] for the home rows
     if (deep) {
@@ -425,41 +474,62 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
       // 1 L1 wavefront per table row instead of 4), CPR rows per group and pass; a reduce-scatter over the group
       // leaves lane j with the dot product of the group's j-th row, and the 32 results of a pass are 32
       // consecutive points (owner lane = j * RPI + group)
+      // KH passes share one memory round trip: their table chunks are all in flight before the first is used
+      constexpr int KH = (CPR * 4 >= 64) ? 1 : ((64 / (CPR * 4) < PPL) ? 64 / (CPR * 4) : PPL);
+      const int ol_out = coj * RPI + coq;
 #pragma unroll
-      for (int k = 0; k < PPL; ++k) {
-        const uint32_t ri_own = (uint32_t)(cw[k] & RMASK);
-        const int ol_out = coj * RPI + coq;
-        const int64_t p = p0 + k * 32 + ol_out;
-        double o[2] = {0.0, 0.0};
+      for (int k0 = 0; k0 < PPL; k0 += KH) {
+        double o[KH][2];
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) o[kk][0] = o[kk][1] = 0.0;
         for (int oi = 0; oi < ch.nout; ++oi) {
           const double* Rt = ch.root + ((size_t)oi * CHI << ch.root_bits);
-          double part[CPR];
+          double2 q[KH][CPR];
 #pragma unroll
-          for (int s = 0; s < CPR; ++s) {
-            const int ol = s * RPI + coq;
-            const uint32_t ri = __shfl_sync(0xffffffffu, ri_own, ol);
-            const double2 q = ldg128(Rt + (size_t)ri * CHI + 2 * coj);
-            const double2 v = lds128(row_chunk<CHI>(state_base, warp * PW + k * 32 + ol, coj));
-            part[s] = fma(v.y, q.y, v.x * q.x);
-          }
+          for (int kk = 0; kk < KH; ++kk) {
+            if (k0 + kk < PPL) {
+              const uint32_t ri_own = (uint32_t)(cw[(k0 + kk) % PPL] & RMASK);
 #pragma unroll
-          for (int off = CPR / 2; off > 0; off >>= 1) {
-            const bool up = (coj & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const double send = up ? part[i] : part[i + off];
-              const double keep = up ? part[i + off] : part[i];
-              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              for (int s = 0; s < CPR; ++s) {
+                const uint32_t ri = __shfl_sync(0xffffffffu, ri_own, s * RPI + coq);
+                q[kk][s] = ldg128(Rt + (size_t)ri * CHI + 2 * coj);
+              }
             }
           }
-          o[oi] = part[0];
-        }
-        if (p < src.npts) {
-          if (out) {
-            if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o[0], o[1]);
-            else out[p] = o[0];
+#pragma unroll
+          for (int kk = 0; kk < KH; ++kk) {
+            if (k0 + kk < PPL) {
+              double part[CPR];
+#pragma unroll
+              for (int s = 0; s < CPR; ++s) {
+                const double2 v = lds128(row_chunk<CHI>(state_base, warp * PW + (k0 + kk) * 32 + s * RPI + coq, coj));
+                part[s] = fma(v.y, q[kk][s].y, v.x * q[kk][s].x);
+              }
+#pragma unroll
+              for (int off = CPR / 2; off > 0; off >>= 1) {
+                const bool up = (coj & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                  const double send = up ? part[i] : part[i + off];
+                  const double keep = up ? part[i + off] : part[i];
+                  part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              if (oi == 0) o[kk][0] = part[0];
+              else o[kk][1] = part[0];
+            }
           }
-          accumulate_point(src, p, o[0], o[1], sum_re, sum_im);
+        }
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) {
+          const int64_t p = p0 + (k0 + kk) * 32 + ol_out;
+          if (k0 + kk < PPL && p < src.npts) {
+            if (out) {
+              if (ch.nout == 2) reinterpret_cast<double2*>(out)[p] = make_double2(o[kk][0], o[kk][1]);
+              else out[p] = o[kk][0];
+            }
+            accumulate_point(src, p, o[kk][0], o[kk][1], sum_re, sum_im);
+          }
         }
       }
     } else {
@@ -492,10 +562,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
         }
       }
     }
+    TPH_MARK(8)
     // the next tile's leaf rows overwrite home rows only: no barrier needed here, the first barrier
     // of the next tile orders them before any other warp's gather
   }
 
+  TPH_FLUSH
   if (do_sum) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -554,6 +626,7 @@ int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double
 #define TTN_V6_CASE(W, N)                                                                                   \
   if (c.chi == W && c.nsl == N)                                                                             \
     return v6 == 2 ? launch_mma6_inst<W, N, 2, 128>(p, src, d_out, d_partial, n_partial, s)                 \
+         : v6 == 4 ? launch_mma6_inst<W, N, 4, 96>(p, src, d_out, d_partial, n_partial, s)                  \
                    : launch_mma6_inst<W, N, 3, 128>(p, src, d_out, d_partial, n_partial, s);
     TTN_V6_CASE(16, 4)
     TTN_V6_CASE(16, 8)
@@ -572,5 +645,14 @@ int launch_chain_team(ttn_plan* p, const CoordSource& src, double* d_out, double
   set_error("team-sorted DMMA kernel: unsupported width / slice count");
   return TTN_ERR_UNSUPPORTED;
 }
+
+#ifdef TTN_TEAM_CLOCKS
+int debug_team_clocks(unsigned long long* out12, int reset) {
+  unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  TTN_CUDA(cudaMemcpyFromSymbol(out12, g_tphase, sizeof(z)));
+  if (reset) TTN_CUDA(cudaMemcpyToSymbol(g_tphase, z, sizeof(z)));
+  return TTN_OK;
+}
+#endif
 
 } // namespace ttn

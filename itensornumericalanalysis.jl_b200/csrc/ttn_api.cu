@@ -1186,6 +1186,9 @@ static int evaluate_any(ttn_plan* p, CoordSource base, const double* coords, voi
 #ifdef TTN_PHASE_CLOCKS
 namespace ttn { int debug_phase_clocks(unsigned long long* out8, int reset); }
 #endif
+#ifdef TTN_TEAM_CLOCKS
+namespace ttn { int debug_team_clocks(unsigned long long* out12, int reset); }
+#endif
 using namespace ttn;
 
 extern "C" {
@@ -1458,6 +1461,9 @@ int ttn_host_unregister(void* ptr) {
 
 #ifdef TTN_PHASE_CLOCKS
 int ttn_debug_phase_clocks(unsigned long long* out8, int reset) { return ttn::debug_phase_clocks(out8, reset); }
+#endif
+#ifdef TTN_TEAM_CLOCKS
+int ttn_debug_team_clocks(unsigned long long* out12, int reset) { return ttn::debug_team_clocks(out12, reset); }
 #endif
 
 /* Test hook, not part of include/ttneval.h (no CUDA calls): the table kernel's plan-time image of a
