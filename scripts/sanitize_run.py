@@ -47,6 +47,7 @@ gs = t.NamedGraph([(i, 1) for i in range(6)], [((0, 1), (i, 1)) for i in range(1
 nets.append(("r2 star with 5 leaves chi2 (tree, binarised at plan time)", t.rand_itn(t.continuous_siteinds(gs, map_dimension=2), link_space=2, rng=15, normalise=True), 2, 3000))
 skip = os.environ.get('SAN_SKIP', '')
 only = os.environ.get('SAN_ONLY', '')
+kernels_only = [k for k in os.environ.get('SAN_KERNELS', '').split(',') if k]   # e.g. SAN_KERNELS=dmma
 # default plans: merged binary chains run the team-sorted kernel (v6); TTN_MMA_MERGE=1 keeps one vertex
 # per position and exercises the warp-autonomous (v5) and warp-specialised (v3) kernels
 for merge in (os.environ.get('SAN_MERGES', 'default,1').split(',')):
@@ -62,6 +63,8 @@ for merge in (os.environ.get('SAN_MERGES', 'default,1').split(',')):
         pts = rng.random((n, ncol))
         avail = plan.info()["kernels_available"]
         for kname, kid in _capi.KERNEL_IDS.items():
+            if kernels_only and kname not in kernels_only:
+                continue
             if kid and kname != 'grid' and avail & (1 << kid) and (merge == 'default' or kname == 'dmma'):
                 out, o = plan.evaluate_host(pts, kernel=kname, reduce_sum=True)
                 print(f"merge={merge}", name, kname, "ok", float(np.abs(out).max()))

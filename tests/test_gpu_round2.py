@@ -689,3 +689,43 @@ def test_skewed_class_distributions():
         finally:
             os.environ.pop("TTN_MMA_DEEP", None)
     f.invalidate_plans()
+
+
+def test_team_counts_and_cooperative_gathers(monkeypatch):
+    """The team-sorted kernel with 2, 3 (default) and 4 teams per CTA (TTN_MMA_V6; 4 teams = tiles of 384 points) on
+    real width 16 and 8, a complex chain (real-embedded width 32, two outputs per point) and the no-rounds shape (deep
+    tables absorb the whole chain): a point's arithmetic does not depend on the tile it sits in, so every team count
+    gives bitwise the same values; the leaf rows arrive by cp.async with 8 / 4 / 16 lanes per table row, the root is
+    the cooperative dot product — compared with the oracle on ragged batch sizes."""
+    rng = np.random.default_rng(99)
+    nets = [
+        ("comb 2x30 chi16", t.rand_itn(t.continuous_siteinds(t.named_comb_tree((2, 30)),
+                                                             [[(i, j) for j in range(1, 31)] for i in (1, 2)]),
+                                       link_space=16, rng=5, normalise=True), 2),
+        ("mps 44 chi8", t.rand_itn(t.continuous_siteinds(t.named_grid((44, 1))), link_space=8, rng=6, normalise=True), 1),
+        ("complex mps 30 chi16", t.rand_itn(t.complex_continuous_siteinds(t.named_grid((30, 1))), link_space=16, rng=7,
+                                            eltype=complex, normalise=True), 1),
+        ("mps 28 chi32 2-D", t.rand_itn(t.continuous_siteinds(t.named_grid((28, 1)), map_dimension=2), link_space=32, rng=8,
+                                        normalise=True), 2),
+    ]
+    for name, f, _ in nets:
+        n = 5000 + 37
+        pts = rng.random((n, f.plan().packed.n_coords))   # complex maps: (re, im) coordinate slots
+        vals = {}
+        for teams in (None, "2", "4"):
+            if teams is None:
+                monkeypatch.delenv("TTN_MMA_V6", raising=False)
+            else:
+                monkeypatch.setenv("TTN_MMA_V6", teams)
+            f.invalidate_plans()
+            got, o = f.plan().evaluate_host(pts, kernel="dmma")
+            assert o.kernel_used == _capi.TTN_KERNEL_DMMA, name
+            vals[teams] = got
+            for m in (1, 383, 385, 1151, 1153):
+                part, _ = f.plan().evaluate_host(pts[:m], kernel="dmma")
+                assert (part == got[:m]).all(), (name, teams, m)
+        ref = orc.evaluate(f.plan().packed, pts, orc.ORACLE_LD)
+        assert orc.error_metric(vals[None], ref).max() < TOL, name
+        assert (vals["2"] == vals[None]).all() and (vals["4"] == vals[None]).all(), name
+        monkeypatch.delenv("TTN_MMA_V6", raising=False)
+        f.invalidate_plans()
