@@ -390,8 +390,9 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
         lambda: plan.evaluate_device(b.x_dev.data_ptr(), npts, b.out_dev.data_ptr()))
     dt_e2e, _, _, o_e2e, clocks_e2e = timed(lambda: plan.evaluate_host(b.x_np, out=b.out_np)[1])
     # correctness guard inside the bench: device path == host path bit for bit on a slice
-    # (host-buffer calls of deep-table chains run the image without deep tables — PCIe-bound, k_chain_mma.cu "Light
-    # variant" — so the two paths may differ by the rounding of two FP64 evaluation orders)
+    # (host-buffer calls of deep-table chains that move every coordinate as a double run the image without deep tables —
+    # PCIe-bound, k_chain_mma.cu "Light variant" — so the two paths may then differ by the rounding of two FP64 evaluation
+    # orders; hybrid-quantised pinned calls run the deep image: bitwise equal)
     nchk = min(npts, 1 << 16) * nc_out
     dv, hv = b.out_dev[:nchk].cpu().numpy(), b.out_host[:nchk].numpy()
     same = bool((dv == hv).all())
@@ -405,8 +406,10 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
            "ms_per_step": dt_e2e * 1e3, "clocks": clocks_e2e,
            "api": "ttn_evaluate(host pinned float64 buffers) via the Python mirror's Plan.evaluate_host; h2d / d2h bytes are what "
                   "the call really moved over PCIe (ttn_opts.h2d_bytes / d2h_bytes): where every coordinate's digits are the bits "
-                  "of floor(x 2^L) the staging threads quantise it to that 32-bit grid index on the host (bit-exact), "
-                  "halving the H2D bytes"}
+                  "of floor(x 2^L) the library's host threads quantise coordinates to that 32-bit grid index on the host "
+                  "(bit-exact, 4 bytes per coordinate instead of 8) — every chunk of a pageable array, every second chunk of "
+                  "a pinned one when this GPU has the host to itself (the copy engines read the chunks in between in place); "
+                  "with several ranks per host (LOCAL_WORLD_SIZE > 1) pinned arrays travel as doubles"}
     if extras:
         # the same bytes with NO kernel: H2D of the coordinates and D2H of the values on two streams, all ranks at
         # once — what this box's PCIe / host memory system can move; e2e is reported as a fraction of it
@@ -425,7 +428,7 @@ def measure(ctx, config, steps, warmup, points=0, bufs=None, extras=False):
                                "gb_per_s": (h2d + d2h) * ctx.world / dt_copy / 1e9,
                                "what": "pinned H2D of the step's coordinates + D2H of its values, concurrently, no "
                                        "kernels, every rank at once (max over ranks)"}
-        e2e["frac_of_copy_ceiling"] = dt_copy / dt_e2e
+        e2e["frac_of_copy_ceiling"] = dt_copy / dt_e2e   # > 1 where host-side quantisation moved fewer bytes than the float64 arrays hold
         # plain (pageable) numpy arrays: the library stages them through its pinned ring with host threads
         xp, op = np.array(b.x_np[: min(npts, 40_000_000)]), np.empty(min(npts, 40_000_000) * nc_out)
         op = op.view(np.complex128) if nc_out == 2 else op

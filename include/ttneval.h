@@ -71,7 +71,12 @@ enum {
                          every coordinate are the bits of floor(x 2^L) (binary digits 1..L on consecutive chain
                          vertices, L <= 32: the K1 run path), PAGEABLE coordinates are QUANTISED to that L-bit grid
                          index by the staging threads on their way into the ring — 4 bytes per coordinate cross PCIe
-                         instead of 8, bit-exact (the evaluation depends on nothing else); opts->staged bit 2 reports it */
+                         instead of 8, bit-exact (the evaluation depends on nothing else); opts->staged bit 2 reports it.
+                         PINNED coordinates of such a chain (>= 2^20 points) go HYBRID when this GPU has the host to itself
+                         (a single-device plan in a process without LOCAL_WORLD_SIZE > 1): two of every three chunks are
+                         quantised by the host threads while the copy engines read the third in place (10.7 B per 2-D point
+                         over PCIe instead of 16); the environment variable TTN_HOST_QUANT overrides (0 never, 1 pageable
+                         arrays only, 2 every chunk, 3 / 4 / 5 / 6: 1 of 2, 1 of 3, 2 of 3, 3 of 4 chunks of a pinned array) */
   TTN_STAGE_OFF = 1,  /* hand every host pointer straight to cudaMemcpyAsync */
   TTN_STAGE_COPY = 2  /* like AUTO, but coordinates always travel as doubles */
 };

@@ -732,7 +732,10 @@ int build_chain_mma(ttn_plan* p, const ttn_desc* d) {
       double fm = 0.0;
       for (int gI = 0; gI < q.n_steps; ++gI) fm += (cplx ? 8.0 : 2.0) * dim_in[kmerge - 1 + gI * kmerge] * dim_out[kmerge - 1 + gI * kmerge + kmerge - 1];
       p->cmma_light_flops = fm + (cplx ? 8.0 : 2.0) * dim_in[n_steps_p - (kmerge - 1)];
-      p->cmma_light_ok = true;
+      // ... where the light image keeps up with the copies: its rate falls with rounds x width^2 (config 2: 13 x 16^2 ->
+      // 3.6 G points/s against a 3.2 G copy ceiling; the config-4 shape: 5 x 32^2 -> 2.1 G, and host-buffer calls of that
+      // shape ran at 2.0 G end to end where the deep image — two row gathers from L2-resident tables — is PCIe-bound)
+      p->cmma_light_ok = (double)q.n_rounds * CHI * CHI <= 3600.0;
     }
   }
   // both kernels keep the digit and threshold tables in static shared memory

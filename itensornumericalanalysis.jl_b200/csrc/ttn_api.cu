@@ -841,10 +841,18 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
   // copy engines directly, which is the cheapest path for the HOST memory system (16 B per point, no CPU pass): with
   // TTN_HOST_QUANT=2 they are quantised too, +8 % on one GPU (3.19 -> 3.46 G points/s, then bound by host DRAM at
   // ~140 GB/s instead of PCIe) but a loss as soon as several GPUs share that DRAM, so it is not the default.
+  // HYBRID (mode 5, the default where this GPU has the host to itself: ttn_plan::host_peers == 1): two of every three chunks
+  // of a PINNED array are quantised by the host threads while the copy engines read the third in place — 10.7 B per point
+  // over PCIe instead of 16, the host pass and the DMA sharing the host's DRAM bandwidth — and the call then runs the
+  // deep-table image (with a third less copy traffic beside it the gathers cost the copies less than the 2x faster kernel
+  // gains).  Config 2, one GPU, end to end (scripts/microbench/quant_probe.sh): doubles + light image 3.15 G points/s,
+  // 1 of 2 chunks quantised + deep image 3.76, 2 of 3: 4.03, every chunk: 3.44 (the 16 host threads then set the pace),
+  // 1 of 2 + light image 3.37 (the light kernel's 3.6 G sets it).  With several GPUs on one host the host's DRAM
+  // bandwidth is the ceiling and every extra host pass costs: mode 1.
   PackParams pp;
-  const int quant_mode = getenv("TTN_HOST_QUANT") ? atoi(getenv("TTN_HOST_QUANT")) : 1;
+  const int quant_mode = getenv("TTN_HOST_QUANT") ? atoi(getenv("TTN_HOST_QUANT")) : (p->host_peers <= 1 ? 5 : 1);
   bool quant = opts->host_staging == TTN_STAGE_AUTO && !base.grid && !digits && coords && !refine && base.layout == TTN_LAYOUT_AOS &&
-               (sp_in == SPACE_PAGEABLE || (sp_in == SPACE_ASYNC && quant_mode == 2)) && quant_mode != 0 &&
+               (sp_in == SPACE_PAGEABLE || (sp_in == SPACE_ASYNC && quant_mode >= 2)) && quant_mode != 0 &&
                kernel == TTN_KERNEL_DMMA && chain_team_applicable(p) && base.n_coords >= 1 && npts >= ((int64_t)1 << 20);
   if (quant) {
     pp.nc = base.n_coords;
@@ -855,7 +863,21 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       pp.qmax[c] = L >= 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u);
     }
   }
-  (void)pcie_bound; // quantised or not, a host-buffer call is bound by its copies / the host pass: light image
+  // which chunks are quantised: all of a pageable array; of a PINNED one all (mode 2) or a fraction — the copy engines
+  // read the other chunks in place while the host threads pack, so the call uses the PCIe link (16 B per direct point,
+  // 8 B per packed one) and the host's DRAM bandwidth (24 B against 40 B) together
+  auto quant_chunk = [&](int ci) {
+    if (!quant) return false;
+    if (sp_in == SPACE_PAGEABLE || quant_mode == 2) return true;
+    switch (quant_mode) {
+      case 3: return (ci & 1) == 1;  // 1 of 2
+      case 4: return (ci % 3) == 2;  // 1 of 3
+      case 6: return (ci & 3) != 0;  // 3 of 4
+      default: return (ci % 3) != 0; // 5: 2 of 3
+    }
+  };
+  // the image the team-sorted kernel runs: pinned arrays in a quantising mode take the deep-table image (above)
+  const bool light_image = pcie_bound && !(quant && sp_in == SPACE_ASYNC);
   bool host_bad = false;
   // the refine pass and its functionals need the values of a chunk in device memory
   const bool need_dout = out_staged || (refine && !out);
@@ -918,7 +940,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
     src.npts = m;
     src.reduce_mode = opts->reduce_sum;
     src.weights = nullptr;
-    src.pcie_bound = pcie_bound ? 1 : 0;
+    src.pcie_bound = light_image ? 1 : 0;
     if (opts->reduce_sum == TTN_REDUCE_WEIGHTED) {
       if (w_staged) opts->h2d_bytes += (int64_t)(sizeof(double) * m);
       if (sp_w == SPACE_PAGEABLE) {
@@ -963,7 +985,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       }
     } else if (base.grid) {
       src.first = base.first + first;
-    } else if (quant) {
+    } else if (quant_chunk(ci)) {
       if (st.q_cap_points < chunk) {
         if (st.h_q) cudaFreeHost(st.h_q);
         if (st.d_q) cudaFree(st.d_q);
@@ -1067,7 +1089,7 @@ static int evaluate_impl(ttn_plan* p, CoordSource base, const double* coords, vo
       if (ev[2 * ci] && ev[2 * ci + 1] && cudaEventElapsedTime(&ms, ev[2 * ci], ev[2 * ci + 1]) == cudaSuccess) total += ms;
     }
     opts->kernel_ms = total;
-    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? ((pcie_bound && p->cmma_light_ok && chain_team_applicable(p)) ? p->cmma_light_flops : p->cmma_flops_exec)
+    opts->flops_executed = ((kernel == TTN_KERNEL_DMMA && p->cmma.merged)   ? ((light_image && p->cmma_light_ok && chain_team_applicable(p)) ? p->cmma_light_flops : p->cmma_flops_exec)
                             : (kernel == TTN_KERNEL_GEMM && p->cgemm.merged) ? p->cgemm_flops_exec
                             : kernel == TTN_KERNEL_TREE ? p->tgemm_flops_exec
                             : kernel == TTN_KERNEL_TABLE ? p->ctab_flops_exec
@@ -1217,6 +1239,7 @@ static int create_single(const ttn_desc* desc, int32_t device, ttn_plan** out) {
   ttn_plan* p = new (std::nothrow) ttn_plan();
   if (!p) return fail(TTN_ERR_NOMEM, "out of host memory");
   p->device = device;
+  if (const char* lws = getenv("LOCAL_WORLD_SIZE")) p->host_peers = std::max(1, atoi(lws));
   int rc = TTN_OK;
   {
     DeviceGuard guard(device);
@@ -1306,6 +1329,7 @@ int ttn_plan_create_multi(const ttn_desc* desc, int32_t n_devices, const int32_t
       }
     }
   }
+  for (ttn_plan* r : mp->replicas) r->host_peers = std::max(r->host_peers, n_devices);
   mp->info = mp->replicas[0]->info;
   mp->info.n_devices = n_devices;
   mp->sm_count = mp->replicas[0]->sm_count;

@@ -262,6 +262,9 @@ struct ttn_plan {
   bool all_base2 = false; // every site index has dimension 2 (branch-free digit path)
   int fe_thr_len = 0; // length of the threshold table (front-end shared-memory copy)
   int v6_teams = 3;        // teams per CTA of the team-sorted kernel (TTN_MMA_V6 at ttn_plan_create; 0 = ring kernels)
+  int host_peers = 1;      // GPUs that stream through this host's memory system at the same time as far as the library can
+                           // tell: the replicas of a multi-device plan, else LOCAL_WORLD_SIZE (one process per GPU under
+                           // torchrun / mpirun wrappers that export it).  Decides the host-side quantisation default (ttn_api.cu)
   double* d_grid_out = nullptr; // grow-only scratch of the grid kernel's host-output path
   size_t grid_out_bytes = 0;
   std::vector<ttn_plan*> replicas; // non-empty: a multi-device plan (ttn_plan_create_multi); this object owns them

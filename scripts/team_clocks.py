@@ -9,11 +9,15 @@ _capi.LIB_PATH = os.path.join(ROOT, "scripts", "microbench", "libttneval_teamdbg
 import torch
 L = _capi.lib()
 npts = int(float(sys.argv[1])) if len(sys.argv) > 1 else 40_000_000
-g = t.named_comb_tree((2, 30))
-s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+base = int(sys.argv[2]) if len(sys.argv) > 2 else 2   # base 3 / 4: a 60-site MPS of one coordinate
+if base == 2:
+    g = t.named_comb_tree((2, 30))
+    s = t.continuous_siteinds(g, [[(i, j) for j in range(1, 31)] for i in (1, 2)])
+else:
+    s = t.continuous_siteinds(t.named_grid((60, 1)), base=base)
 f = t.rand_itn(s, link_space=16, rng=0, normalise=True)
 plan = f.plan()
-x = torch.rand((npts, 2), dtype=torch.float64, device="cuda:0")
+x = torch.rand((npts, 2 if base == 2 else 1), dtype=torch.float64, device="cuda:0")
 out = torch.empty(npts, dtype=torch.float64, device="cuda:0")
 buf = (C.c_ulonglong * 12)()
 plan.evaluate_device(x.data_ptr(), npts, out.data_ptr(), kernel="dmma")

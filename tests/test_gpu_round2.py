@@ -3,6 +3,7 @@ the kernels with a FUSED K1 compared as integers, pageable host buffers through 
 multi-device plans (ttn_plan_create_multi) and the refined accuracy mode.  Everything goes through the C ABI;
 the oracle (oracle/) is the checker only."""
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -391,7 +392,8 @@ def test_pageable_end_to_end_rate_close_to_pinned():
     finally:
         _unpin(pts), _unpin(out)
     print(f"e2e pageable {r_page / 1e9:.2f} G points/s, pinned {r_pin / 1e9:.2f} G points/s, ratio {r_page / r_pin:.2f}")
-    assert r_page > 0.6 * r_pin     # measured 0.70-0.78 on the 16-core GPU boxes (host memcpy bandwidth beside the DMA traffic)
+    assert r_page > 0.5 * r_pin     # measured 0.62-0.68 on the 16-core GPU boxes (host memcpy bandwidth beside the DMA traffic; 0.70-0.78
+                                    # before pinned arrays went hybrid: 3.7 G points/s against 3.15)
 
 
 def test_host_side_coordinate_quantisation():
@@ -415,8 +417,34 @@ def test_host_side_coordinate_quantisation():
     pp, outp = pts.copy(), np.empty(len(pts))
     _pin(pp), _pin(outp)
     try:
-        c, oc = plan.evaluate_host(pp, out=outp)           # pinned arrays are read by the copy engines directly
+        # pinned arrays, this GPU alone on the host (no LOCAL_WORLD_SIZE): HYBRID — every second 2 Mi-point chunk is
+        # quantised by the host threads, the copy engines read the chunks in between in place
+        c, oc = plan.evaluate_host(pp, out=outp)
+        n1 = len(pts) - (1 << 21)
+        assert oc.staged == 4 and oc.h2d_bytes == (1 << 21) * 16 + n1 * 8 and (c == a).all()
+        for mode, nbytes in (("1", pts.size * 8), ("2", pts.size * 4), ("0", pts.size * 8)):
+            os.environ["TTN_HOST_QUANT"] = mode           # 1: pinned arrays as doubles; 2: every chunk quantised; 0: never
+            try:
+                c, oc = plan.evaluate_host(pp, out=outp)
+            finally:
+                del os.environ["TTN_HOST_QUANT"]
+            assert oc.h2d_bytes == nbytes and bool(oc.staged & 4) == (mode == "2") and (c == a).all(), mode
+        os.environ["LOCAL_WORLD_SIZE"] = "8"              # several ranks share the host: a new plan moves doubles
+        try:
+            f.invalidate_plans()
+            c, oc = f.plan().evaluate_host(pp, out=outp)
+        finally:
+            del os.environ["LOCAL_WORLD_SIZE"]
+            f.invalidate_plans()
         assert oc.staged == 0 and oc.h2d_bytes == pts.size * 8 and (c == a).all()
+        plan = f.plan()
+        for where in (5, 2_500_000):                      # a chunk the kernel reads as doubles / one the host threads pack
+            keep = pp[where, 0]
+            pp[where, 0] = -1e-300
+            with pytest.raises(_capi.TTNError) as ei:
+                plan.evaluate_host(pp, out=outp)
+            assert ei.value.code == _capi.TTN_ERR_DOMAIN
+            pp[where, 0] = keep
     finally:
         _unpin(pp), _unpin(outp)
     sub = np.concatenate([np.arange(20_000), np.arange(len(pts) - 150, len(pts))])
