@@ -141,3 +141,25 @@ def test_delta_p_known_answers():
     assert ev(psi, [[x0, y0], [y0, x0], [0, 0], [0, y0]]).tolist() == [1.0, 1.0, 0.0, 0.0]
     psi = t.delta_p(s, [[x0, y0], [0.5]], [[1, 2], [2]])
     assert ev(psi, [[x0, y0]] + [[x, 0.5] for x in xs] + [[0, 0], [0, y0]]).tolist() == [1.0] * 8 + [0.0, 0.0]
+
+
+def test_inv_pow_is_julias_pow_body():
+    """float(b)^-k as Julia's `^(::Float64, ::Integer)` computes it (Base.Math.pow_body; realindexmap.jl:14,
+    complexindexmap.jl:27) — the thresholds of the greedy loop.  n == -2 is the UNCOMPENSATED inv(x) * inv(x): one ulp
+    above the correctly rounded value in bases 5 and 10 (constants from Julia >= 1.8), exact agreement in bases 3, 4, 6,
+    7; powers of two are exact; every other exponent runs the compensated loop and is correctly rounded or one ulp off."""
+    from fractions import Fraction
+    from itna_b200.indexmaps import _inv_pow
+    assert _inv_pow(5, 2) == 0.04000000000000001 and _inv_pow(10, 2) == 0.010000000000000002
+    assert 0.04000000000000001 != 0.04 and 0.010000000000000002 != 0.01
+    for b in (3, 4, 6, 7):
+        assert _inv_pow(b, 2) == float(Fraction(1, b * b)), b
+    for b in (2, 4, 8, 16):
+        for k in range(0, 40):
+            assert _inv_pow(b, k) == float(Fraction(1, b ** k))
+    for b in (3, 5, 6, 7, 10):
+        assert _inv_pow(b, 1) == 1.0 / b and _inv_pow(b, 0) == 1.0
+        for k in range(3, 40):
+            exact = Fraction(1, b ** k)
+            got = _inv_pow(b, k)
+            assert abs(Fraction(got) - exact) <= Fraction(float(exact)) * Fraction(1, 2 ** 52), (b, k)   # within one ulp
