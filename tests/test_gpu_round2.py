@@ -392,8 +392,10 @@ def test_pageable_end_to_end_rate_close_to_pinned():
     finally:
         _unpin(pts), _unpin(out)
     print(f"e2e pageable {r_page / 1e9:.2f} G points/s, pinned {r_pin / 1e9:.2f} G points/s, ratio {r_page / r_pin:.2f}")
-    assert r_page > 0.5 * r_pin     # measured 0.62-0.68 on the 16-core GPU boxes (host memcpy bandwidth beside the DMA traffic; 0.70-0.78
-                                    # before pinned arrays went hybrid: 3.7 G points/s against 3.15)
+    # measured 0.55-0.75 on the 16-core GPU boxes (both rates move with what else the host threads are doing: pageable
+    # 2.1-3.0 G points/s, pinned hybrid 3.4-4.0; 0.70-0.78 before pinned arrays went hybrid).  A collapsed pipeline —
+    # the driver staging pageable memory on one thread — would sit near 0.15.
+    assert r_page > 0.4 * r_pin
 
 
 def test_host_side_coordinate_quantisation():
