@@ -59,6 +59,23 @@ __device__ __forceinline__ Digit4 make_digit4(const DigitTable& dg, int i) {
   d4.wv = ((uint32_t)e.base << 24) | ((uint32_t)e.site << 16) | ((uint32_t)e.word << 8);
   return d4;
 }
+// One step of the loop for one point in the team-sorted kernel (few warps per SM: K1 is a LATENCY chain there): the chosen
+// value v, x updated.  Base 2 / 3: both candidate residuals are formed beside the compares (x - t_v is only USED for the
+// chosen v, so it is the loop's own __dsub_rn) — one FP64 operation and two selects per digit instead of compare -> select
+// -> subtract: 40-site base-3 chain 4.1 -> 5.0 G points/s.  Base 4 keeps select-then-subtract (a third speculative
+// subtraction costs the FP64 pipe more than the shorter chain gains), and so does the table kernel (k1_digit4 below), whose
+// many resident warps make K1 a THROUGHPUT matter: there the speculative form measured 19-30 % slower.
+__device__ __forceinline__ uint32_t digit4_step(double& x, const Digit4& e, bool base4) {
+  const bool g1 = x >= e.t1, g2 = x >= e.t2;
+  if (base4) { // warp-uniform
+    const bool g3 = x >= e.t3;
+    x = __dsub_rn(x, g3 ? e.t3 : (g2 ? e.t2 : (g1 ? e.t1 : 0.0)));
+    return (uint32_t)g1 + (uint32_t)g2 + (uint32_t)g3;
+  }
+  const double x1 = __dsub_rn(x, e.t1), x2 = __dsub_rn(x, e.t2);
+  x = g2 ? x2 : (g1 ? x1 : x); // no threshold reached: x - thr[0] = x - 0 = x
+  return (uint32_t)g1 + (uint32_t)g2;
+}
 template <int NP>
 __device__ __forceinline__ void k1_digit4(const Digit4 e, const DigitTable& dg, const CoordSource& src, int64_t p0, int64_t step,
                                           double (&x)[NP], uint64_t (&w0)[NP], uint64_t (&w1)[NP], int* err) {
@@ -76,6 +93,42 @@ __device__ __forceinline__ void k1_digit4(const Digit4 e, const DigitTable& dg, 
     }
     stream_add128(w0[k], w1[k], (uint64_t)(v * stride), sh, hi);
   }
+}
+// The entries [e0, e1) of one coordinate for NP points: digits that land in the same stream field (a radix-3 group field
+// holds up to 12 of them, each adding v * 3^i) are summed in a 32-bit register and inserted into the 128-bit stream once
+// per field instead of once per digit.  (Partial sums of a field whose digits belong to several coordinates are simply
+// added one after the other.)
+template <int NP>
+__device__ __forceinline__ void k1_digit4_run(const Digit4* s_d4, int e0, int e1, const DigitTable& dg, const CoordSource& src,
+                                              int64_t p0, int64_t step, double (&x)[NP], uint64_t (&w0)[NP], uint64_t (&w1)[NP],
+                                              int* err) {
+  if (e0 >= e1) return;
+  uint32_t acc[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) acc[k] = 0u;
+  uint32_t cur = (s_d4[e0].sh & 0xffu) | (s_d4[e0].wv & 0xff00u); // (shift, word) of the open field
+  for (int e_i = e0; e_i < e1; ++e_i) {
+    const Digit4 e = s_d4[e_i];
+    const uint32_t pos = (e.sh & 0xffu) | (e.wv & 0xff00u);
+    if (pos != cur) {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        stream_add128(w0[k], w1[k], (uint64_t)acc[k], cur & 0xffu, (cur >> 8) != 0u);
+        acc[k] = 0u;
+      }
+      cur = pos;
+    }
+    const uint32_t stride = e.sh >> 8;
+    const bool base4 = (e.wv >> 24) > 3u;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const uint32_t v = src.digits ? (uint32_t)given_digit(src, p0 + k * step, dg.n_sites, (int)((e.wv >> 16) & 0xffu), (int)(e.wv >> 24), err)
+                                    : digit4_step(x[k], e, base4);
+      acc[k] += v * stride;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) stream_add128(w0[k], w1[k], (uint64_t)acc[k], cur & 0xffu, (cur >> 8) != 0u);
 }
 
 constexpr int kFeMaxSites = 160; // static shared-memory copies of the digit tables (within the 12 KB the

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1)
           }
         }
       } else if (ch.k1_generic == 1) {
-        for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_digit4<PPL>(s_d4[e_i], dg, src, p0 + lane, 32, x, w0, w1, err);
+        k1_digit4_run<PPL>(s_d4, s_cptr[c], s_cptr[c + 1], dg, src, p0 + lane, 32, x, w0, w1, err);
       } else if (ch.k1_generic) {
         for (int e_i = s_cptr[c]; e_i < s_cptr[c + 1]; ++e_i) k1_generic_site<PPL>(dg, src, e_i, p0 + lane, 32, x, w0, w1, err);
       } else {
