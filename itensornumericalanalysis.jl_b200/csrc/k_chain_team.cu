@@ -12,6 +12,9 @@ namespace ttn {
 // NCLS = 4, 8 or 16 slices per position).  A CTA holds NTEAM independent teams of 4 warps; a team
 // owns a tile of 512 points.
 //  * every warp is "home" to 128 points of the tile: K1, leaf rows, class counts, root;
+//    with deep leaf / root tables (k_chain_mma.cu) the table rows are gathered cooperatively — CHI / 2 lanes per 128-byte
+//    row: leaf rows by cp.async straight into the state tile, root rows chunk by chunk with a reduce-scatter over the
+//    lanes of a row — 1 L1 wavefront per row instead of 4 (DESIGN.md "Cooperative gathers");
 //  * per round the team counting-sorts its 512 points by class: per-warp match.any counts, one
 //    word of 4 byte counters per class in shared memory, ONE team barrier per round (the counts of
 //    round r+1 are published before the barrier of round r);
